@@ -1,0 +1,102 @@
+"""ctypes binding of ``libgnndelete_b200.so`` (C ABI in ``include/gnndelete_b200.h``).
+
+There is deliberately no fallback: if the library is missing, or a tensor handed
+to a kernel is not a contiguous CUDA tensor of the expected dtype, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libgnndelete_b200.so')
+
+_vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+
+
+class CsrStruct(C.Structure):
+    """``gd_csr_t``"""
+    _fields_ = [
+        ('num_rows', _i64), ('nnz', _i64), ('rowptr', _vp), ('col', _vp),
+        ('seg_len', _i32), ('num_heavy', _i32), ('num_seg', _i32),
+        ('heavy_row', _vp), ('heavy_seg_beg', _vp), ('heavy_nseg', _vp),
+        ('seg_row', _vp), ('seg_beg', _vp),
+    ]
+
+
+_csr_p = C.POINTER(CsrStruct)
+
+# name -> (restype, argtypes); must list every symbol the header declares
+SIGNATURES = {
+    'gd_version': (C.c_int, []),
+    'gd_last_error': (C.c_char_p, []),
+    'gd_csr_workspace_bytes': (_sz, [_i64, _i64]),
+    'gd_csr_from_coo': (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'gd_invert_perm': (C.c_int, [_vp, _i64, _vp, _vp]),
+    'gd_gcn_dinv': (C.c_int, [_vp, _i64, _vp, _vp]),
+    'gd_spmm_plan_build': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'gd_spmm': (C.c_int, [_csr_p, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _vp]),
+    'gd_gemm_rows': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
+    'gd_gemm_tn_workspace_bytes': (_sz, [_i64, _i32, _i32]),
+    'gd_gemm_tn_rows': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    'gd_copy_rows': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
+    'gd_relu_fwd': (C.c_int, [_vp, _i64, _vp, _vp]),
+    'gd_relu_bwd': (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    'gd_edge_loss_workspace_bytes': (_sz, [_i64]),
+    'gd_edge_loss_fwd': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'gd_pair_decode': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    'gd_adam_step': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare every signature."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            '(nvcc, sm_100a). gnndelete_b200 has no CPU or PyTorch fallback for its kernels.')
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().gd_last_error().decode()
+
+
+def call(name: str, *args):
+    """Invoke an ``int``-returning entry point; raise with ``gd_last_error`` on failure."""
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise RuntimeError(f'{name} failed ({rc}): {last_error()}')
+
+
+_DTYPES = {'f32': torch.float32, 'i32': torch.int32, 'i64': torch.int64, 'u8': torch.uint8}
+
+
+def ptr(t, kind=None):
+    """Device pointer of a contiguous CUDA tensor (``None`` -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError('gnndelete_b200 kernels take CUDA tensors only (no CPU fallback)')
+    if not t.is_contiguous():
+        raise RuntimeError('non-contiguous tensor passed to a gnndelete_b200 kernel')
+    if kind is not None and t.dtype != _DTYPES[kind]:
+        raise RuntimeError(f'expected {kind} tensor, got {t.dtype}')
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,14 @@
+// Error reporting and version of the C ABI.
+#include "common.cuh"
+
+namespace gd {
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+}  // namespace gd
+
+extern "C" int gd_version(void) { return 100; /* 0.1.0 */ }
+extern "C" const char* gd_last_error(void) { return gd::g_last_error.c_str(); }

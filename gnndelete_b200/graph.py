@@ -1,0 +1,190 @@
+"""Device-side graph structures behind the conv layers: destination-major CSR, its
+transpose for the backward pass, GCN normalisation and the long-row split plan.
+
+The reference rebuilds the equivalent state inside every PyG conv call
+(``gcn_norm`` with ``cached=False``, ``add_remaining_self_loops``; gcn.py:11-12).
+The edge set of an unlearning run is fixed (``train_pos_edge_index[:, sdf_mask]``,
+gnndelete.py:215), so the structures are built once by the CUDA builders in
+``csrc/graph_build.cu`` and cached.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+SEG_LEN = 64     # rows longer than this are split into segments (spmm.cu)
+
+
+class CSR:
+    """Destination-major CSR on the device + the ``gd_csr_t`` the kernels take."""
+
+    def __init__(self, rowptr, col, eid, rel, num_rows, nnz, plan=None):
+        self.rowptr, self.col, self.eid, self.rel = rowptr, col, eid, rel
+        self.num_rows, self.nnz = int(num_rows), int(nnz)
+        self.plan = plan or {}
+        self._scratch = {}
+        s = L.CsrStruct()
+        s.num_rows, s.nnz = self.num_rows, self.nnz
+        s.rowptr, s.col = rowptr.data_ptr(), col.data_ptr()
+        if plan:
+            s.seg_len, s.num_heavy, s.num_seg = plan['seg_len'], plan['num_heavy'], plan['num_seg']
+            for k in ('heavy_row', 'heavy_seg_beg', 'heavy_nseg', 'seg_row', 'seg_beg'):
+                setattr(s, k, plan[k].data_ptr())
+        self.struct = s
+        self.ref = C.byref(s)
+
+    @property
+    def num_seg(self):
+        return self.plan.get('num_seg', 0)
+
+    def scratch(self, feat):
+        """Per-width scratch for the split-row partial sums (allocated once)."""
+        if self.num_seg == 0:
+            return None
+        buf = self._scratch.get(feat)
+        if buf is None:
+            buf = torch.empty(self.num_seg * feat, dtype=torch.float32, device=self.rowptr.device)
+            self._scratch[feat] = buf
+        return buf
+
+
+def build_csr(src, dst, num_nodes, self_loops=False, rel=None, num_rel=1, seg_len=SEG_LEN):
+    """COO (int64, ``src -> dst``) -> :class:`CSR` via ``gd_csr_from_coo`` +
+    ``gd_spmm_plan_build``.  Raises on out-of-range endpoints."""
+    dev = src.device
+    src = src.contiguous()
+    dst = dst.contiguous()
+    E, N = src.numel(), int(num_nodes)
+    cap = E + (N if self_loops else 0)
+    rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    eid = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    rel_out = torch.empty(max(cap, 1), dtype=torch.int32, device=dev) if rel is not None else None
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    ws_bytes = L.load().gd_csr_workspace_bytes(E, N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    L.call('gd_csr_from_coo', L.ptr(src, 'i64'), L.ptr(dst, 'i64'),
+           L.ptr(rel.contiguous(), 'i64') if rel is not None else None,
+           E, N, int(num_rel), int(bool(self_loops)), L.ptr(rowptr), L.ptr(col), L.ptr(eid),
+           L.ptr(rel_out), L.ptr(status), L.ptr(ws), ws_bytes, L.stream())
+    nnz, bad = status.tolist()
+    if bad:
+        raise ValueError(f'edge_index holds {bad} endpoints / relation ids outside [0, {N})')
+    del ws
+    col, eid = col[:nnz], eid[:nnz]
+    if rel_out is not None:
+        rel_out = rel_out[:nnz]
+    plan = None
+    if seg_len and nnz > 0:
+        hcap, scap = nnz // seg_len + 1, 2 * nnz // seg_len + 2
+        bufs = {k: torch.empty(hcap if k.startswith('heavy') else scap, dtype=torch.int32, device=dev)
+                for k in ('heavy_row', 'heavy_seg_beg', 'heavy_nseg', 'seg_row', 'seg_beg')}
+        counts = torch.zeros(2, dtype=torch.int32, device=dev)
+        L.call('gd_spmm_plan_build', L.ptr(rowptr), N, int(seg_len), L.ptr(bufs['heavy_row']),
+               L.ptr(bufs['heavy_seg_beg']), L.ptr(bufs['heavy_nseg']), L.ptr(bufs['seg_row']),
+               L.ptr(bufs['seg_beg']), L.ptr(counts), L.stream())
+        nh, ns = counts.tolist()
+        if nh > 0:
+            plan = dict(seg_len=int(seg_len), num_heavy=nh, num_seg=ns, **bufs)
+    return CSR(rowptr, col, eid, rel_out, N, nnz, plan)
+
+
+def invert_perm(perm, n_out):
+    inv = torch.empty(n_out, dtype=torch.int32, device=perm.device)
+    L.call('gd_invert_perm', L.ptr(perm, 'i32'), perm.numel(), L.ptr(inv), L.stream())
+    return inv
+
+
+class GraphPlan:
+    """Everything a conv layer needs for one fixed edge set.
+
+    ``fwd``: CSR over destinations (messages j -> i).  ``bwd``: CSR of the transposed
+    edge set for the gradient w.r.t. the source features (shared with ``fwd`` when the
+    edge set is symmetric, which ``to_undirected`` guarantees on the reference's data,
+    delete_gnn.py:175-182).  ``dinv``: GCN ``deg^-1/2`` (self loops included)."""
+
+    def __init__(self, edge_index, num_nodes, self_loops, edge_type=None, num_rel=1, gcn_norm=False,
+                 need_bwd=True):
+        src, dst = edge_index[0], edge_index[1]
+        self.num_nodes = int(num_nodes)
+        self.self_loops = bool(self_loops)
+        self.fwd = build_csr(src, dst, num_nodes, self_loops, edge_type, num_rel)
+        self.bwd = None
+        self.symmetric = False
+        if need_bwd:
+            bwd = build_csr(dst, src, num_nodes, self_loops, edge_type, num_rel)
+            if edge_type is None and bwd.nnz == self.fwd.nnz and torch.equal(bwd.rowptr, self.fwd.rowptr) \
+                    and torch.equal(bwd.col, self.fwd.col):
+                self.symmetric = True
+                self.bwd = self.fwd
+            else:
+                self.bwd = bwd
+        self.dinv = None
+        if gcn_norm:
+            self.dinv = torch.empty(self.num_nodes, dtype=torch.float32, device=src.device)
+            L.call('gd_gcn_dinv', L.ptr(self.fwd.rowptr), self.num_nodes, L.ptr(self.dinv), L.stream())
+
+
+class PlanCache:
+    """Two-level cache: tensor identity ``(data_ptr, shape, version)`` first, then a
+    content check against the cached copy, so that callers which re-materialise the
+    same edge set every epoch (``edge_index[:, sdf_mask]``, gnndelete.py:215) do not
+    trigger a rebuild."""
+
+    def __init__(self, max_entries=8):
+        self.max_entries = max_entries
+        self._by_id = {}
+        self._entries = []      # (edge_index_copy, edge_type_copy, key, plan)
+
+    @staticmethod
+    def _ident(t):
+        return None if t is None else (t.data_ptr(), tuple(t.shape), t._version, str(t.device))
+
+    def get(self, edge_index, edge_type, key, builder):
+        ident = (self._ident(edge_index), self._ident(edge_type), key)
+        hit = self._by_id.get(ident)
+        if hit is not None:
+            return hit
+        for ei, et, k, plan in self._entries:
+            if k == key and ei.shape == edge_index.shape and ei.device == edge_index.device \
+                    and torch.equal(ei, edge_index) and (et is None or torch.equal(et, edge_type)):
+                self._by_id[ident] = plan
+                return plan
+        plan = builder()
+        self._entries.append((edge_index.clone(), None if edge_type is None else edge_type.clone(), key, plan))
+        if len(self._entries) > self.max_entries:
+            self._entries.pop(0)
+            self._by_id.clear()
+        if len(self._by_id) > 64:
+            self._by_id.clear()
+        self._by_id[ident] = plan
+        return plan
+
+
+_GLOBAL_CACHE = PlanCache()
+
+
+def plan_for(edge_index, num_nodes, kind, edge_type=None, num_rel=1):
+    """``kind``: 'gcn' (self loops + D^-1/2), 'gat' (self loops), 'gin' / 'rgcn' (as is)."""
+    self_loops = kind in ('gcn', 'gat')
+    key = (kind, int(num_nodes), int(num_rel))
+    return _GLOBAL_CACHE.get(
+        edge_index, edge_type, key,
+        lambda: GraphPlan(edge_index, num_nodes, self_loops, edge_type, num_rel, gcn_norm=(kind == 'gcn')))
+
+
+def rows_of(mask, num_nodes=None):
+    """``(rows, complement)`` int32 index lists of a DeletionLayer mask.  The reference
+    indexes with the mask directly (``new_rep[mask]``, deletion.py:25), so a bool
+    ``[N]`` mask or an integer index tensor are both accepted."""
+    if mask.dtype == torch.bool:
+        rows = mask.nonzero().squeeze(1).to(torch.int32)
+        comp = (~mask).nonzero().squeeze(1).to(torch.int32)
+        return rows, comp
+    n = int(num_nodes)
+    flag = torch.ones(n, dtype=torch.bool, device=mask.device)
+    flag[mask.long()] = False
+    return mask.to(torch.int32).contiguous(), flag.nonzero().squeeze(1).to(torch.int32)

@@ -1,0 +1,176 @@
+"""Conv layers, two-layer encoders, DeletionLayer and the ``*Delete`` models on the CUDA
+kernels.  Class names, constructor / forward / decode signatures, attribute names and
+state-dict keys mirror the reference (``framework/models/{gcn,gat,gin,rgcn,deletion}.py``
+and the PyG layers it instantiates) so checkpoints and callers are interchangeable
+(SURVEY.md §8(b)); ``framework/`` at the repo root re-exports these under the
+reference's import paths.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .graph import plan_for, rows_of
+from .losses import PairPlan
+
+
+def _glorot_(t):
+    a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+    with torch.no_grad():
+        return t.uniform_(-a, a)
+
+
+class _Weight(nn.Module):
+    """Stands in for PyG's ``Linear(bias=False)`` so the key is ``<name>.weight``."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.weight = nn.Parameter(_glorot_(torch.empty(out_channels, in_channels)))
+
+
+def _p(t, frozen):
+    return t.detach() if frozen else t
+
+
+# ------------------------------------------------------------------------- convs
+class GCNConv(nn.Module):
+    """PyG ``GCNConv(in, out)`` defaults (gcn.py:11-12): ``A_hat (x W^T) + b`` with
+    ``A_hat = D^-1/2 (A + I) D^-1/2``.  The ``D^-1/2`` on the source side is applied in
+    the GEMM epilogue and the one on the destination side in the SpMM epilogue, so the
+    aggregation reads no per-edge weight."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin = _Weight(in_channels, out_channels)
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+
+    def forward(self, x, edge_index, relu_in=False, frozen=False, plan=None):
+        plan = plan or plan_for(edge_index, x.size(0), 'gcn')
+        h = ops.LinearFn.apply(x, _p(self.lin.weight, frozen), None, plan.dinv, relu_in)
+        return ops.SpMMFn.apply(h, _p(self.bias, frozen), plan, None, plan.dinv, 0.0)
+
+
+class GINConv(nn.Module):
+    """PyG ``GINConv(nn.Linear(in, out))``, ``eps = 0`` buffer (gin.py:11-12):
+    ``Linear(sum_j x_j + (1 + eps) x_i)`` — aggregation at the INPUT width."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.nn = nn.Linear(in_channels, out_channels)
+        self.register_buffer('eps', torch.tensor([0.0]))
+        self._eps_host = 0.0
+
+    def forward(self, x, edge_index, relu_in=False, frozen=False, plan=None):
+        plan = plan or plan_for(edge_index, x.size(0), 'gin')
+        if relu_in:
+            x = ops.ReLUFn.apply(x)
+        agg = ops.SpMMFn.apply(x, None, plan, None, None, 1.0 + self._eps_host)
+        return ops.LinearFn.apply(agg, _p(self.nn.weight, frozen), _p(self.nn.bias, frozen), None, False)
+
+    def _load_from_state_dict(self, state_dict, prefix, *a, **kw):
+        super()._load_from_state_dict(state_dict, prefix, *a, **kw)
+        self._eps_host = float(self.eps.detach().cpu().reshape(-1)[0])
+
+
+# -------------------------------------------------------------------- encoders
+class _Encoder(nn.Module):
+    """conv1 -> ReLU -> conv2, no dropout (gcn.py:15-24).  The ReLU is folded into the
+    consumer of conv1's output instead of being materialised."""
+    conv_cls = None
+
+    def __init__(self, args, **kwargs):
+        super().__init__()
+        self.conv1 = self.conv_cls(args.in_dim, args.hidden_dim)
+        self.conv2 = self.conv_cls(args.hidden_dim, args.out_dim)
+
+    def forward(self, x, edge_index, return_all_emb=False):
+        x1 = self.conv1(x, edge_index)
+        x2 = self.conv2(x1, edge_index, relu_in=True)
+        if return_all_emb:
+            return x1, x2
+        return x2
+
+    def decode(self, z, pos_edge_index, neg_edge_index=None):
+        """``<z_u, z_v>`` for ``cat(pos, neg)``, positives first (gcn.py:26-35)."""
+        ei = pos_edge_index if neg_edge_index is None else torch.cat([pos_edge_index, neg_edge_index], dim=-1)
+        pairs = PairPlan(ei[0], ei[1], z.size(0))
+        return ops.PairDecodeFn.apply(z, pairs)
+
+
+class GCN(_Encoder):
+    conv_cls = GCNConv
+
+
+class GIN(_Encoder):
+    conv_cls = GINConv
+
+
+# ------------------------------------------------------------------- Del operator
+class DeletionLayer(nn.Module):
+    """``framework/models/deletion.py:8-29``: rows selected by ``mask`` are multiplied by
+    the trainable ``deletion_weight`` (init ``ones / 1000``), the rest pass through; a
+    new tensor is returned.  ``mask=None`` falls back to the constructor mask, both
+    ``None`` is the identity."""
+
+    def __init__(self, dim, mask):
+        super().__init__()
+        self.dim = dim
+        self.mask = mask
+        self.deletion_weight = nn.Parameter(torch.ones(dim, dim) / 1000)
+        self._rows_cache = {}
+
+    def rows(self, mask, num_nodes, device):
+        key = (mask.data_ptr(), tuple(mask.shape), mask._version, str(device))
+        hit = self._rows_cache.get(key)
+        if hit is None:
+            if len(self._rows_cache) > 8:
+                self._rows_cache.clear()
+            hit = rows_of(mask.to(device), num_nodes)
+            self._rows_cache[key] = hit
+        return hit
+
+    def forward(self, x, mask=None):
+        if mask is None:
+            mask = self.mask
+        if mask is None:
+            return x
+        rows, comp = self.rows(mask, x.size(0), x.device)
+        return ops.DeletionFn.apply(x, self.deletion_weight, rows, comp)
+
+
+def _make_delete(base):
+    class _Delete(base):
+        """``deletion.py:52-133``: the base encoder with a Del operator after each conv.
+        The conv weights are frozen by the optimizer's parameter filter in the reference
+        (``delete_gnn.py:229-233``); here their gradients are simply never computed."""
+
+        def __init__(self, args, mask_1hop=None, mask_2hop=None, **kwargs):
+            super().__init__(args)
+            self.deletion1 = DeletionLayer(args.hidden_dim, mask_1hop)
+            self.deletion2 = DeletionLayer(args.out_dim, mask_2hop)
+            self.conv1.requires_grad = False      # kept for attribute parity (a no-op upstream too)
+            self.conv2.requires_grad = False
+
+        def forward(self, x, edge_index, mask_1hop=None, mask_2hop=None, return_all_emb=False):
+            with torch.no_grad():
+                x1 = self.conv1(x, edge_index, frozen=True)
+            x1 = self.deletion1(x1, mask_1hop)
+            x2 = self.conv2(x1, edge_index, relu_in=True, frozen=True)
+            x2 = self.deletion2(x2, mask_2hop)
+            if return_all_emb:
+                return x1, x2
+            return x2
+
+        def get_original_embeddings(self, x, edge_index, return_all_emb=False):
+            return base.forward(self, x, edge_index, return_all_emb)
+
+    _Delete.__name__ = _Delete.__qualname__ = base.__name__ + 'Delete'
+    return _Delete
+
+
+GCNDelete = _make_delete(GCN)
+GINDelete = _make_delete(GIN)

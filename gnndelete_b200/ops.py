@@ -1,0 +1,219 @@
+"""Functional wrappers (raw kernels) and ``torch.autograd.Function``s over the C ABI.
+
+The raw wrappers (``spmm``, ``gemm_rows`` …) write into caller-provided or freshly
+allocated CUDA tensors and are what the fused epoch engine (``engine.py``) calls; the
+autograd Functions make the drop-in modules differentiable for arbitrary user losses.
+Gradients nobody can consume on the Del path (frozen conv weights) are only computed
+when the corresponding input ``requires_grad``.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+from .graph import CSR
+
+
+def _f32(t):
+    if t.dtype != torch.float32:
+        raise RuntimeError(f'gnndelete_b200 kernels compute in fp32; got {t.dtype}')
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------ raw kernels
+def spmm(csr: CSR, x, out=None, val=None, col_scale=None, row_scale=None, self_coef=0.0, bias=None):
+    x = _f32(x)
+    n, f = csr.num_rows, x.shape[1]
+    if out is None:
+        out = torch.empty(n, f, dtype=torch.float32, device=x.device)
+    L.call('gd_spmm', csr.ref, L.ptr(val), L.ptr(col_scale), L.ptr(row_scale), L.ptr(x), x.stride(0), f,
+           float(self_coef), L.ptr(bias), L.ptr(out), out.stride(0), L.ptr(csr.scratch(f)), L.stream())
+    return out
+
+
+def gemm_rows(a, b, b_is_nk, out=None, rows=None, bias=None, out_scale=None, gate=None,
+              relu_in=False, relu_out=False):
+    """out[r,:] = epi(pro(a[r,:]) . B) over all rows or the ``rows`` list (in place in ``out``)."""
+    a = _f32(a)
+    b = _f32(b)
+    k = a.shape[1]
+    n = b.shape[0] if b_is_nk else b.shape[1]
+    assert (b.shape[1] if b_is_nk else b.shape[0]) == k, 'inner dimensions differ'
+    m = a.shape[0] if rows is None else rows.numel()
+    if out is None:
+        out = torch.empty(a.shape[0], n, dtype=torch.float32, device=a.device)
+    L.call('gd_gemm_rows', L.ptr(a), a.stride(0), L.ptr(rows), m, k, L.ptr(b), int(b_is_nk), n,
+           L.ptr(bias), L.ptr(out_scale), L.ptr(gate), gate.stride(0) if gate is not None else 0,
+           int(relu_in), int(relu_out), L.ptr(out), out.stride(0), L.stream())
+    return out
+
+
+_tn_ws = {}
+
+
+def gemm_tn_rows(a, g, rows=None, relu_a=False, a_scale=None, out=None):
+    """c[k1,n2] = sum_r a_scale[r] * a[r,:]^T (x) g[r,:] over all rows or the ``rows`` list."""
+    a = _f32(a)
+    g = _f32(g)
+    k1, n2 = a.shape[1], g.shape[1]
+    m = a.shape[0] if rows is None else rows.numel()
+    if out is None:
+        out = torch.empty(k1, n2, dtype=torch.float32, device=a.device)
+    nbytes = L.load().gd_gemm_tn_workspace_bytes(m, k1, n2)
+    key = (a.device, nbytes)
+    ws = _tn_ws.get(key)
+    if ws is None:
+        ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=a.device)
+        _tn_ws[key] = ws
+    L.call('gd_gemm_tn_rows', L.ptr(a), a.stride(0), L.ptr(g), g.stride(0), L.ptr(rows), m, k1, n2,
+           int(relu_a), L.ptr(a_scale), L.ptr(out), L.ptr(ws), nbytes, L.stream())
+    return out
+
+
+def copy_rows(src, dst, rows):
+    L.call('gd_copy_rows', L.ptr(src), src.stride(0), L.ptr(rows), rows.numel(), src.shape[1],
+           L.ptr(dst), dst.stride(0), L.stream())
+    return dst
+
+
+def relu_fwd(x, out=None):
+    x = _f32(x)
+    if out is None:
+        out = torch.empty_like(x)
+    L.call('gd_relu_fwd', L.ptr(x), x.numel(), L.ptr(out), L.stream())
+    return out
+
+
+def relu_bwd(grad, pre, out=None):
+    grad = _f32(grad)
+    if out is None:
+        out = torch.empty_like(grad)
+    L.call('gd_relu_bwd', L.ptr(grad), L.ptr(pre), grad.numel(), L.ptr(out), L.stream())
+    return out
+
+
+def pair_decode(z, pu, pv, rel_weight=None, pair_rel=None):
+    z = _f32(z)
+    out = torch.empty(pu.numel(), dtype=torch.float32, device=z.device)
+    L.call('gd_pair_decode', L.ptr(z), z.stride(0), z.shape[1], L.ptr(pu, 'i32'), L.ptr(pv, 'i32'),
+           pu.numel(), L.ptr(rel_weight), L.ptr(pair_rel), L.ptr(out), L.stream())
+    return out
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    L.call('gd_adam_step', L.ptr(param), L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), L.ptr(step),
+           param.numel(), float(lr), float(beta1), float(beta2), float(eps), L.stream())
+
+
+# ------------------------------------------------------------- autograd Functions
+class SpMMFn(torch.autograd.Function):
+    """out = R A C x + self_coef x + bias  (R/C: optional diagonal row/col scales)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, plan, col_scale, row_scale, self_coef):
+        ctx.plan, ctx.col_scale, ctx.row_scale, ctx.self_coef = plan, col_scale, row_scale, self_coef
+        ctx.has_bias = bias is not None
+        return spmm(plan.fwd, x, col_scale=col_scale, row_scale=row_scale, self_coef=self_coef,
+                    bias=None if bias is None else bias.detach())
+
+    @staticmethod
+    def backward(ctx, gout):
+        gout = gout.contiguous()
+        gx = gb = None
+        if ctx.needs_input_grad[0]:
+            # (R A C)^T = C A^T R
+            gx = spmm(ctx.plan.bwd, gout, col_scale=ctx.row_scale, row_scale=ctx.col_scale,
+                      self_coef=ctx.self_coef)
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            gb = gout.sum(0)
+        return gx, gb, None, None, None, None
+
+
+class LinearFn(torch.autograd.Function):
+    """out = (relu?(x) W^T + b) * out_scale   with W = nn.Linear weight [out, in]."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, out_scale, relu_in):
+        ctx.save_for_backward(x, weight)
+        ctx.out_scale, ctx.relu_in, ctx.has_bias = out_scale, relu_in, bias is not None
+        return gemm_rows(x, weight.detach(), True, bias=None if bias is None else bias.detach(),
+                         out_scale=out_scale, relu_in=relu_in)
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, weight = ctx.saved_tensors
+        gout = gout.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            # gx = (gout * s) W, gated by relu'(x)
+            gx = gemm_rows(gout, weight.detach(), False, out_scale=ctx.out_scale,
+                           gate=x if ctx.relu_in else None)
+        if ctx.needs_input_grad[1]:
+            # gw[o, i] = sum_r s_r gout[r, o] relu?(x)[r, i]
+            gw = gemm_tn_rows(gout, x, a_scale=ctx.out_scale) if not ctx.relu_in else \
+                gemm_tn_rows(x, gout, relu_a=True, a_scale=ctx.out_scale).t().contiguous()
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = (gout * ctx.out_scale.view(-1, 1)).sum(0) if ctx.out_scale is not None else gout.sum(0)
+        return gx, gw, gb, None, None
+
+
+class ReLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32(x)
+        ctx.save_for_backward(x)
+        return relu_fwd(x)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (x,) = ctx.saved_tensors
+        return relu_bwd(gout.contiguous(), x)
+
+
+class DeletionFn(torch.autograd.Function):
+    """y = x.clone(); y[rows] = x[rows] @ W   (framework/models/deletion.py:24-25) without
+    materialising the clone-then-overwrite: masked rows come out of the gathered-row GEMM,
+    the complement is copied."""
+
+    @staticmethod
+    def forward(ctx, x, weight, rows, comp):
+        x = _f32(x)
+        ctx.save_for_backward(x, weight)
+        ctx.rows, ctx.comp = rows, comp
+        out = torch.empty_like(x)
+        gemm_rows(x, weight.detach(), False, out=out, rows=rows)
+        copy_rows(x, out, comp)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, weight = ctx.saved_tensors
+        gout = gout.contiguous()
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(gout)
+            gemm_rows(gout, weight.detach(), True, out=gx, rows=ctx.rows)     # gout[rows] @ W^T
+            copy_rows(gout, gx, ctx.comp)
+        if ctx.needs_input_grad[1]:
+            gw = gemm_tn_rows(x, gout, rows=ctx.rows)                           # x[rows]^T gout[rows]
+        return gx, gw, None, None
+
+
+class PairDecodeFn(torch.autograd.Function):
+    """logits[p] = sum_d z[u_p,d] w[t_p,d] z[v_p,d]; differentiable w.r.t. z through the
+    incidence CSR of the pair list (deterministic gather, no atomics)."""
+
+    @staticmethod
+    def forward(ctx, z, pairs):
+        ctx.pairs = pairs
+        ctx.save_for_backward(z)
+        return pair_decode(z, pairs.pu, pairs.pv, pairs.rel_weight, pairs.pair_rel)
+
+    @staticmethod
+    def backward(ctx, glogits):
+        (z,) = ctx.saved_tensors
+        pairs = ctx.pairs
+        if pairs.rel_weight is not None:
+            raise NotImplementedError('DistMult decode backward is not on the unlearning hot path')
+        val = glogits.contiguous()[pairs.inc_pair.long()]
+        return spmm(pairs.inc, z, val=val), None

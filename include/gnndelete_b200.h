@@ -1,0 +1,177 @@
+/*
+ * libgnndelete_b200.so — C ABI of the B200 (sm_100a) kernels behind GNNDelete's
+ * unlearning hot path.
+ *
+ * The reference (mims-harvard/GNNDelete) has no FFI boundary of its own: its hot
+ * path is Python that calls PyTorch-Geometric operators.  Each
+ * entry point below therefore cites the reference call site / PyG operator whose
+ * arithmetic it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - all buffers (inputs, outputs, workspaces) are owned by the caller;
+ *   - feature matrices are row-major fp32 with an explicit leading dimension;
+ *   - node / edge ids are int32 inside the library; the COO builders take the
+ *     reference's int64 `edge_index` rows;
+ *   - every call is asynchronous on `stream` (a cudaStream_t) and re-entrant;
+ *   - return 0 on success, negative on error; `gd_last_error()` gives the text of
+ *     the calling thread's last failure.
+ */
+#ifndef GNNDELETE_B200_H
+#define GNNDELETE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gd_stream_t; /* cudaStream_t */
+
+#define GD_OK 0
+#define GD_ERR_INVALID (-1)
+#define GD_ERR_CUDA (-2)
+#define GD_ERR_WORKSPACE (-3)
+
+int gd_version(void);
+const char* gd_last_error(void);
+
+/* ------------------------------------------------------------------ graph build
+ * Replaces the per-call index plumbing of torch_geometric MessagePassing
+ * (`add_remaining_self_loops`, `gcn_norm`, gather/scatter index handling) used by
+ * GCNConv/GATConv/GINConv/RGCNConv at framework/models/gcn.py:11-12, gat.py:11-12,
+ * gin.py:11-12, rgcn.py:17-22.  Built once per (edge set) and cached by the host.
+ */
+
+/* Destination-major CSR view of a message-passing edge set. */
+typedef struct gd_csr {
+    int64_t num_rows;           /* destinations */
+    int64_t nnz;
+    const int32_t* rowptr;      /* [num_rows + 1] */
+    const int32_t* col;         /* [nnz] source ids; ascending (relation, source) within a row */
+    /* long-row split plan from gd_spmm_plan_build (all zero / NULL: no splitting) */
+    int32_t seg_len;
+    int32_t num_heavy;
+    int32_t num_seg;
+    const int32_t* heavy_row;     /* [num_heavy] */
+    const int32_t* heavy_seg_beg; /* [num_heavy] first segment of the row */
+    const int32_t* heavy_nseg;    /* [num_heavy] */
+    const int32_t* seg_row;       /* [num_seg] */
+    const int32_t* seg_beg;       /* [num_seg] absolute offset into col */
+} gd_csr_t;
+
+size_t gd_csr_workspace_bytes(int64_t num_edges, int64_t num_nodes);
+
+/* COO (int64 rows of the reference's edge_index: src = edge_index[0], dst =
+ * edge_index[1]) -> CSR sorted by (dst, [rel,] src).
+ *   self_loops = 1: PyG add_remaining_self_loops — existing (v,v) entries are
+ *                   dropped and one (v,v) per node is inserted (GCNConv, GATConv);
+ *   self_loops = 0: entries kept as they are (GINConv, RGCNConv, loss incidence).
+ * `rel` (nullable, values in [0, num_rel)) adds the relation as a secondary sort key
+ * and is written per entry to `rel_out`.
+ * `eid[k]` = column of the input COO that landed at CSR position k, or -1 for an
+ * inserted self loop.  nnz = rowptr[num_nodes]; `col`/`eid`/`rel_out` must hold
+ * num_edges (+ num_nodes when self_loops) entries.
+ * `status` (device int32[2]) receives {nnz, number of out-of-range endpoints}. */
+int gd_csr_from_coo(const int64_t* src, const int64_t* dst, const int64_t* rel, int64_t num_edges,
+                    int64_t num_nodes, int32_t num_rel, int32_t self_loops, int32_t* rowptr,
+                    int32_t* col, int32_t* eid, int32_t* rel_out, int32_t* status, void* workspace,
+                    size_t workspace_bytes, gd_stream_t stream);
+
+/* dst[perm[k]] = k for k in [0,n) where perm[k] >= 0. */
+int gd_invert_perm(const int32_t* perm, int64_t n, int32_t* inv, gd_stream_t stream);
+
+/* gcn_norm (GCNConv defaults, gcn.py:11-12): dinv[i] = deg(i)^-1/2 with
+ * deg = in-degree incl. the inserted self loop (unit weights), inf -> 0. */
+int gd_gcn_dinv(const int32_t* rowptr, int64_t num_nodes, float* dinv, gd_stream_t stream);
+
+/* Long-row split plan: rows with more than seg_len entries are cut into segments of
+ * seg_len so a power-law hub never serialises on one warp.  Array capacities:
+ * heavy_* >= nnz / seg_len + 1, seg_* >= 2 * nnz / seg_len + 2.
+ * `counts` (device int32[2]) receives {num_heavy, num_seg}. */
+int gd_spmm_plan_build(const int32_t* rowptr, int64_t num_rows, int32_t seg_len, int32_t* heavy_row,
+                       int32_t* heavy_seg_beg, int32_t* heavy_nseg, int32_t* seg_row,
+                       int32_t* seg_beg, int32_t* counts, gd_stream_t stream);
+
+/* ------------------------------------------------------------- aggregation (1)
+ * out[i,:] = row_scale[i] * ( sum_{k in row i} val[k] * col_scale[col[k]] * x[col[k],:] )
+ *            + self_coef * x[i,:] + bias[:]
+ * val / col_scale / row_scale / bias nullable.  Covers
+ *   GCNConv propagate  (A_hat = D^-1/2 (A+I) D^-1/2 via row/col scale), gcn.py:11-12;
+ *   GINConv propagate  (unit weights, self_coef = 1 + eps), gin.py:11-12;
+ *   their transpose-backward (same call on the transposed CSR);
+ *   the loss backward  (val = d loss / d logit per incidence entry).
+ * `scratch` holds num_seg * feat floats when the CSR carries a split plan. */
+int gd_spmm(const gd_csr_t* csr, const float* val, const float* col_scale, const float* row_scale,
+            const float* x, int64_t ldx, int32_t feat, float self_coef, const float* bias,
+            float* out, int64_t ldo, float* scratch, gd_stream_t stream);
+
+/* ------------------------------------------------------ dense contractions (2)
+ * out[r(i),:] = epi( pro(a[r(i),:]) . B ),  i in [0,m),  r(i) = rows ? rows[i] : i
+ *   pro : optional ReLU;           B : b_is_nk ? B[n,k] (nn.Linear weight, x @ B^T)
+ *                                                : B[k,n] (deletion_weight / root, x @ B)
+ *   epi : + bias[n], * out_scale[r(i)], optional ReLU, optional gate (kept where
+ *         gate[r(i), c] > 0 else 0 — the ReLU backward of the producing layer).
+ * Replaces nn.Linear inside GCNConv/GATConv/GINConv and
+ * DeletionLayer.forward's `new_rep[mask] = new_rep[mask] @ deletion_weight`
+ * (framework/models/deletion.py:24-25) when `rows` lists the masked rows. */
+int gd_gemm_rows(const float* a, int64_t lda, const int32_t* rows, int64_t m, int32_t k,
+                 const float* b, int32_t b_is_nk, int32_t n, const float* bias,
+                 const float* out_scale, const float* gate, int64_t ldgate, int32_t relu_in,
+                 int32_t relu_out, float* out, int64_t ldo, gd_stream_t stream);
+
+/* c[k1,n2] = sum_i a_scale[r(i)] * a[r(i),:k1]^T (outer) g[r(i),:n2] — weight gradient
+ * of the contraction above over the (gathered) rows; relu_a applies ReLU to the `a`
+ * rows first, a_scale is nullable.  Deterministic two-stage reduction through
+ * `workspace`. */
+size_t gd_gemm_tn_workspace_bytes(int64_t m, int32_t k1, int32_t n2);
+int gd_gemm_tn_rows(const float* a, int64_t lda, const float* g, int64_t ldg, const int32_t* rows,
+                    int64_t m, int32_t k1, int32_t n2, int32_t relu_a, const float* a_scale, float* c,
+                    void* workspace, size_t workspace_bytes, gd_stream_t stream);
+
+/* dst[rows[i], :] = src[rows[i], :]  (the unmasked rows of DeletionLayer.forward's clone). */
+int gd_copy_rows(const float* src, int64_t lds, const int32_t* rows, int64_t m, int32_t feat,
+                 float* dst, int64_t ldd, gd_stream_t stream);
+
+/* out = max(x, 0)  (F.relu between the two convs, deletion.py:67; used where the ReLU
+ * cannot be folded into the next contraction's prologue: GIN / RGCN aggregate first) */
+int gd_relu_fwd(const float* x, int64_t count, float* out, gd_stream_t stream);
+
+/* out = grad * (pre > 0)   (ReLU backward, elementwise over [rows, feat]) */
+int gd_relu_bwd(const float* grad, const float* pre, int64_t count, float* out, gd_stream_t stream);
+
+/* ------------------------------------------------ decoder + DEC / NI losses (3)
+ * Pairs [0,n_df) are the Df edges, [n_df, 2 n_df) the supplied negatives and
+ * [2 n_df, 2 n_df + n_ni) the S_Df edges with u < v whose original logits are
+ * `target`.  logits[p] = <z[u_p], z[v_p]>          (GCN.decode, gcn.py:26-35)
+ *   loss_r = mean_i (logits[i] - logits[n_df+i])^2  (gnndelete.py:227-228, :362-363)
+ *   loss_l = mean_j (logits[2n_df+j] - target[j])^2 (gnndelete.py:379-386)
+ *   loss   = alpha * loss_r + (1-alpha) * loss_l    (gnndelete.py:249-250, :390-398)
+ * losses[3] = {loss, loss_r, loss_l}.  d loss / d logits[p] is scattered to
+ * inc_val[pos_u[p]] and inc_val[pos_v[p]], the two incidence entries of pair p, so
+ * that dz = gd_spmm(incidence CSR, val = inc_val, x = z) is a deterministic gather. */
+size_t gd_edge_loss_workspace_bytes(int64_t num_pairs);
+int gd_edge_loss_fwd(const float* z, int64_t ldz, int32_t dim, const int32_t* pair_u,
+                     const int32_t* pair_v, int64_t n_df, int64_t n_ni, const float* target,
+                     float alpha, const int32_t* pos_u, const int32_t* pos_v, float* logits,
+                     float* inc_val, float* losses, void* workspace, size_t workspace_bytes,
+                     gd_stream_t stream);
+
+/* logits[p] = sum_d z[u_p,d] * w[t_p,d] * z[v_p,d]  (w, t nullable => plain dot).
+ * GCN.decode (gcn.py:26-35) / RGCN.decode DistMult (rgcn.py:40-47). */
+int gd_pair_decode(const float* z, int64_t ldz, int32_t dim, const int32_t* pair_u,
+                   const int32_t* pair_v, int64_t num_pairs, const float* rel_weight,
+                   const int32_t* pair_rel, float* logits, gd_stream_t stream);
+
+/* Adam step with torch.optim.Adam semantics (delete_gnn.py:229-241: lr 1e-3,
+ * betas (0.9, 0.999), eps 1e-8, weight_decay 0, amsgrad off) on a flat parameter.
+ * `step` is a device float holding the step count BEFORE this call; it is
+ * incremented by the kernel so the call can be replayed inside a CUDA graph. */
+int gd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* step,
+                 int64_t count, float lr, float beta1, float beta2, float eps, gd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNDELETE_B200_H */

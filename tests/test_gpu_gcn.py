@@ -1,0 +1,223 @@
+"""GPU parity: GCN path kernels and GCNDelete against the CPU oracle (fp64 truth)."""
+import pytest
+import torch
+
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+@pytest.fixture(scope='module')
+def case(lib):
+    return U.make_case('cora', 0.05)
+
+
+def test_csr_build_bit_exact(lib, case):
+    """CSR of the sdf edge set with PyG self-loop handling: bit-exact vs a CPU sort."""
+    from gnndelete_b200.graph import build_csr
+    shape, raw, df, data, neg = case
+    ei = data.train_pos_edge_index[:, data.sdf_mask]
+    # inject a few explicit self loops: they must be dropped and re-inserted once per node
+    ei = torch.cat([ei, torch.tensor([[3, 5, 5], [3, 5, 5]])], 1)
+    n = data.num_nodes
+    csr = build_csr(ei[0].to(DEV), ei[1].to(DEV), n, self_loops=True)
+    from oracle import pyg_ops as P
+    full = P.add_remaining_self_loops(ei, n)
+    key = full[1] * n + full[0]
+    order = torch.sort(key, stable=True)[0]
+    assert csr.nnz == full.shape[1]
+    assert torch.equal(csr.col.cpu().long(), order % n)
+    deg = torch.bincount(full[1], minlength=n)
+    assert torch.equal(csr.rowptr.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long), deg.cumsum(0)]))
+    # eid maps back to the input column (or -1 for inserted loops)
+    eid = csr.eid.cpu().long()
+    real = eid >= 0
+    assert int((~real).sum()) == n
+    assert torch.equal(ei[0][eid[real]], csr.col.cpu().long()[real])
+
+
+def test_csr_rejects_out_of_range(lib):
+    from gnndelete_b200.graph import build_csr
+    ei = torch.tensor([[0, 1, 7], [1, 2, 0]], device=DEV)
+    with pytest.raises(ValueError):
+        build_csr(ei[0], ei[1], 4)
+
+
+@pytest.mark.parametrize('feat', [128, 64, 32, 100, 7])
+def test_spmm_matches_dense(lib, case, feat):
+    from gnndelete_b200 import ops
+    from gnndelete_b200.graph import build_csr
+    shape, raw, df, data, neg = case
+    ei = data.train_pos_edge_index
+    n = data.num_nodes
+    csr = build_csr(ei[0].to(DEV), ei[1].to(DEV), n, self_loops=False, seg_len=32)
+    assert csr.num_seg > 0, 'case must exercise the long-row split path'
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, feat, generator=g)
+    rs, cs = torch.rand(n, generator=g) + 0.5, torch.rand(n, generator=g) + 0.5
+    bias = torch.randn(feat, generator=g)
+    A = torch.zeros(n, n, dtype=torch.float64)
+    A.index_put_((ei[1], ei[0]), torch.ones(ei.shape[1], dtype=torch.float64), accumulate=True)
+    ref = rs.double().view(-1, 1) * (A @ (cs.double().view(-1, 1) * x.double())) + 0.5 * x.double() + bias.double()
+    out = ops.spmm(csr, x.to(DEV), col_scale=cs.to(DEV), row_scale=rs.to(DEV), self_coef=0.5, bias=bias.to(DEV))
+    U.assert_close(out, ref, what=f'spmm F={feat}')
+    ref2 = A @ x.double()
+    out2 = ops.spmm(csr, x.to(DEV))
+    U.assert_close(out2, ref2, what=f'spmm unweighted F={feat}')
+
+
+@pytest.mark.parametrize('m,k,n,nk', [(300, 128, 128, True), (1000, 128, 64, True), (257, 500, 128, True),
+                                      (513, 64, 64, False), (100, 30, 17, False)])
+def test_gemm_rows(lib, m, k, n, nk):
+    from gnndelete_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    a = torch.randn(m, k, generator=g)
+    b = torch.randn((n, k) if nk else (k, n), generator=g)
+    bias = torch.randn(n, generator=g)
+    s = torch.rand(m, generator=g) + 0.5
+    bm = b.double().t() if nk else b.double()
+    ref = (a.double().clamp(min=0) @ bm + bias.double()) * s.double().view(-1, 1)
+    out = ops.gemm_rows(a.to(DEV), b.to(DEV), nk, bias=bias.to(DEV), out_scale=s.to(DEV), relu_in=True)
+    U.assert_close(out, ref, what='gemm_rows')
+    # gathered rows, in place
+    rows = torch.randperm(m, generator=g)[: m // 3].sort()[0]
+    out2 = torch.full((m, n), -7.0, device=DEV)
+    ops.gemm_rows(a.to(DEV), b.to(DEV), nk, out=out2, rows=rows.to(DEV).int())
+    ref2 = torch.full((m, n), -7.0, dtype=torch.float64)
+    ref2[rows] = a.double()[rows] @ bm
+    U.assert_close(out2, ref2, what='gemm_rows gathered')
+
+
+@pytest.mark.parametrize('m,k1,n2', [(5000, 128, 128), (777, 64, 64), (300, 100, 30)])
+def test_gemm_tn_rows(lib, m, k1, n2):
+    from gnndelete_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    a, gr = torch.randn(m, k1, generator=g), torch.randn(m, n2, generator=g)
+    rows = torch.randperm(m, generator=g)[: m // 2].sort()[0]
+    ref = a.double()[rows].t() @ gr.double()[rows]
+    out = ops.gemm_tn_rows(a.to(DEV), gr.to(DEV), rows=rows.to(DEV).int())
+    U.assert_close(out, ref, what='gemm_tn_rows')
+
+
+def _load(gnn, om, shape, data, **kw):
+    from gnndelete_b200 import models as M
+    cls = {'gcn': M.GCNDelete, 'gin': M.GINDelete}[gnn]
+    m = cls(U.args_for(shape), data.sdf_node_1hop_mask, data.sdf_node_2hop_mask, **kw)
+    missing = m.load_state_dict({k: v.float() for k, v in om.state_dict().items()}, strict=True)
+    return m.to(DEV)
+
+
+@pytest.mark.parametrize('gnn', ['gcn', 'gin'])
+def test_delete_model_forward_and_grads(lib, case, gnn):
+    """z1, z2, decode logits, edge-form loss and deletion_weight.grad vs the oracle."""
+    from oracle import unlearn as OU
+    shape, raw, df, data, neg = case
+    om = U.oracle_model(gnn, shape, data, dtype=torch.float64)
+    d64 = data.clone()
+    d64.x = data.x.double()
+    with torch.no_grad():
+        zo = om.get_original_embeddings(d64.x, d64.train_pos_edge_index[:, d64.dr_mask])
+    loss_o, lr_o, ll_o, z_o = OU.edge_form_loss(om, d64, neg, zo)
+    loss_o.backward()
+
+    m = _load(gnn, om, shape, data)
+    dd = data.clone().to(DEV)
+    ei = dd.train_pos_edge_index[:, dd.sdf_mask]
+    z1, z2 = m(dd.x, ei, return_all_emb=True)
+    z1_o, z2_o = om(d64.x, d64.train_pos_edge_index[:, d64.sdf_mask], return_all_emb=True)
+    U.assert_close(z1, z1_o, what='z1')
+    U.assert_close(z2, z2_o, what='z2')
+    # original embeddings on the dr edge set
+    zo_g = m.get_original_embeddings(dd.x, dd.train_pos_edge_index[:, dd.dr_mask])
+    U.assert_close(zo_g, zo, what='z_ori')
+    # decode + losses through the reference-shaped autograd path
+    negd = neg.to(DEV)
+    logits = m.decode(z2, dd.train_pos_edge_index[:, dd.df_mask], negd)
+    U.assert_close(logits, om.decode(z2_o, d64.train_pos_edge_index[:, d64.df_mask], neg), what='df_logits')
+    n = int(dd.df_mask.sum())
+    loss_r = torch.nn.functional.mse_loss(logits[:n], logits[n:])
+    edge = ei
+    lower = edge[0] < edge[1]
+    row, col = edge[0][lower], edge[1][lower]
+    lg = m.decode(z2, torch.stack([row, col]))
+    lo = m.decode(zo_g, torch.stack([row, col])).detach()
+    loss_l = torch.nn.functional.mse_loss(lg, lo)
+    loss = 0.5 * loss_r + 0.5 * loss_l
+    U.assert_close(loss_r, lr_o, what='loss_r')
+    U.assert_close(loss_l, ll_o, what='loss_l')
+    loss.backward()
+    U.assert_close(m.deletion2.deletion_weight.grad, om.deletion2.deletion_weight.grad, what='dW_del2')
+    U.assert_close(m.deletion1.deletion_weight.grad, om.deletion1.deletion_weight.grad, what='dW_del1')
+
+
+def test_fused_edge_loss(lib, case):
+    """gd_edge_loss_fwd + incidence gather == autograd of the oracle's loss w.r.t. z."""
+    from gnndelete_b200.losses import EdgeLossPlan
+    shape, raw, df, data, neg = case
+    g = torch.Generator().manual_seed(5)
+    n = data.num_nodes
+    z = torch.randn(n, 64, generator=g, dtype=torch.float64, requires_grad=True)
+    zo = torch.randn(n, 64, generator=g, dtype=torch.float64)
+    ei = data.train_pos_edge_index
+    dfe = ei[:, data.df_mask]
+    sdf = ei[:, data.sdf_mask]
+    ni = sdf[:, sdf[0] < sdf[1]]
+    nd = dfe.shape[1]
+    lg = (z[torch.cat([dfe[0], neg[0]])] * z[torch.cat([dfe[1], neg[1]])]).sum(-1)
+    loss_r = torch.nn.functional.mse_loss(lg[:nd], lg[nd:])
+    loss_l = torch.nn.functional.mse_loss((z[ni[0]] * z[ni[1]]).sum(-1), (zo[ni[0]] * zo[ni[1]]).sum(-1))
+    loss = 0.5 * loss_r + 0.5 * loss_l
+    loss.backward()
+    zg = z.detach().float().to(DEV)
+    plan = EdgeLossPlan(dfe.to(DEV), neg.to(DEV), ni.to(DEV), n, z_ori=zo.float().to(DEV))
+    losses = plan.forward(zg)
+    dz = plan.backward(zg)
+    U.assert_close(losses, torch.stack([loss, loss_r, loss_l]), what='losses')
+    U.assert_close(dz, z.grad, what='dz')
+    U.assert_close(plan.logits[:2 * nd], lg, what='logits')
+    # deterministic: bitwise identical on repeat
+    l2 = plan.forward(zg).clone()
+    dz2 = plan.backward(zg)
+    assert torch.equal(l2, losses) and torch.equal(dz, dz2)
+
+
+def test_deletion_layer_semantics(lib):
+    """mask=None -> stored mask; both None -> identity; returns a new tensor; index-tensor mask."""
+    from gnndelete_b200.models import DeletionLayer
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(50, 64, generator=g).to(DEV)
+    mask = torch.rand(50, generator=g) < 0.4
+    lay = DeletionLayer(64, mask).to(DEV)
+    y = lay(x)
+    w = lay.deletion_weight.detach()
+    ref = x.clone()
+    ref[mask.to(DEV)] = x[mask.to(DEV)] @ w
+    U.assert_close(y, ref, what='stored mask')
+    assert y.data_ptr() != x.data_ptr()
+    assert DeletionLayer(64, None).to(DEV)(x) is x
+    other = torch.rand(50, generator=g) < 0.5
+    y2 = lay(x, other.to(DEV))
+    ref2 = x.clone()
+    ref2[other.to(DEV)] = x[other.to(DEV)] @ w
+    U.assert_close(y2, ref2, what='call mask')
+    idx = other.nonzero().squeeze(1).to(DEV)
+    U.assert_close(lay(x, idx), ref2, what='index mask')
+
+
+def test_adam_matches_torch(lib):
+    from gnndelete_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    p0 = torch.randn(64, 64, generator=g)
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([p_ref], lr=1e-3)
+    p = p0.clone().to(DEV)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    step = torch.zeros(1, device=DEV)
+    for i in range(5):
+        gr = torch.randn(64, 64, generator=g)
+        p_ref.grad = gr.clone()
+        opt.step()
+        ops.adam_step(p, gr.to(DEV), m, v, step, 1e-3)
+    assert step.item() == 5
+    U.assert_close(p, p_ref.detach(), tol=1e-6, what='adam')
