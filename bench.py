@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Headline benchmark: GNNDelete edge-unlearning (Del-training) epochs/s on the
+OGB-Collab-shaped synthetic graph (BASELINE.json configs[2]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload NAME]
+
+One step = one epoch: GCNDelete forward on the fixed sdf-masked edge
+set (BOTH conv layers recomputed — hoisting the frozen layer-1 conv is reported
+separately as ``value_hoisted``) -> decode on (Df, supplied negatives) ->
+0.5*MSE(pos,neg) + 0.5*NI(edge form) -> backward to deletion{1,2}.deletion_weight -> Adam.
+
+N > 1: the Collab-shaped graph fits one GPU ("small graphs stay on one GPU"), so ranks
+run independent replicas (different seeds = different deletion requests), no data-path
+collective; value = all ranks' epochs / max-over-ranks device time ("scaling": "weak").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = 'Del-training epochs/s on OGB-Collab shape'
+UNIT = 'epochs/s'
+
+
+# --------------------------------------------------------------------------- utils
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        out = self.proc.communicate()[0]
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    return rank, local, world
+
+
+def barrier_sync(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(value, world, dev):
+    if world == 1:
+        return value
+    import torch.distributed as dist
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------------ workload
+def build_case(shape, seed, dev):
+    """Synthetic inputs + masks (CUDA mask pipeline) + random-init model + z_ori."""
+    import types
+    from gnndelete_b200 import synthetic as S
+    from gnndelete_b200 import masks as MK
+    from gnndelete_b200 import models as M
+    raw = S.make_graph(shape, seed=seed, device='cpu').to(dev)
+    df = S.sample_df_mask(shape.num_edges, shape.num_deleted, seed=seed, device='cpu').to(dev)
+    data = MK.build_unlearning_data(raw, df)
+    neg = S.supplied_negatives(shape.num_nodes, int(data.df_mask.sum()), seed=seed + 1, device='cpu').to(dev)
+    args = types.SimpleNamespace(in_dim=shape.in_dim, hidden_dim=shape.hidden_dim, out_dim=shape.out_dim)
+    torch.manual_seed(seed)
+    model = M.GCNDelete(args, data.sdf_node_1hop_mask, data.sdf_node_2hop_mask).to(dev)
+    with torch.no_grad():
+        z_ori = model.get_original_embeddings(data.x, data.train_pos_edge_index[:, data.dr_mask])
+    return data, neg, model, z_ori
+
+
+def spmm_algo_bytes(n, nnz, feat):
+    """rowptr + col + deg^-1/2 + read N*F + write N*F, fp32, int32 ids."""
+    return 4 * (n + 1) + 4 * nnz + 4 * n + 4 * n * feat + 4 * n * feat
+
+
+def time_kernels(eng, steps):
+    """Eager epochs with CUDA events around each aggregation launch (on the launch stream)."""
+    from gnndelete_b200 import ops
+    st = torch.cuda.current_stream()
+    rec = {}
+
+    def timed(name, fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st); fn(); b.record(st)
+        rec.setdefault(name, []).append((a, b))
+
+    m, p = eng.model, eng.plan
+    for _ in range(steps):
+        ops.gemm_rows(eng.x, m.conv1.lin.weight.detach(), True, out=eng.h0, out_scale=p.dinv)
+        timed('spmm_l1_f128', lambda: ops.spmm(p.fwd, eng.h0, out=eng.a1, row_scale=p.dinv, bias=m.conv1.bias.detach()))
+        eng._layer1_done = True
+        hoist, eng.hoist = eng.hoist, True
+        # forward with the layer-2 aggregation bracketed
+        w1 = m.deletion1.deletion_weight.detach(); w2 = m.deletion2.deletion_weight.detach()
+        ops.gemm_rows(eng.a1, w1, False, out=eng.x1, rows=eng.rows1)
+        ops.copy_rows(eng.a1, eng.x1, eng.comp1)
+        ops.gemm_rows(eng.x1, m.conv2.lin.weight.detach(), True, out=eng.h1, out_scale=p.dinv, relu_in=True)
+        timed('spmm_l2_f64', lambda: ops.spmm(p.fwd, eng.h1, out=eng.a2, row_scale=p.dinv, bias=m.conv2.bias.detach()))
+        ops.gemm_rows(eng.a2, w2, False, out=eng.z, rows=eng.rows2)
+        ops.copy_rows(eng.a2, eng.z, eng.comp2)
+        timed('edge_loss_fwd', lambda: eng.loss.forward(eng.z))
+        timed('edge_loss_bwd_spmm', lambda: eng.loss.backward(eng.z, out=eng.dz))
+        ops.gemm_tn_rows(eng.a2, eng.dz, rows=eng.rows2, out=eng.params[1].grad)
+        ops.gemm_rows(eng.dz, w2, True, out=eng.da2, rows=eng.rows2)
+        ops.copy_rows(eng.dz, eng.da2, eng.comp2)
+        timed('spmm_bwd_f64', lambda: ops.spmm(p.bwd, eng.da2, out=eng.dh1, col_scale=p.dinv))
+        ops.gemm_rows(eng.dh1, m.conv2.lin.weight.detach(), False, out=eng.dx1, rows=eng.rows1,
+                      out_scale=p.dinv, gate=eng.x1)
+        ops.gemm_tn_rows(eng.a1, eng.dx1, rows=eng.rows1, out=eng.params[0].grad)
+        eng.hoist = hoist
+    torch.cuda.synchronize()
+    return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in rec.items()}
+
+
+def timed_epochs(eng, steps, world):
+    """K epochs between barrier+sync brackets, CUDA events on the launch stream; ms total."""
+    st = torch.cuda.current_stream()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier_sync(world)
+    a.record(st)
+    for _ in range(steps):
+        eng.epoch()
+    b.record(st)
+    barrier_sync(world)
+    return a.elapsed_time(b)
+
+
+# ---------------------------------------------------------------- CPU reference leg
+def cpu_epoch_runner(shape, seed=42):
+    """The reference's CPU path for the same epoch: the oracle restatement executed with
+    PyG's op sequence (eager PyTorch fp32 autograd) on all host cores."""
+    import types
+    from gnndelete_b200 import synthetic as S
+    from oracle import models as OM
+    from oracle import unlearn as OU
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    raw = S.make_graph(shape, seed=seed, device='cpu')
+    df = S.sample_df_mask(shape.num_edges, shape.num_deleted, seed=seed)
+    data = OU.build_unlearning_data(raw, df)
+    neg = S.supplied_negatives(shape.num_nodes, int(data.df_mask.sum()), seed=seed + 1)
+    args = types.SimpleNamespace(in_dim=shape.in_dim, hidden_dim=shape.hidden_dim, out_dim=shape.out_dim)
+    torch.manual_seed(seed)
+    model = OM.GCNDelete(args, data.sdf_node_1hop_mask, data.sdf_node_2hop_mask)
+    opt = torch.optim.Adam([p for n, p in model.named_parameters() if 'del' in n], lr=1e-3)
+    with torch.no_grad():
+        z_ori = model.get_original_embeddings(data.x, data.train_pos_edge_index[:, data.dr_mask])
+
+    def epoch():
+        loss, _, _, _ = OU.edge_form_loss(model, data, neg, z_ori, masks_positional=False)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        return float(loss)
+
+    return epoch, cores
+
+
+def run_reference(args, shape):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    epoch, cores = cpu_epoch_runner(shape)
+    for _ in range(max(1, min(args.warmup, 2))):
+        epoch()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        epoch()
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    sample = f'{args.steps} full epochs of the {shape.name} workload (whole graph, no sub-sampling)'
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(shape, 'cpu'),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'note': 'PyTorch-Geometric is not installable here; the reference arm is the oracle restatement run with '
+                "PyG's op sequence (eager PyTorch CPU autograd), parity unpinned",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(shape, where):
+    return {
+        'workload': f'GCNDelete edge unlearning, {shape.name}-shaped synthetic power-law graph '
+                    f'({shape.num_nodes} nodes / {shape.num_edges} directed train edges / {shape.num_deleted} deleted), '
+                    f'{shape.in_dim}->{shape.hidden_dim}->{shape.out_dim}, edge-form NI loss, full graph per step',
+        'epoch': 'fwd (both convs recomputed) + decode + DEC/NI loss + bwd to Del weights + Adam',
+        'l2': 'per-epoch working set ~0.9 GB > 126 MB L2, no flush between steps',
+        'where': where,
+    }
+
+
+# --------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=None)
+    ap.add_argument('--warmup', type=int, default=None)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--workload', default='collab')
+    ap.add_argument('--scale', type=float, default=1.0)
+    ap.add_argument('--cpu-epochs', type=int, default=4, help='bounded CPU-baseline sample (epochs)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    from gnndelete_b200 import synthetic as S
+    shape = S.SHAPES[args.workload].scaled(args.scale)
+
+    if args.impl == 'reference':
+        args.steps = args.steps if args.steps is not None else 5
+        args.warmup = args.warmup if args.warmup is not None else 1
+        return run_reference(args, shape)
+
+    args.steps = args.steps if args.steps is not None else 200
+    args.warmup = max(3, args.warmup if args.warmup is not None else 10)
+    rank, local, world = dist_setup(args.gpus)
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    from gnndelete_b200 import _lib, build
+    if rank == 0:
+        build.build()
+    barrier_sync(world)
+    lib = _lib.load()
+    from gnndelete_b200.engine import GCNDeleteEngine
+
+    data, neg, model, z_ori = build_case(shape, 42 + rank, dev)
+    n = shape.num_nodes
+    nnz = data.train_pos_edge_index[:, data.sdf_mask].shape[1] + n
+
+    # ---- value: device-resident epochs, CUDA-graph replay, both conv layers recomputed
+    eng = GCNDeleteEngine(model, data, neg, z_ori=z_ori, hoist_layer1=False)
+    c0 = lib.gd_launch_count()
+    eng.epoch()
+    launches_per_epoch = lib.gd_launch_count() - c0
+    eng.capture(warmup=2)
+    for _ in range(args.warmup):
+        eng.epoch()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed_epochs(eng, args.steps, world)
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms, world, dev)
+    value = world * args.steps / (ms / 1e3)
+    losses = eng.loss.losses.tolist()
+
+    # ---- value_hoisted: layer-1 conv (frozen, input-constant) computed once outside the loop
+    eng_h = GCNDeleteEngine(model, data, neg, z_ori=z_ori, hoist_layer1=True)
+    eng_h.capture(warmup=2)
+    for _ in range(args.warmup):
+        eng_h.epoch()
+    ms_h = max_over_ranks(timed_epochs(eng_h, args.steps, world), world, dev)
+
+    # ---- per-kernel durations (eager launches, events on the launch stream) -> roofline
+    peak, peak_src = load_peaks()
+    eng_k = GCNDeleteEngine(model, data, neg, z_ori=z_ori, hoist_layer1=False)
+    time_kernels(eng_k, 3)
+    kt = time_kernels(eng_k, min(args.steps, 50))
+    b64 = spmm_algo_bytes(n, nnz, shape.out_dim)
+    b128 = spmm_algo_bytes(n, nnz, shape.hidden_dim)
+    achieved = b64 / (kt['spmm_l2_f64'] * 1e-3) / 1e9
+    roofline = {
+        'kernel': 'spmm_vec_kernel<16> (GCN layer-2 aggregation, F=64)', 'bound': 'hbm',
+        'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+        'peak_source': peak_src, 'algorithmic_bytes_per_launch': b64, 'kernel_ms': kt['spmm_l2_f64'],
+        'bytes_gather_per_launch': b64 - 4 * n * shape.out_dim + 4 * nnz * shape.out_dim,
+        'other_kernels': {
+            'spmm_l1_f128': {'ms': kt['spmm_l1_f128'], 'algo_bytes': b128,
+                             'frac': b128 / (kt['spmm_l1_f128'] * 1e-3) / 1e9 / peak},
+            'spmm_bwd_f64': {'ms': kt['spmm_bwd_f64'], 'algo_bytes': b64,
+                             'frac': b64 / (kt['spmm_bwd_f64'] * 1e-3) / 1e9 / peak},
+            'edge_loss_fwd': {'ms': kt['edge_loss_fwd']}, 'edge_loss_bwd_spmm': {'ms': kt['edge_loss_bwd_spmm']},
+        },
+    }
+
+    # ---- e2e: public API with host buffers — per step: pinned negatives -> device, plan
+    #      refresh, epoch, losses -> host
+    eng_e = GCNDeleteEngine(model, data, neg, z_ori=z_ori, hoist_layer1=False)
+    neg_host = neg.cpu().pin_memory()
+    neg_dev = torch.empty_like(neg)
+    out_host = torch.empty(3, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        neg_dev.copy_(neg_host, non_blocking=True)
+        eng_e.set_negatives(neg_dev)
+        out_host.copy_(eng_e.epoch(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    e2e_steps = min(args.steps, 50)
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier_sync(world)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world, dev)
+    e2e = {'value': world * e2e_steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': neg_host.numel() * 8,
+           'd2h_bytes_per_step': 12, 'steps': e2e_steps,
+           'what': 'per step: supplied negatives pinned-host->device, pair-plan refresh, epoch, losses->host'}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(shape, 'B200'),
+        'value_hoisted': world * args.steps / (ms_h / 1e3), 'ms_per_step_hoisted': ms_h / args.steps,
+        'roofline': roofline, 'e2e': e2e, 'gpu_launches': int(launches_per_epoch * args.steps),
+        'launches_per_epoch': int(launches_per_epoch), 'clocks': clocks,
+        'losses_last': losses, 'parallelism': 'replicas' if world > 1 else 'single',
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        epoch, cores = cpu_epoch_runner(shape)
+        epoch()
+        t0 = time.perf_counter()
+        for _ in range(args.cpu_epochs):
+            epoch()
+        dt = time.perf_counter() - t0
+        line['cpu_baseline'] = {'value': args.cpu_epochs / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                'sample': f'{args.cpu_epochs} full epochs of the same workload (after 1 warm-up)'}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

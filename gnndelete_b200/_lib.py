@@ -32,6 +32,7 @@ _csr_p = C.POINTER(CsrStruct)
 SIGNATURES = {
     'gd_version': (C.c_int, []),
     'gd_last_error': (C.c_char_p, []),
+    'gd_launch_count': (C.c_longlong, []),
     'gd_csr_workspace_bytes': (_sz, [_i64, _i64]),
     'gd_csr_from_coo': (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'gd_invert_perm': (C.c_int, [_vp, _i64, _vp, _vp]),
@@ -48,6 +49,10 @@ SIGNATURES = {
     'gd_edge_loss_fwd': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'gd_pair_decode': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     'gd_adam_step': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp]),
+    'gd_khop_workspace_bytes': (_sz, [_i64]),
+    'gd_khop_masks': (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'gd_to_undirected_workspace_bytes': (_sz, [_i64]),
+    'gd_to_undirected': (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

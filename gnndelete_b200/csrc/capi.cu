@@ -3,6 +3,7 @@
 
 namespace gd {
 static thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
 void set_error(const std::string& msg) { g_last_error = msg; }
 int fail(int code, const std::string& msg) {
     g_last_error = msg;
@@ -12,3 +13,4 @@ int fail(int code, const std::string& msg) {
 
 extern "C" int gd_version(void) { return 100; /* 0.1.0 */ }
 extern "C" const char* gd_last_error(void) { return gd::g_last_error.c_str(); }
+extern "C" long long gd_launch_count(void) { return gd::g_launches.load(); }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <atomic>
 #include <string>
 
 #include "../../include/gnndelete_b200.h"
@@ -11,6 +12,7 @@ namespace gd {
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
+extern std::atomic<long long> g_launches;   // kernels this library has launched (capi.cu)
 void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 
@@ -26,7 +28,11 @@ int fail(int code, const std::string& msg);
             return ::gd::fail(GD_ERR_CUDA, std::string(__func__) + ": " #expr ": " + cudaGetErrorString(e__)); \
     } while (0)
 
-#define GD_LAUNCH_CHECK() GD_CUDA(cudaGetLastError())
+#define GD_LAUNCH_CHECK()                                                    \
+    do {                                                                     \
+        ::gd::g_launches.fetch_add(1, std::memory_order_relaxed);            \
+        GD_CUDA(cudaGetLastError());                                         \
+    } while (0)
 
 inline cudaStream_t as_stream(gd_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

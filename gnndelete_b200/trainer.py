@@ -1,0 +1,204 @@
+"""Host-side mirror of the reference trainers for the unlearning hot path
+(``framework/trainer/base.py`` ``Trainer`` and ``framework/trainer/gnndelete.py``
+``GNNDeleteTrainer``): same class names, constructor, ``train`` / ``eval`` / ``test`` /
+``save_log`` signatures, log keys and checkpoint files.  The epoch body runs on the
+fused CUDA engine (``engine.py``); wandb / tqdm logging of the reference is replaced by
+the ``trainer_log`` dict only (no third-party logging dependency).
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import torch
+
+from . import metrics
+from .engine import GCNDeleteEngine
+
+
+def get_loss_fct(name):
+    """``gnndelete.py:25-35``: the two train loops hard-code MSE; anything else raises."""
+    if name in ('mse', 'mse_mean'):
+        return torch.nn.MSELoss()
+    raise NotImplementedError(name)
+
+
+class Trainer:
+    """``framework/trainer/base.py:24-35, 229-391`` (the parts GNNDelete uses)."""
+
+    def __init__(self, args):
+        self.args = args
+        self.trainer_log = {'unlearning_model': args.unlearning_model, 'dataset': args.dataset, 'log': []}
+        self.logit_all_pair = None
+        self.df_pos_edge = []
+        os.makedirs(args.checkpoint_dir, exist_ok=True)
+        with open(os.path.join(args.checkpoint_dir, 'training_args.json'), 'w') as f:
+            json.dump({k: v for k, v in vars(args).items() if _jsonable(v)}, f)
+
+    @torch.no_grad()
+    def get_link_labels(self, pos_edge_index, neg_edge_index):
+        e = pos_edge_index.size(1) + neg_edge_index.size(1)
+        labels = torch.zeros(e, dtype=torch.float, device=pos_edge_index.device)
+        labels[:pos_edge_index.size(1)] = 1.
+        return labels
+
+    @torch.no_grad()
+    def eval(self, model, data, stage='val', pred_all=False, num_df_resamples=500):
+        """``base.py:229-305``: forward on the ``dr_mask`` edge set, decode val/test edges,
+        BCE + AUC/AP on Dt, AUC/AP of Df against ``num_df_resamples`` random Dr samples.
+        AUC / AP are computed on the device (``metrics.py``, rank based, same tie handling
+        as sklearn) instead of 500 sklearn calls on Python lists."""
+        model.eval()
+        pos, neg = data[f'{stage}_pos_edge_index'], data[f'{stage}_neg_edge_index']
+        mask = data.dtrain_mask if hasattr(data, 'dtrain_mask') else data.dr_mask
+        z = model(data.x, data.train_pos_edge_index[:, mask])
+        logits = model.decode(z, pos, neg).sigmoid()
+        label = self.get_link_labels(pos, neg)
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, label).item()
+        dt_auc = metrics.roc_auc(label, logits)
+        dt_aup = metrics.average_precision(label, logits)
+        if self.args.unlearning_model in ['original']:
+            df_logit = torch.empty(0, device=z.device)
+        else:
+            df_logit = model.decode(z, data.directed_df_edge_index).sigmoid()
+        n_df = df_logit.numel()
+        if n_df > 0:
+            dr_edges = data.train_pos_edge_index[:, data.dr_mask]
+            if len(self.df_pos_edge) == 0:
+                g = torch.Generator(device='cpu').manual_seed(getattr(self.args, 'random_seed', 42))
+                for _ in range(num_df_resamples):
+                    self.df_pos_edge.append(torch.randperm(dr_edges.shape[1], generator=g)[:n_df].to(z.device))
+            dr_logit = model.decode(z, dr_edges).sigmoid()
+            lab = torch.cat([torch.zeros(n_df, device=z.device), torch.ones(n_df, device=z.device)])
+            aucs, aups = [], []
+            for idx in self.df_pos_edge:
+                lg = torch.cat([df_logit, dr_logit[idx]])
+                aucs.append(metrics.roc_auc(lab, lg, as_tensor=True))
+                aups.append(metrics.average_precision(lab, lg, as_tensor=True))
+            df_auc = torch.stack(aucs).mean().item()
+            df_aup = torch.stack(aups).mean().item()
+        else:
+            df_auc = df_aup = float('nan')
+        logit_all_pair = (z @ z.t()).cpu() if pred_all else None
+        log = {
+            f'{stage}_loss': loss, f'{stage}_dt_auc': dt_auc, f'{stage}_dt_aup': dt_aup,
+            f'{stage}_df_auc': df_auc, f'{stage}_df_aup': df_aup,
+            f'{stage}_df_logit_mean': df_logit.mean().item() if n_df else float('nan'),
+            f'{stage}_df_logit_std': df_logit.std(unbiased=False).item() if n_df else float('nan'),
+        }
+        return loss, dt_auc, dt_aup, df_auc, df_aup, df_logit.tolist(), logit_all_pair, log
+
+    @torch.no_grad()
+    def test(self, model, data, model_retrain=None, attack_model_all=None, attack_model_sub=None, ckpt='best'):
+        """``base.py:307-375`` without the membership-inference / retrain-comparison legs
+        (out of scope)."""
+        if ckpt == 'best':
+            path = os.path.join(self.args.checkpoint_dir, 'model_best.pt')
+            if os.path.exists(path):
+                model.load_state_dict(torch.load(path, map_location=data.x.device)['model_state'])
+        pred_all = 'ogbl' not in self.args.dataset
+        loss, dt_auc, dt_aup, df_auc, df_aup, df_logit, logit_all_pair, test_log = self.eval(model, data, 'test', pred_all)
+        self.trainer_log['dt_loss'] = loss
+        self.trainer_log['dt_auc'] = dt_auc
+        self.trainer_log['dt_aup'] = dt_aup
+        self.trainer_log['df_logit'] = df_logit
+        self.logit_all_pair = logit_all_pair
+        self.trainer_log['df_auc'] = df_auc
+        self.trainer_log['df_aup'] = df_aup
+        return loss, dt_auc, dt_aup, df_auc, df_aup, df_logit, logit_all_pair, test_log
+
+    def save_log(self):
+        with open(os.path.join(self.args.checkpoint_dir, 'trainer_log.json'), 'w') as f:
+            json.dump(self.trainer_log, f)
+        torch.save(self.logit_all_pair, os.path.join(self.args.checkpoint_dir, 'pred_proba.pt'))
+
+
+def _jsonable(v):
+    try:
+        json.dumps(v)
+        return True
+    except TypeError:
+        return False
+
+
+class GNNDeleteTrainer(Trainer):
+    """``framework/trainer/gnndelete.py:37-450``.
+
+    Both reference loops run one optimisation step per (sub)graph with
+    ``loss = 0.5 * MSE(df_logits, neg_logits) + 0.5 * NI``.  Here the whole graph is the
+    batch (180 GB of HBM make GraphSAINT sampling unnecessary) and NI is
+    the edge form of ``train_minibatch`` (:379-386).  ``z_ori`` — which the reference
+    fails to produce (``data.dtrain_mask`` is never set) — is the base
+    model's embedding on the ``dr_mask`` edge set unless supplied as ``data.z_ori``.
+    """
+
+    log_every = 100      # epochs between device->host loss reads (the reference syncs 3x per epoch)
+
+    def train(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
+        if not hasattr(model, 'deletion1') or type(model).__name__ != 'GCNDelete':
+            raise NotImplementedError('the fused epoch engine currently drives GCNDelete; other *Delete models '
+                                      'train through the autograd modules')
+        return self.train_edge_form(model, data, optimizer, args)
+
+    def _negatives(self, data, count, generator):
+        """Uniform random pairs (``negative_sampling`` is randomised rejection sampling in
+        PyG and not reproducible across implementations); a caller that
+        needs parity supplies ``data.neg_edge_index``."""
+        return torch.randint(0, data.num_nodes, (2, count), generator=generator, device=data.x.device)
+
+    def train_edge_form(self, model, data, optimizer, args):
+        dev = torch.device('cuda')
+        model = model.to(dev)
+        data = data.to(dev)
+        n_df = int(data.df_mask.sum())
+        gen = torch.Generator(device=dev).manual_seed(getattr(args, 'random_seed', 42))
+        fixed_neg = getattr(data, 'neg_edge_index', None)
+        neg = fixed_neg if fixed_neg is not None else self._negatives(data, n_df, gen)
+        with torch.no_grad():
+            z_ori = getattr(data, 'z_ori', None)
+            if z_ori is None:
+                z_ori = model.get_original_embeddings(data.x, data.train_pos_edge_index[:, data.dr_mask])
+        group = optimizer.param_groups[0]
+        eng = GCNDeleteEngine(model, data, neg, z_ori=z_ori, lr=group['lr'], betas=group['betas'], eps=group['eps'])
+        best_metric = 0
+        ring = []
+        t0 = time.time()
+        for epoch in range(args.epochs):
+            model.train()
+            if fixed_neg is None and epoch > 0:
+                eng.set_negatives(self._negatives(data, n_df, gen))
+            losses = eng.epoch()
+            ring.append(losses.clone())
+            last = epoch + 1 == args.epochs
+            if (epoch + 1) % self.log_every == 0 or last or (epoch + 1) % args.valid_freq == 0:
+                vals = torch.stack(ring).cpu()
+                dt = (time.time() - t0) / len(ring)
+                for i, v in enumerate(vals.tolist()):
+                    self.trainer_log['log'].append({'Epoch': epoch + 1 - len(ring) + i, 'train_loss': v[0],
+                                                    'loss_r': v[1], 'loss_l': v[2], 'train_time': dt})
+                ring, t0 = [], time.time()
+            if (epoch + 1) % args.valid_freq == 0:
+                valid_loss, dt_auc, dt_aup, df_auc, df_aup, _, _, valid_log = self.eval(model, data, 'val')
+                valid_log['epoch'] = epoch
+                self.trainer_log['log'].append(valid_log)
+                if dt_auc + df_auc > best_metric:
+                    best_metric = dt_auc + df_auc
+                    torch.save({'model_state': model.state_dict(), 'optimizer_state': self._optimizer_state(optimizer, eng)},
+                               os.path.join(args.checkpoint_dir, 'model_best.pt'))
+        torch.save({'model_state': {k: v.to('cpu') for k, v in model.state_dict().items()},
+                    'optimizer_state': self._optimizer_state(optimizer, eng)},
+                   os.path.join(args.checkpoint_dir, 'model_final.pt'))
+        return eng
+
+    @staticmethod
+    def _optimizer_state(optimizer, eng):
+        """Mirror the engine's Adam moments into the caller's ``torch.optim.Adam`` so the
+        saved ``optimizer_state`` stays loadable by the reference."""
+        params = [p for g in optimizer.param_groups for p in g['params']]
+        for p, st in zip(eng.params, eng.state):
+            for q in params:
+                if q is p:
+                    optimizer.state[q] = {'step': st['step'].detach().cpu().reshape(()).clone(),
+                                          'exp_avg': st['m'], 'exp_avg_sq': st['v']}
+        return optimizer.state_dict()

@@ -36,6 +36,9 @@ typedef void* gd_stream_t; /* cudaStream_t */
 
 int gd_version(void);
 const char* gd_last_error(void);
+/* kernels launched by this library since load (process-wide; evidence for bench.py's
+ * gpu_launches). */
+long long gd_launch_count(void);
 
 /* ------------------------------------------------------------------ graph build
  * Replaces the per-call index plumbing of torch_geometric MessagePassing
@@ -170,6 +173,31 @@ int gd_pair_decode(const float* z, int64_t ldz, int32_t dim, const int32_t* pair
  * incremented by the kernel so the call can be replayed inside a CUDA graph. */
 int gd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* step,
                  int64_t count, float lr, float beta1, float beta2, float eps, gd_stream_t stream);
+
+/* ------------------------------------------------------ deletion masks (4)
+ * torch_geometric.utils.k_hop_subgraph(seeds, num_hops, edge_index, num_nodes,
+ * flow='source_to_target') as used at delete_gnn.py:128-151, seeds = endpoints of the
+ * edges selected by `seed_edge_mask` (= edge_index[:, df_mask].flatten().unique()).
+ * Each hop adds the SOURCES of edges whose TARGET is in the previous frontier
+ * (src = edge_index[0], dst = edge_index[1]); the result is the induced-edge mask of
+ * the union of all frontiers and the node mask of those edges' endpoints
+ * (delete_gnn.py:141-145).  Frontiers are N-bit bitmaps; one streaming pass over the
+ * edge list per hop.  `status` (device int32) counts out-of-range endpoints. */
+size_t gd_khop_workspace_bytes(int64_t num_nodes);
+int gd_khop_masks(const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t num_nodes,
+                  const uint8_t* seed_edge_mask, int32_t num_hops, uint8_t* edge_mask,
+                  uint8_t* node_mask, int32_t* status, void* workspace, size_t workspace_bytes,
+                  gd_stream_t stream);
+
+/* torch_geometric.utils.to_undirected(edge_index, [a, b]) (reduce='add') as used at
+ * delete_gnn.py:175-182: concatenate the flipped list, sort by row * N + col, merge
+ * duplicates summing the int attributes.  Outputs hold up to 2 * num_edges entries;
+ * `out_count` (device int64) receives the number of distinct entries. */
+size_t gd_to_undirected_workspace_bytes(int64_t num_edges);
+int gd_to_undirected(const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t num_nodes,
+                     const int32_t* attr_a, const int32_t* attr_b, int64_t* out_row,
+                     int64_t* out_col, int32_t* out_a, int32_t* out_b, int64_t* out_count,
+                     void* workspace, size_t workspace_bytes, gd_stream_t stream);
 
 #ifdef __cplusplus
 }

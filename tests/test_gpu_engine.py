@@ -1,0 +1,56 @@
+"""GPU parity of the fused epoch engine (eager and CUDA-graph) against the oracle over several epochs."""
+import pytest
+import torch
+
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _oracle_run(shape, data, neg, epochs, dtype):
+    from oracle import unlearn as OU
+    om = U.oracle_model('gcn', shape, data, dtype=dtype)
+    d = data.clone()
+    d.x = data.x.to(dtype)
+    with torch.no_grad():
+        zo = om.get_original_embeddings(d.x, d.train_pos_edge_index[:, d.dr_mask])
+    opt = torch.optim.Adam([p for n, p in om.named_parameters() if 'del' in n], lr=1e-3)
+    hist = []
+    for _ in range(epochs):
+        loss, lr, ll, _ = OU.edge_form_loss(om, d, neg, zo)
+        loss.backward()
+        opt.step(); opt.zero_grad()
+        hist.append([float(loss), float(lr), float(ll)])
+    return om, zo, torch.tensor(hist, dtype=torch.float64)
+
+
+@pytest.mark.parametrize('graph,hoist', [(False, False), (True, False), (True, True)])
+def test_engine_loss_curve(lib, graph, hoist):
+    from gnndelete_b200 import models as M
+    from gnndelete_b200.engine import GCNDeleteEngine
+    shape, raw, df, data, neg = U.make_case('cora', 0.05)
+    epochs = 10
+    om, zo, hist = _oracle_run(shape, data, neg, epochs, torch.float64)
+    init = U.oracle_model('gcn', shape, data, dtype=torch.float32)       # same seed -> same initial weights
+    m = M.GCNDelete(U.args_for(shape), data.sdf_node_1hop_mask, data.sdf_node_2hop_mask)
+    m.load_state_dict(init.state_dict())
+    m = m.to(DEV)
+    eng = GCNDeleteEngine(m, data.clone().to(DEV), neg.to(DEV), z_ori=zo.float().to(DEV), hoist_layer1=hoist)
+    if graph:
+        eng.capture()
+    got = []
+    for _ in range(epochs):
+        got.append(eng.epoch().clone())
+    got = torch.stack(got).cpu().double()
+    # loss curve over 10 Adam steps; tolerance widened to 1e-4 because ten
+    # optimizer steps compound the fp32 rounding of the gradients
+    U.assert_close(got, hist, tol=1e-4, what='loss curve')
+    U.assert_close(m.deletion1.deletion_weight, om.deletion1.deletion_weight, tol=1e-4, what='W_del1 after training')
+    U.assert_close(m.deletion2.deletion_weight, om.deletion2.deletion_weight, tol=1e-4, what='W_del2 after training')
+
+
+def test_engine_first_step_tight(lib):
+    """One epoch at the 1e-5 bar: losses and both Del gradients."""
+    import __graft_entry__ as G
+    G.smoke()
