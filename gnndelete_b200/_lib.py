@@ -39,6 +39,15 @@ SIGNATURES = {
     'gd_gcn_dinv': (C.c_int, [_vp, _i64, _vp, _vp]),
     'gd_spmm_plan_build': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'gd_spmm': (C.c_int, [_csr_p, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _vp]),
+    'gd_gat_scores': (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    'gd_gat_fwd': (C.c_int, [_csr_p, _vp, _i64, _i32, _vp, _vp, _vp, _f32, _vp, _i64, _vp, _vp, _vp]),
+    'gd_gat_bwd_dst': (C.c_int, [_csr_p, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _f32,
+                                 _vp, _vp, _vp, _vp]),
+    'gd_gat_bwd_src': (C.c_int, [_csr_p, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    'gd_rgcn_norm': (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    'gd_rgcn_conv': (C.c_int, [_csr_p, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
+    'gd_permute_f32': (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    'gd_gather_rows': (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i32, _vp, _i64, _vp, _vp]),
     'gd_gemm_rows': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
     'gd_gemm_tn_workspace_bytes': (_sz, [_i64, _i32, _i32]),
     'gd_gemm_tn_rows': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),

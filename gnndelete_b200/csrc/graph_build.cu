@@ -26,7 +26,7 @@ __global__ void make_keys_kernel(const int64_t* __restrict__ src, const int64_t*
         } else {
             int64_t v = i - E;
             keys[i] = (v * R) * N + v;
-            vals[i] = -1;
+            vals[i] = (int32_t)(E + v);   // inserted self loop of node v
         }
     }
 }

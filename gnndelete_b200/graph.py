@@ -114,18 +114,50 @@ class GraphPlan:
         self.fwd = build_csr(src, dst, num_nodes, self_loops, edge_type, num_rel)
         self.bwd = None
         self.symmetric = False
+        self.bwd_eid = None      # edge ids in TRANSPOSED order (differs from fwd.eid even when symmetric)
         if need_bwd:
             bwd = build_csr(dst, src, num_nodes, self_loops, edge_type, num_rel)
+            self.bwd_eid = bwd.eid
             if edge_type is None and bwd.nnz == self.fwd.nnz and torch.equal(bwd.rowptr, self.fwd.rowptr) \
                     and torch.equal(bwd.col, self.fwd.col):
                 self.symmetric = True
                 self.bwd = self.fwd
             else:
                 self.bwd = bwd
+        self._tinv = None
         self.dinv = None
         if gcn_norm:
             self.dinv = torch.empty(self.num_nodes, dtype=torch.float32, device=src.device)
             L.call('gd_gcn_dinv', L.ptr(self.fwd.rowptr), self.num_nodes, L.ptr(self.dinv), L.stream())
+
+
+def _tinv_of(plan):
+    """fwd CSR position -> position of the same edge in the transposed CSR (edge-valued
+    backward passes write per-edge values straight into transposed order)."""
+    if plan._tinv is None:
+        n_ids = int(max(plan.fwd.eid.max().item(), plan.bwd_eid.max().item())) + 1 if plan.fwd.nnz else 0
+        inv_bwd = invert_perm(plan.bwd_eid, max(n_ids, 1))
+        plan._tinv = inv_bwd[plan.fwd.eid.long()].contiguous()
+    return plan._tinv
+
+
+GraphPlan.tinv = property(_tinv_of)
+
+
+def _rgcn_weights_of(plan):
+    """(entry weights of the forward CSR, the same weights in transposed-CSR order):
+    1 / |N_r(i)| per entry — RGCNConv's per-(destination, relation) mean."""
+    if getattr(plan, '_rgcn_w', None) is None:
+        dev = plan.fwd.rowptr.device
+        w = torch.empty(max(plan.fwd.nnz, 1), dtype=torch.float32, device=dev)
+        L.call('gd_rgcn_norm', L.ptr(plan.fwd.rowptr), L.ptr(plan.fwd.rel), plan.num_nodes, L.ptr(w), L.stream())
+        wt = torch.empty_like(w)
+        L.call('gd_permute_f32', L.ptr(w), L.ptr(plan.tinv), plan.fwd.nnz, L.ptr(wt), L.stream())
+        plan._rgcn_w = (w, wt)
+    return plan._rgcn_w
+
+
+GraphPlan.rgcn_weights = property(_rgcn_weights_of)
 
 
 class PlanCache:
@@ -150,7 +182,8 @@ class PlanCache:
             return hit
         for ei, et, k, plan in self._entries:
             if k == key and ei.shape == edge_index.shape and ei.device == edge_index.device \
-                    and torch.equal(ei, edge_index) and (et is None or torch.equal(et, edge_type)):
+                    and torch.equal(ei, edge_index) and (et is None) == (edge_type is None) \
+                    and (et is None or (et.shape == edge_type.shape and torch.equal(et, edge_type))):
                 self._by_id[ident] = plan
                 return plan
         plan = builder()

@@ -76,6 +76,28 @@ class GINConv(nn.Module):
         self._eps_host = float(self.eps.detach().cpu().reshape(-1)[0])
 
 
+class GATConv(nn.Module):
+    """PyG ``GATConv(in, out)`` defaults ``heads=1, negative_slope=0.2, dropout=0,
+    add_self_loops=True`` (gat.py:11-12).  ``lin_src`` and ``lin_dst`` are the same module
+    (PyG 2.0–2.2 with an int ``in_channels``), hence both state-dict keys."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.negative_slope = 0.2
+        self.lin_src = _Weight(in_channels, out_channels)
+        self.lin_dst = self.lin_src
+        self.att_src = nn.Parameter(_glorot_(torch.empty(1, 1, out_channels)))
+        self.att_dst = nn.Parameter(_glorot_(torch.empty(1, 1, out_channels)))
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+
+    def forward(self, x, edge_index, relu_in=False, frozen=False, plan=None):
+        plan = plan or plan_for(edge_index, x.size(0), 'gat')
+        h = ops.LinearFn.apply(x, _p(self.lin_src.weight, frozen), None, None, relu_in)
+        return ops.GATAggregateFn.apply(h, _p(self.att_src, frozen), _p(self.att_dst, frozen),
+                                        _p(self.bias, frozen), plan, self.negative_slope)
+
+
 # -------------------------------------------------------------------- encoders
 class _Encoder(nn.Module):
     """conv1 -> ReLU -> conv2, no dropout (gcn.py:15-24).  The ReLU is folded into the
@@ -103,6 +125,10 @@ class _Encoder(nn.Module):
 
 class GCN(_Encoder):
     conv_cls = GCNConv
+
+
+class GAT(_Encoder):
+    conv_cls = GATConv
 
 
 class GIN(_Encoder):
@@ -173,4 +199,89 @@ def _make_delete(base):
 
 
 GCNDelete = _make_delete(GCN)
+GATDelete = _make_delete(GAT)
 GINDelete = _make_delete(GIN)
+
+
+# ------------------------------------------------------------------ knowledge graphs
+class RGCNConv(nn.Module):
+    """PyG ``RGCNConv(in, out, num_relations, num_blocks=B|None)``, ``aggr='mean'``
+    (rgcn.py:17-22): keys ``weight`` ([R, in, out] or [R, B, in/B, out/B]), ``root``, ``bias``."""
+
+    def __init__(self, in_channels, out_channels, num_relations, num_blocks=None):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.num_relations, self.num_blocks = num_relations, num_blocks
+        if num_blocks is None:
+            self.weight = nn.Parameter(_glorot_(torch.empty(num_relations, in_channels, out_channels)))
+        else:
+            self.weight = nn.Parameter(_glorot_(torch.empty(num_relations, num_blocks, in_channels // num_blocks,
+                                                            out_channels // num_blocks)))
+        self.root = nn.Parameter(_glorot_(torch.empty(in_channels, out_channels)))
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+
+    def forward(self, x, edge_index, edge_type, relu_in=False, frozen=False, plan=None):
+        plan = plan or plan_for(edge_index, x.size(0), 'rgcn', edge_type, self.num_relations)
+        if relu_in:
+            x = ops.ReLUFn.apply(x)
+        return ops.RGCNConvFn.apply(x, _p(self.weight, frozen), _p(self.root, frozen), _p(self.bias, frozen), plan)
+
+
+class RGCN(nn.Module):
+    """``framework/models/rgcn.py:9-47``: embedding -> RGCNConv -> ReLU -> RGCNConv, DistMult
+    decoder ``sum_d h_d W[r]_d t_d``; ``num_blocks = 4`` iff ``num_edge_type > 20``."""
+
+    def __init__(self, args, num_nodes, num_edge_type, **kwargs):
+        super().__init__()
+        self.args = args
+        self.num_edge_type = num_edge_type
+        self.node_emb = nn.Embedding(num_nodes, args.in_dim)
+        blocks = 4 if num_edge_type > 20 else None
+        self.conv1 = RGCNConv(args.in_dim, args.hidden_dim, num_edge_type * 2, num_blocks=blocks)
+        self.conv2 = RGCNConv(args.hidden_dim, args.out_dim, num_edge_type * 2, num_blocks=blocks)
+        self.relu = nn.ReLU()
+        self.W = nn.Parameter(torch.empty(num_edge_type, args.out_dim))
+        nn.init.xavier_uniform_(self.W, gain=nn.init.calculate_gain('relu'))
+
+    def embed(self, x):
+        out, status = ops.gather_rows(self.node_emb.weight.detach(), x)
+        return out
+
+    def forward(self, x, edge, edge_type, return_all_emb=False):
+        x = self.embed(x)
+        x1 = self.conv1(x, edge, edge_type)
+        x2 = self.conv2(x1, edge, edge_type, relu_in=True)
+        if return_all_emb:
+            return x1, x2
+        return x2
+
+    def decode(self, z, edge_index, edge_type):
+        pairs = PairPlan(edge_index[0], edge_index[1], z.size(0), rel_weight=self.W.detach().contiguous(),
+                         pair_rel=edge_type.to(torch.int32).contiguous())
+        return ops.PairDecodeFn.apply(z, pairs)
+
+
+class RGCNDelete(RGCN):
+    """``deletion.py:135-163``."""
+
+    def __init__(self, args, num_nodes, num_edge_type, mask_1hop=None, mask_2hop=None, **kwargs):
+        super().__init__(args, num_nodes, num_edge_type)
+        self.deletion1 = DeletionLayer(args.hidden_dim, mask_1hop)
+        self.deletion2 = DeletionLayer(args.out_dim, mask_2hop)
+        self.node_emb.requires_grad = False
+        self.conv1.requires_grad = False
+        self.conv2.requires_grad = False
+
+    def forward(self, x, edge_index, edge_type, mask_1hop=None, mask_2hop=None, return_all_emb=False):
+        with torch.no_grad():
+            x = self.embed(x)
+            x1 = self.conv1(x, edge_index, edge_type, frozen=True)
+        x1 = self.deletion1(x1, mask_1hop)
+        x2 = self.conv2(x1, edge_index, edge_type, relu_in=True, frozen=True)
+        x2 = self.deletion2(x2, mask_2hop)
+        if return_all_emb:
+            return x1, x2
+        return x2
+
+    def get_original_embeddings(self, x, edge_index, edge_type, return_all_emb=False):
+        return RGCN.forward(self, x, edge_index, edge_type, return_all_emb)

@@ -217,3 +217,110 @@ class PairDecodeFn(torch.autograd.Function):
             raise NotImplementedError('DistMult decode backward is not on the unlearning hot path')
         val = glogits.contiguous()[pairs.inc_pair.long()]
         return spmm(pairs.inc, z, val=val), None
+
+
+def rgcn_conv(plan, x, weight, root, bias, transposed=False, out=None):
+    """One ``gd_rgcn_conv`` call; ``transposed`` = gradient w.r.t. the layer input."""
+    x = _f32(x)
+    weight = weight.detach().contiguous()
+    root = root.detach().contiguous()
+    if weight.dim() == 4:
+        num_rel, blocks, ib, ob = weight.shape
+        in_dim, out_dim = blocks * ib, blocks * ob
+    else:
+        num_rel, in_dim, out_dim = weight.shape
+        blocks = 1
+    w_fwd, w_bwd = plan.rgcn_weights
+    csr = plan.bwd if transposed else plan.fwd
+    fout = in_dim if transposed else out_dim
+    if out is None:
+        out = torch.empty(x.shape[0], fout, dtype=torch.float32, device=x.device)
+    b = None if (bias is None or transposed) else bias.detach().contiguous()
+    L.call('gd_rgcn_conv', csr.ref, L.ptr(csr.rel), L.ptr(w_bwd if transposed else w_fwd), L.ptr(x), x.stride(0),
+           L.ptr(weight), L.ptr(root), L.ptr(b), num_rel, blocks, in_dim, out_dim, int(transposed), L.ptr(out),
+           out.stride(0), L.stream())
+    return out
+
+
+def gather_rows(src, idx):
+    """``src[idx]`` (nn.Embedding lookup) with range checking on the device."""
+    src = _f32(src)
+    idx = idx.contiguous()
+    out = torch.empty(idx.numel(), src.shape[1], dtype=torch.float32, device=src.device)
+    status = torch.zeros(1, dtype=torch.int32, device=src.device)
+    L.call('gd_gather_rows', L.ptr(src), src.stride(0), src.shape[0], L.ptr(idx, 'i64'), idx.numel(), src.shape[1],
+           L.ptr(out), out.stride(0), L.ptr(status), L.stream())
+    return out, status
+
+
+class RGCNConvFn(torch.autograd.Function):
+    """RGCNConv forward; differentiable w.r.t. the input features only (relation weights,
+    root and bias are frozen on the Del path)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, root, bias, plan):
+        ctx.plan = plan
+        ctx.save_for_backward(weight, root)
+        return rgcn_conv(plan, x, weight, root, bias)
+
+    @staticmethod
+    def backward(ctx, gout):
+        if any(ctx.needs_input_grad[1:4]):
+            raise NotImplementedError('gradients of the RGCN relation weights are outside the Del hot path')
+        if not ctx.needs_input_grad[0]:
+            return (None,) * 5
+        weight, root = ctx.saved_tensors
+        return rgcn_conv(ctx.plan, gout.contiguous(), weight, root, None, transposed=True), None, None, None, None
+
+
+class GATAggregateFn(torch.autograd.Function):
+    """out_i = sum_k softmax_i(LeakyReLU(a_src[k] + a_dst[i])) h_k + bias over the self-looped
+    CSR (GATConv heads=1).  Differentiable w.r.t. ``h`` only — on the Del path the attention
+    vectors and bias are frozen."""
+
+    @staticmethod
+    def forward(ctx, h, att_src, att_dst, bias, plan, slope):
+        h = _f32(h)
+        n, c = h.shape
+        dev = h.device
+        a_src = torch.empty(n, dtype=torch.float32, device=dev)
+        a_dst = torch.empty(n, dtype=torch.float32, device=dev)
+        att_src = att_src.detach().reshape(-1).contiguous()
+        att_dst = att_dst.detach().reshape(-1).contiguous()
+        L.call('gd_gat_scores', L.ptr(h), h.stride(0), n, c, L.ptr(att_src), L.ptr(att_dst), L.ptr(a_src),
+               L.ptr(a_dst), L.stream())
+        out = torch.empty(n, c, dtype=torch.float32, device=dev)
+        rowmax = torch.empty(n, dtype=torch.float32, device=dev)
+        rowden = torch.empty(n, dtype=torch.float32, device=dev)
+        b = None if bias is None else bias.detach().contiguous()
+        L.call('gd_gat_fwd', plan.fwd.ref, L.ptr(h), h.stride(0), c, L.ptr(a_src), L.ptr(a_dst), L.ptr(b),
+               float(slope), L.ptr(out), out.stride(0), L.ptr(rowmax), L.ptr(rowden), L.stream())
+        ctx.plan, ctx.slope = plan, float(slope)
+        ctx.save_for_backward(h, att_src, att_dst, a_src, a_dst, rowmax, rowden, out, b if b is not None else h.new_empty(0))
+        ctx.has_bias = b is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        h, att_src, att_dst, a_src, a_dst, rowmax, rowden, out, b = ctx.saved_tensors
+        if any(ctx.needs_input_grad[1:4]):
+            raise NotImplementedError('gradients of the GAT attention vectors / bias are outside the Del hot path')
+        if not ctx.needs_input_grad[0]:
+            return (None,) * 6
+        plan = ctx.plan
+        gout = gout.contiguous()
+        n, c = h.shape
+        dev = h.device
+        nnz = plan.fwd.nnz
+        alpha_t = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+        dpre_t = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+        da_dst = torch.empty(n, dtype=torch.float32, device=dev)
+        da_src = torch.empty(n, dtype=torch.float32, device=dev)
+        dh = torch.empty(n, c, dtype=torch.float32, device=dev)
+        L.call('gd_gat_bwd_dst', plan.fwd.ref, L.ptr(plan.tinv), L.ptr(h), h.stride(0), c, L.ptr(a_src),
+               L.ptr(a_dst), L.ptr(rowmax), L.ptr(rowden), L.ptr(gout), gout.stride(0), L.ptr(out), out.stride(0),
+               L.ptr(b) if ctx.has_bias else None, ctx.slope, L.ptr(alpha_t), L.ptr(dpre_t), L.ptr(da_dst),
+               L.stream())
+        L.call('gd_gat_bwd_src', plan.bwd.ref, L.ptr(alpha_t), L.ptr(dpre_t), L.ptr(gout), gout.stride(0), c,
+               L.ptr(att_src), L.ptr(att_dst), L.ptr(da_dst), L.ptr(dh), dh.stride(0), L.ptr(da_src), L.stream())
+        return dh, None, None, None, None, None

@@ -73,8 +73,8 @@ size_t gd_csr_workspace_bytes(int64_t num_edges, int64_t num_nodes);
  *   self_loops = 0: entries kept as they are (GINConv, RGCNConv, loss incidence).
  * `rel` (nullable, values in [0, num_rel)) adds the relation as a secondary sort key
  * and is written per entry to `rel_out`.
- * `eid[k]` = column of the input COO that landed at CSR position k, or -1 for an
- * inserted self loop.  nnz = rowptr[num_nodes]; `col`/`eid`/`rel_out` must hold
+ * `eid[k]` = column of the input COO that landed at CSR position k, or
+ * num_edges + v for the inserted self loop of node v.  nnz = rowptr[num_nodes]; `col`/`eid`/`rel_out` must hold
  * num_edges (+ num_nodes when self_loops) entries.
  * `status` (device int32[2]) receives {nnz, number of out-of-range endpoints}. */
 int gd_csr_from_coo(const int64_t* src, const int64_t* dst, const int64_t* rel, int64_t num_edges,
@@ -109,6 +109,57 @@ int gd_spmm_plan_build(const int32_t* rowptr, int64_t num_rows, int32_t seg_len,
 int gd_spmm(const gd_csr_t* csr, const float* val, const float* col_scale, const float* row_scale,
             const float* x, int64_t ldx, int32_t feat, float self_coef, const float* bias,
             float* out, int64_t ldo, float* scratch, gd_stream_t stream);
+
+/* GATConv(heads=1) edge-softmax aggregation (gat.py:11-12; defaults negative_slope=0.2,
+ * add_self_loops=True — the CSR must be built with self_loops=1):
+ *   a_src[k] = <h_k, att_src>, a_dst[i] = <h_i, att_dst>                 (gd_gat_scores)
+ *   e_ik = LeakyReLU(a_src[k] + a_dst[i]);  alpha = softmax over the row (+1e-16 in the
+ *   denominator);  out_i = sum_k alpha_ik h_k + bias                     (gd_gat_fwd)
+ * rowmax / rowden (row max and softmax denominator) are saved for the backward.
+ * Backward w.r.t. h (the attention parameters are frozen on the Del path):
+ *   gd_gat_bwd_dst: per edge alpha and d e_ik * LeakyReLU', written at the entry's position
+ *                   in the transposed CSR (`tinv[fwd position] = transposed position`),
+ *                   and d a_dst[i];
+ *   gd_gat_bwd_src: dh_k = sum_i alpha_ik g_i + d a_src[k] att_src + d a_dst[k] att_dst.
+ * out_channels must be 32, 64 or 128. */
+int gd_gat_scores(const float* h, int64_t ldh, int64_t num_nodes, int32_t channels,
+                  const float* att_src, const float* att_dst, float* a_src, float* a_dst,
+                  gd_stream_t stream);
+int gd_gat_fwd(const gd_csr_t* csr, const float* h, int64_t ldh, int32_t channels, const float* a_src,
+               const float* a_dst, const float* bias, float negative_slope, float* out, int64_t ldo,
+               float* rowmax, float* rowden, gd_stream_t stream);
+int gd_gat_bwd_dst(const gd_csr_t* csr, const int32_t* tinv, const float* h, int64_t ldh,
+                   int32_t channels, const float* a_src, const float* a_dst, const float* rowmax,
+                   const float* rowden, const float* gout, int64_t ldg, const float* out, int64_t ldo,
+                   const float* bias, float negative_slope, float* alpha_t, float* dpre_t,
+                   float* da_dst, gd_stream_t stream);
+int gd_gat_bwd_src(const gd_csr_t* csr_t, const float* alpha_t, const float* dpre_t, const float* gout,
+                   int64_t ldg, int32_t channels, const float* att_src, const float* att_dst,
+                   const float* da_dst, float* dh, int64_t lddh, float* da_src, gd_stream_t stream);
+
+/* RGCNConv(in, out, R, num_blocks=B|None), aggr='mean', root_weight, bias (rgcn.py:17-22):
+ *   out_i = sum_r mean_{k in N_r(i)} x_k . W_r + x_i . root + bias
+ * on a CSR built with `rel` as secondary key (entries of a row sorted by relation).
+ *   gd_rgcn_norm : entry_weight[k] = 1 / |N_rel(k)(dst(k))|  (the per-(dst, relation) mean);
+ *   gd_rgcn_conv : one kernel for all relations (replaces PyG's Python loop over R masked
+ *                  propagate calls).  weight is [R, B, in/B, out/B] (B = 1: dense
+ *                  [R, in, out]), root [in, out].  transposed = 1 computes the gradient
+ *                  w.r.t. x: pass the TRANSPOSED CSR, its relation array, the forward entry
+ *                  weights permuted to transposed order (gd_permute_f32 with tinv) and
+ *                  x = d out; W_r^T / root^T are applied, bias is ignored.
+ * in / out must be in {32, 64, 128}. */
+int gd_rgcn_norm(const int32_t* rowptr, const int32_t* rel, int64_t num_rows, float* entry_weight,
+                 gd_stream_t stream);
+int gd_rgcn_conv(const gd_csr_t* csr, const int32_t* rel, const float* entry_weight, const float* x,
+                 int64_t ldx, const float* weight, const float* root, const float* bias,
+                 int32_t num_rel, int32_t num_blocks, int32_t in_dim, int32_t out_dim,
+                 int32_t transposed, float* out, int64_t ldo, gd_stream_t stream);
+/* dst[perm[i]] = src[i] */
+int gd_permute_f32(const float* src, const int32_t* perm, int64_t n, float* dst, gd_stream_t stream);
+/* dst[i,:] = src[idx[i],:]  — nn.Embedding lookup `node_emb(x)` (rgcn.py:30); `status`
+ * (device int32) counts out-of-range indices. */
+int gd_gather_rows(const float* src, int64_t lds, int64_t src_rows, const int64_t* idx, int64_t m,
+                   int32_t feat, float* dst, int64_t ldd, int32_t* status, gd_stream_t stream);
 
 /* ------------------------------------------------------ dense contractions (2)
  * out[r(i),:] = epi( pro(a[r(i),:]) . B ),  i in [0,m),  r(i) = rows ? rows[i] : i

@@ -30,10 +30,11 @@ def test_csr_build_bit_exact(lib, case):
     assert torch.equal(csr.col.cpu().long(), order % n)
     deg = torch.bincount(full[1], minlength=n)
     assert torch.equal(csr.rowptr.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long), deg.cumsum(0)]))
-    # eid maps back to the input column (or -1 for inserted loops)
+    # eid maps back to the input column (or E + v for the inserted loop of node v)
     eid = csr.eid.cpu().long()
-    real = eid >= 0
+    real = eid < ei.shape[1]
     assert int((~real).sum()) == n
+    assert torch.equal(eid[~real] - ei.shape[1], csr.col.cpu().long()[~real])
     assert torch.equal(ei[0][eid[real]], csr.col.cpu().long()[real])
 
 

@@ -46,7 +46,7 @@ def oracle_model(gnn, shape, data, dtype=torch.float32, seed=0, delete=True, **k
     torch.manual_seed(seed)
     cls = (OM.DELETE_MODELS if delete else OM.MODELS)[gnn]
     if delete:
-        m = cls(args_for(shape), data.sdf_node_1hop_mask, data.sdf_node_2hop_mask, **kw)
+        m = cls(args_for(shape), mask_1hop=data.sdf_node_1hop_mask, mask_2hop=data.sdf_node_2hop_mask, **kw)
     else:
         m = cls(args_for(shape), **kw)
     randomize(m, seed)
