@@ -178,7 +178,10 @@ class DeletionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, rows, comp):
         x = _f32(x)
-        ctx.save_for_backward(x, weight)
+        # like autograd's matmul, keep W only if the input needs a gradient: the KG trainer
+        # steps deletion1's optimizer between the two backward passes of one forward
+        # (gnndelete_nodeemb.py:788-796), which must not invalidate this node
+        ctx.save_for_backward(x, weight if ctx.needs_input_grad[0] else None)
         ctx.rows, ctx.comp = rows, comp
         out = torch.empty_like(x)
         gemm_rows(x, weight.detach(), False, out=out, rows=rows)

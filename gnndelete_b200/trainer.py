@@ -202,3 +202,77 @@ class GNNDeleteTrainer(Trainer):
                     optimizer.state[q] = {'step': st['step'].detach().cpu().reshape(()).clone(),
                                           'exp_avg': st['m'], 'exp_avg_sq': st['v']}
         return optimizer.state_dict()
+
+
+class KGGNNDeleteNodeembTrainer(Trainer):
+    """``framework/trainer/gnndelete_nodeemb.py:659-846`` (``KGGNNDeleteNodeembTrainer``),
+    the route ``--gnn rgcn --unlearning_model gnndelete[_nodeemb]`` dispatches to.
+
+    Per step (:749-798): forward on the ``dr_mask`` edges with the ``*_non_df`` node masks,
+    original embeddings under ``no_grad``, ``negative_sampling_kg`` on the forward-direction
+    Df triples, per-layer node-embedding MSEs, then TWO backward passes and TWO Adam steps
+    (``optimizer`` is the ``[optimizer1, optimizer2]`` pair of delete_gnn.py:221-226).
+    The schedule is reproduced literally — including that ``loss2.backward()`` leaves its
+    deletion1 gradient in ``.grad`` until the next step's ``optimizer[0].step()``.  The whole
+    graph is the batch (no GraphSAINT sampling); the frozen original embeddings are
+    computed once instead of once per step."""
+
+    log_every = 10
+
+    def eval(self, model, data, stage='val', pred_all=False, num_df_resamples=500):
+        raise NotImplementedError('KG evaluation (KGTrainer.eval, base.py:394-692) is outside the accelerated hot path')
+
+    def train(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
+        from .kg import negative_sampling_kg
+        if not isinstance(optimizer, (list, tuple)) or len(optimizer) != 2:
+            raise ValueError('expects the [optimizer1, optimizer2] pair built for *layerwise loss types '
+                             '(delete_gnn.py:221-226)')
+        dev = torch.device('cuda')
+        model = model.to(dev)
+        data = data.to(dev)
+        F = torch.nn.functional
+        alpha = args.alpha
+        non_df = torch.ones(data.x.shape[0], dtype=torch.bool, device=dev)          # :723-727
+        non_df[data.directed_df_edge_index.flatten().unique()] = False
+        m1 = data.sdf_node_1hop_mask & non_df
+        m2 = data.sdf_node_2hop_mask & non_df
+        data.sdf_node_1hop_mask_non_df_mask, data.sdf_node_2hop_mask_non_df_mask = m1, m2
+        edge_index = data.edge_index[:, data.dr_mask].contiguous()                  # :749-750
+        edge_type = data.edge_type[data.dr_mask].contiguous()
+        pos_ei = data.edge_index[:, data.df_mask]                                    # :758-763
+        pos_et = data.edge_type[data.df_mask]
+        dec = pos_et < args.num_edge_type
+        dec_ei, dec_et = pos_ei[:, dec], pos_et[dec]
+        with torch.no_grad():                                                        # :754-755
+            z1o, z2o = model.get_original_embeddings(data.x, edge_index, edge_type, return_all_emb=True)
+        gen = torch.Generator(device=dev).manual_seed(getattr(args, 'random_seed', 42))
+        fixed_neg = getattr(data, 'neg_edge_index', None)
+        ring = []
+        for epoch in range(args.epochs):
+            model.train()
+            z1, z2 = model(data.x, edge_index, edge_type, m1, m2, return_all_emb=True)
+            neg = fixed_neg if fixed_neg is not None else negative_sampling_kg(dec_ei, dec_et, gen)
+            e1 = torch.cat([z1[dec_ei[0]], z1[dec_ei[1]]], 0)                        # :770-774
+            e1o = torch.cat([z1o[neg[0]], z1o[neg[1]]], 0)
+            e2 = torch.cat([z2[dec_ei[0]], z2[dec_ei[1]]], 0)
+            e2o = torch.cat([z2o[neg[0]], z2o[neg[1]]], 0)
+            loss_r1, loss_r2 = F.mse_loss(e1, e1o), F.mse_loss(e2, e2o)
+            loss_l1, loss_l2 = F.mse_loss(z1[m1], z1o[m1]), F.mse_loss(z2[m2], z2o[m2])
+            loss1 = alpha * loss_r1 + (1 - alpha) * loss_l1                          # :788-796
+            loss1.backward(retain_graph=True)
+            optimizer[0].step()
+            optimizer[0].zero_grad()
+            loss2 = alpha * loss_r2 + (1 - alpha) * loss_l2
+            loss2.backward(retain_graph=True)
+            optimizer[1].step()
+            optimizer[1].zero_grad()
+            ring.append(torch.stack([(loss1 + loss2).detach(), (loss_r1 + loss_r2).detach(),
+                                     (loss_l1 + loss_l2).detach()]))
+            if (epoch + 1) % self.log_every == 0 or epoch + 1 == args.epochs:
+                for i, v in enumerate(torch.stack(ring).cpu().tolist()):
+                    self.trainer_log['log'].append({'Epoch': epoch + 1 - len(ring) + i, 'train_loss': v[0],
+                                                    'loss_r': v[1], 'loss_l': v[2]})
+                ring = []
+        torch.save({'model_state': {k: v.to('cpu') for k, v in model.state_dict().items()}},
+                   os.path.join(args.checkpoint_dir, 'model_final.pt'))
+        return model

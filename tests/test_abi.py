@@ -1,0 +1,72 @@
+"""CPU: the C-ABI shared library builds for sm_100a, loads, and exports every symbol that
+include/gnndelete_b200.h declares (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'gnndelete_b200.h')
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(gd_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_header_declares_the_expected_groups():
+    syms = declared_symbols()
+    for must in ['gd_csr_from_coo', 'gd_spmm', 'gd_gat_fwd', 'gd_gat_bwd_dst', 'gd_gat_bwd_src', 'gd_rgcn_conv',
+                 'gd_gemm_rows', 'gd_gemm_tn_rows', 'gd_edge_loss_fwd', 'gd_khop_masks', 'gd_to_undirected',
+                 'gd_adam_step']:
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from gnndelete_b200 import _lib
+    exported = subprocess.run(['nm', '-D', '--defined-only', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    names = set(re.findall(r'\b(gd_[a-z0-9_]+)\b', exported))
+    missing = [s for s in declared_symbols() if s not in names]
+    assert not missing, f'declared in the header but not exported: {missing}'
+    # and the ctypes table covers exactly the header
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+
+
+def test_library_targets_sm_100a(lib):
+    from gnndelete_b200 import _lib
+    out = subprocess.run(['cuobjdump', '-lelf', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert 'sm_100a' in out, out
+
+
+def test_version_and_error_string(lib):
+    assert lib.gd_version() >= 100
+    assert isinstance(lib.gd_last_error(), bytes)
+    assert lib.gd_launch_count() >= 0
+    # pure host-side query functions are callable without a device
+    assert lib.gd_csr_workspace_bytes(1000, 100) > 0
+    assert lib.gd_gemm_tn_workspace_bytes(10_000, 128, 128) >= 128 * 128 * 4
+    assert lib.gd_khop_workspace_bytes(1 << 20) >= 3 * (1 << 20) // 8
+
+
+def test_no_cpu_fallback():
+    """Kernels refuse CPU tensors instead of silently computing on the host."""
+    import pytest
+    import torch
+    from gnndelete_b200 import _lib
+    with pytest.raises(RuntimeError):
+        _lib.ptr(torch.zeros(4))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'gnndelete_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'framework')):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
