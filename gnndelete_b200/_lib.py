@@ -22,7 +22,7 @@ class CsrStruct(C.Structure):
         ('num_rows', _i64), ('nnz', _i64), ('rowptr', _vp), ('col', _vp),
         ('seg_len', _i32), ('num_heavy', _i32), ('num_seg', _i32),
         ('heavy_row', _vp), ('heavy_seg_beg', _vp), ('heavy_nseg', _vp),
-        ('seg_row', _vp), ('seg_beg', _vp),
+        ('seg_row', _vp), ('seg_beg', _vp), ('seg_heavy', _vp), ('heavy_ticket', _vp), ('row_perm', _vp),
     ]
 
 
@@ -37,7 +37,7 @@ SIGNATURES = {
     'gd_csr_from_coo': (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'gd_invert_perm': (C.c_int, [_vp, _i64, _vp, _vp]),
     'gd_gcn_dinv': (C.c_int, [_vp, _i64, _vp, _vp]),
-    'gd_spmm_plan_build': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'gd_spmm_plan_build': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'gd_spmm': (C.c_int, [_csr_p, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _vp]),
     'gd_gat_scores': (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     'gd_gat_fwd': (C.c_int, [_csr_p, _vp, _i64, _i32, _vp, _vp, _vp, _f32, _vp, _i64, _vp, _vp, _vp]),
@@ -49,6 +49,8 @@ SIGNATURES = {
     'gd_permute_f32': (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     'gd_gather_rows': (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i32, _vp, _i64, _vp, _vp]),
     'gd_gemm_rows': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
+    'gd_gemm_rows_tc_supported': (C.c_int, [_i32, _i32, _i64, _i64]),
+    'gd_gemm_rows_tc': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
     'gd_gemm_tn_workspace_bytes': (_sz, [_i64, _i32, _i32]),
     'gd_gemm_tn_rows': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     'gd_copy_rows': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),

@@ -1,0 +1,366 @@
+// Gathered-row GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+//   out[r(i), :] = epi( pro(a[r(i), :]) . B )        m rows (gathered through `rows`), K, N <= 128
+//
+// These contractions (X.W^T, the DeletionLayer's x[mask].W_del, their input gradients) have an
+// arithmetic intensity of 21-32 flop/B: HBM-bound on tensor cores, FMA-bound on CUDA cores.
+// fp32 parity (1e-5) is kept with the 3xTF32 split  a = a_hi + a_lo, b = b_hi + b_lo,
+//   a.b ~= a_hi.b_hi + a_lo.b_hi + a_hi.b_lo      (a_hi = a rounded to tf32)
+// which costs 3 MMAs per k-step and still leaves the kernel memory-bound.
+//
+// Structure (one persistent CTA per SM, 288 threads):
+//   warps 0-3  producers : gather 128 rows x 32 k (one 128-byte swizzle row each) per stage with
+//                          128-bit loads, optional ReLU, hi/lo split, st.shared in the canonical
+//                          K-major SWIZZLE_128B layout, fence.proxy.async, arrive on full[stage];
+//   warp  8    MMA issue : one elected lane waits full[stage], issues 12 tcgen05.mma
+//                          (M=128, N, K=8, kind::tf32) per stage, tcgen05.commit -> empty[stage],
+//                          and -> tmem_full[acc] after the last stage of a tile;
+//   warps 4-7  epilogue  : tcgen05.ld the 128 x N fp32 accumulator (thread = row), bias / row
+//                          scale / ReLU / gate, 128-bit stores to the (scattered) output rows,
+//                          arrive on tmem_empty[acc].
+// B (<= 128 x 128, hi and lo) is staged once per CTA and stays resident in shared memory; the
+// accumulator is double buffered in TMEM so the epilogue of tile i overlaps the loads and MMAs
+// of tile i+1.
+#include "common.cuh"
+
+namespace gd {
+namespace tc {
+
+constexpr int BM = 128;            // rows per tile (UMMA M)
+constexpr int KC = 32;             // k per stage: 32 tf32 = one 128-byte swizzle row
+constexpr int MAX_STAGES = 4;      // A ring depth (runtime: as many as shared memory allows)
+constexpr int TILE_BYTES = BM * 128;            // one [128 rows x 128 B] operand tile
+constexpr int NUM_THREADS = 288;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100): rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address            bits [0,14)
+    d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset       bits [32,46)
+    d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                             // layout: SWIZZLE_128B
+    return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// hi = v rounded to tf32 (10-bit mantissa), lo = the remainder rounded to tf32
+__device__ __forceinline__ float round_tf32(float v) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));     // round-to-nearest: unbiased, unlike the
+    return __uint_as_float(u);                               // truncation the MMA applies to raw fp32
+}
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+    hi = round_tf32(v);
+    lo = round_tf32(v - hi);
+}
+__device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
+    split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
+    split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+}
+// byte offset of 16-byte chunk j of row r inside a [rows x 128 B] SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t swz(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
+
+struct Args {
+    const float* a; int64_t lda;
+    const int32_t* rows; int64_t m; int k;
+    const float* b; int b_is_nk; int n;
+    const float* bias; const float* out_scale; const float* gate; int64_t ldgate;
+    int relu_in, relu_out;
+    float* out; int64_t ldo;
+    int num_tiles;
+    int stages;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rows_tc_kernel(const Args g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve (all operand tiles 1024-byte aligned)
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int kchunks = (g.k + KC - 1) / KC;
+    const int b_tile = g.n * 128;                                  // bytes of one [n x 128 B] B tile
+    uint8_t* b_hi = smem;                                          // [kchunks][n x 128 B]
+    uint8_t* b_lo = b_hi + kchunks * b_tile;
+    uint8_t* a_ring = b_lo + kchunks * b_tile;                     // [stages][hi 16 KB | lo 16 KB]
+    a_ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a_ring) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
+    const int STAGES = g.stages;
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ int32_t row_id[2][BM];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // per tile: main accumulator (a_hi.b_hi) + correction accumulator (a_lo.b_hi + a_hi.b_lo), double buffered.
+    // The tensor core truncates when it adds into the fp32 accumulator; keeping the 2^-11-scaled correction
+    // terms out of the main chain cuts that (biased) rounding from 3 to 1 accumulation per k-step.
+    const uint32_t tmem_cols = g.n <= 32 ? 128 : (g.n <= 64 ? 256 : 512);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"(tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // ---- stage B once (hi / lo, K-major SWIZZLE_128B), all threads
+    for (int idx = tid; idx < kchunks * g.n * 8; idx += NUM_THREADS) {
+        const int c = idx / (g.n * 8), rem = idx - c * g.n * 8;
+        const int nn = rem >> 3, j = rem & 7;
+        float4 v;
+        float* vp = reinterpret_cast<float*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int kk = c * KC + j * 4 + e;
+            vp[e] = kk < g.k ? (g.b_is_nk ? __ldg(g.b + (int64_t)nn * g.k + kk) : __ldg(g.b + (int64_t)kk * g.n + nn)) : 0.f;
+        }
+        float4 hi, lo;
+        split4(v, hi, lo);
+        *reinterpret_cast<float4*>(b_hi + c * b_tile + swz(nn, j)) = hi;
+        *reinterpret_cast<float4*>(b_lo + c * b_tile + swz(nn, j)) = lo;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp < 4) {
+        // ================================ producers ================================
+        const int j = tid & 7, r0 = tid >> 3;                      // 8 threads per row, 16 rows per pass
+        uint32_t stage = 0, phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+            const int64_t m0 = (int64_t)tile * BM;
+            // row ids of this tile (double buffered: a fast producer thread may already be one tile ahead)
+            int32_t* rid = row_id[it & 1];
+            {
+                const int64_t i = m0 + tid;
+                rid[tid] = i < g.m ? (g.rows ? __ldg(g.rows + i) : (int32_t)i) : -1;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");       // producers only
+            const float* src[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const int32_t r = rid[r0 + 16 * p];
+                src[p] = r >= 0 ? g.a + (int64_t)r * g.lda + j * 4 : nullptr;
+            }
+            for (int c = 0; c < kchunks; ++c) {
+                const int kbase = c * KC + j * 4;
+                float4 v[8];
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    v[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (src[p] != nullptr) {
+                        if (kbase + 4 <= g.k) v[p] = __ldg(reinterpret_cast<const float4*>(src[p] + c * KC));
+                        else {
+                            float* vp = reinterpret_cast<float*>(&v[p]);
+                            for (int e = 0; e < 4; ++e) if (kbase + e < g.k) vp[e] = __ldg(src[p] + c * KC + e);
+                        }
+                    }
+                }
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* ahi = a_ring + stage * 2 * TILE_BYTES;
+                uint8_t* alo = ahi + TILE_BYTES;
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    float4 x = v[p];
+                    if (g.relu_in) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                    float4 hi, lo;
+                    split4(x, hi, lo);
+                    const uint32_t o = swz(r0 + 16 * p, j);
+                    *reinterpret_cast<float4*>(ahi + o) = hi;
+                    *reinterpret_cast<float4*>(alo + o) = lo;
+                }
+                fence_proxy_async();
+                mbar_arrive(&full_bar[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 8) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(g.n);
+            uint32_t stage = 0, phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + acc * 2 * g.n, dc = d + g.n;
+                for (int c = 0; c < kchunks; ++c) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t ahi = smem_u32(a_ring + stage * 2 * TILE_BYTES), alo = ahi + TILE_BYTES;
+                    const uint32_t bhi = smem_u32(b_hi + c * b_tile), blo = smem_u32(b_lo + c * b_tile);
+#pragma unroll
+                    for (int ks = 0; ks < KC / 8; ++ks) {
+                        const uint64_t da_hi = make_desc(ahi + ks * 32), da_lo = make_desc(alo + ks * 32);
+                        const uint64_t db_hi = make_desc(bhi + ks * 32), db_lo = make_desc(blo + ks * 32);
+                        umma_tf32(dc, da_lo, db_hi, idesc, (c | ks) != 0);
+                        umma_tf32(dc, da_hi, db_lo, idesc, 1);
+                        umma_tf32(d, da_hi, db_hi, idesc, (c | ks) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);                // frees the smem stage when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);                      // accumulator of this tile complete
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================ epilogue ================================
+        const int q = warp & 3;                                    // TMEM lane quarter of this warp
+        const int lr = q * 32 + lane;                              // row inside the tile == TMEM lane
+        int it = 0;
+        for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const int64_t gi = (int64_t)tile * BM + lr;
+            const int32_t r = gi < g.m ? (g.rows ? __ldg(g.rows + gi) : (int32_t)gi) : -1;
+            const float sc = (r >= 0 && g.out_scale) ? __ldg(g.out_scale + r) : 1.0f;
+            for (int c0 = 0; c0 < g.n; c0 += 32) {
+                uint32_t v[32], vc[32];
+                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * g.n + c0;
+                tmem_ld32(t0, v);
+                tmem_ld32(t0 + g.n, vc);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(vc[e]));
+                if (r >= 0) {
+                    float* op = g.out + (int64_t)r * g.ldo + c0;
+                    const float* gp = g.gate ? g.gate + (int64_t)r * g.ldgate + c0 : nullptr;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4) {
+                        if (c0 + e >= g.n) break;
+                        float o[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            float x = __uint_as_float(v[e + u]);
+                            if (g.bias) x += __ldg(g.bias + c0 + e + u);
+                            x *= sc;
+                            if (g.relu_out) x = fmaxf(x, 0.f);
+                            o[u] = x;
+                        }
+                        if (gp) {
+                            const float4 gt = __ldg(reinterpret_cast<const float4*>(gp + e));
+                            if (!(gt.x > 0.f)) o[0] = 0.f;
+                            if (!(gt.y > 0.f)) o[1] = 0.f;
+                            if (!(gt.z > 0.f)) o[2] = 0.f;
+                            if (!(gt.w > 0.f)) o[3] = 0.f;
+                        }
+                        *reinterpret_cast<float4*>(op + e) = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+    }
+}
+
+constexpr size_t SMEM_LIMIT = 227 * 1024 - 4096;   // leave room for the static barriers / row ids
+static size_t fixed_bytes(int k, int n) {
+    const int kchunks = (k + KC - 1) / KC;
+    return 1024 + (size_t)2 * kchunks * n * 128 + 1024;
+}
+static int num_stages(int k, int n) {
+    const size_t fixed = fixed_bytes(k, n);
+    if (fixed + 2 * TILE_BYTES > SMEM_LIMIT) return 0;
+    return (int)std::min<size_t>(MAX_STAGES, (SMEM_LIMIT - fixed) / (2 * TILE_BYTES));
+}
+static size_t smem_bytes(int k, int n) { return fixed_bytes(k, n) + (size_t)num_stages(k, n) * 2 * TILE_BYTES; }
+
+}  // namespace tc
+}  // namespace gd
+
+using namespace gd;
+
+// 1 if gd_gemm_rows_tc supports the shape (else the caller uses gd_gemm_rows)
+extern "C" int gd_gemm_rows_tc_supported(int32_t k, int32_t n, int64_t lda, int64_t ldo) {
+    if (k <= 0 || n <= 0 || n > 128 || n % 32 != 0) return 0;
+    if (lda % 4 != 0 || ldo % 4 != 0) return 0;
+    return tc::num_stages(k, n) >= 2 ? 1 : 0;
+}
+
+extern "C" int gd_gemm_rows_tc(const float* a, int64_t lda, const int32_t* rows, int64_t m, int32_t k,
+                               const float* b, int32_t b_is_nk, int32_t n, const float* bias,
+                               const float* out_scale, const float* gate, int64_t ldgate, int32_t relu_in,
+                               int32_t relu_out, float* out, int64_t ldo, gd_stream_t stream_) {
+    cudaStream_t stream = as_stream(stream_);
+    GD_CHECK_ARG(m >= 0 && k > 0 && n > 0, "bad shape");
+    if (m == 0) return GD_OK;
+    GD_CHECK_ARG(a && b && out, "null pointer");
+    GD_CHECK_ARG(gd_gemm_rows_tc_supported(k, n, lda, ldo), "shape not supported by the tcgen05 path");
+    GD_CHECK_ARG(((uintptr_t)a | (uintptr_t)out | (uintptr_t)gate) % 16 == 0 && (!gate || ldgate % 4 == 0), "operands must be 16-byte aligned");
+    tc::Args g{a, lda, rows, m, k, b, b_is_nk, n, bias, out_scale, gate, ldgate, relu_in, relu_out, out, ldo,
+               (int)ceil_div<int64_t>(m, tc::BM), tc::num_stages(k, n)};
+    const size_t smem = tc::smem_bytes(k, n);
+    GD_CUDA(cudaFuncSetAttribute(tc::gemm_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::min(g.num_tiles, kNumSMs);
+    tc::gemm_rows_tc_kernel<<<grid, tc::NUM_THREADS, smem, stream>>>(g);
+    GD_LAUNCH_CHECK();
+    return GD_OK;
+}

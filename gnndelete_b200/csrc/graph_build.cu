@@ -83,7 +83,8 @@ __global__ void gcn_dinv_kernel(const int32_t* __restrict__ rowptr, int64_t n, f
 __global__ void spmm_plan_kernel(const int32_t* __restrict__ rowptr, int64_t n, int seg_len,
                                  int32_t* __restrict__ heavy_row, int32_t* __restrict__ heavy_seg_beg,
                                  int32_t* __restrict__ heavy_nseg, int32_t* __restrict__ seg_row,
-                                 int32_t* __restrict__ seg_beg, int32_t* __restrict__ counts) {
+                                 int32_t* __restrict__ seg_beg, int32_t* __restrict__ seg_heavy,
+                                 int32_t* __restrict__ counts) {
     int lane = threadIdx.x & 31;
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -107,9 +108,11 @@ __global__ void spmm_plan_kernel(const int32_t* __restrict__ rowptr, int64_t n, 
                 heavy_nseg[h] = nseg;
             }
             s0 = __shfl_sync(0xffffffffu, s0, 0);
+            h = __shfl_sync(0xffffffffu, h, 0);
             for (int s = lane; s < nseg; s += 32) {
                 seg_row[s0 + s] = (int32_t)(base + l);
                 seg_beg[s0 + s] = r_beg + s * seg_len;
+                seg_heavy[s0 + s] = h;
             }
         }
     }
@@ -195,16 +198,16 @@ extern "C" int gd_gcn_dinv(const int32_t* rowptr, int64_t n, float* dinv, gd_str
 
 extern "C" int gd_spmm_plan_build(const int32_t* rowptr, int64_t n, int32_t seg_len, int32_t* heavy_row,
                                   int32_t* heavy_seg_beg, int32_t* heavy_nseg, int32_t* seg_row,
-                                  int32_t* seg_beg, int32_t* counts, gd_stream_t stream_) {
+                                  int32_t* seg_beg, int32_t* seg_heavy, int32_t* counts, gd_stream_t stream_) {
     cudaStream_t stream = as_stream(stream_);
     GD_CHECK_ARG(counts, "null counts");
     GD_CHECK_ARG(seg_len >= 32, "seg_len must be >= 32");
     GD_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(int32_t), stream));
     if (n == 0) return GD_OK;
-    GD_CHECK_ARG(rowptr && heavy_row && heavy_seg_beg && heavy_nseg && seg_row && seg_beg, "null pointer");
+    GD_CHECK_ARG(rowptr && heavy_row && heavy_seg_beg && heavy_nseg && seg_row && seg_beg && seg_heavy, "null pointer");
     int blocks = (int)std::min<int64_t>(ceil_div<int64_t>(n, 256), kNumSMs * 16);
     spmm_plan_kernel<<<blocks, 256, 0, stream>>>(rowptr, n, seg_len, heavy_row, heavy_seg_beg, heavy_nseg,
-                                                 seg_row, seg_beg, counts);
+                                                 seg_row, seg_beg, seg_heavy, counts);
     GD_LAUNCH_CHECK();
     return GD_OK;
 }

@@ -1,12 +1,18 @@
 // CSR aggregation (SpMM): the GCN / GIN neighbourhood sum, its transpose-backward and
-// the loss backward gather.  HBM/L2-bound gather kernel:
-//   * a sub-warp of F/4 lanes owns one destination row and reads each source row as
-//     one coalesced run of 128-bit loads (F=64: 256 B, F=128: 512 B);
-//   * column ids of a row are fetched with one coalesced load per LANES entries and
-//     broadcast by shuffle, 8 independent row gathers are kept in flight per lane;
-//   * rows longer than seg_len are cut into segments (gd_spmm_plan_build) that are
-//     scheduled first and reduced by a small finalize kernel, so a power-law hub
-//     never serialises on one warp and the result stays deterministic (no atomics).
+// the loss backward gather.  Gather kernel bound by L2 / HBM bandwidth once the instruction
+// stream is thin enough, so the design minimises warp-instructions per gathered row:
+//   * LANES lanes own one destination row and each lane reads VPL consecutive 128-bit words
+//     of every source row (F=64: 4 lanes x 64 B, F=128: 8 lanes x 64 B), so a warp works on
+//     8 / 4 destination rows at once and one index shuffle + one address computation are
+//     amortised over VPL loads;
+//   * column ids are fetched LANES at a time with one coalesced load and broadcast by
+//     shuffle; 4 edges x VPL loads (16 x 16 B) are in flight per lane;
+//   * rows can be visited through a (windowed, degree-sorted) permutation so that the rows
+//     sharing a warp have similar length;
+//   * rows longer than seg_len are cut into segments (gd_spmm_plan_build) that are scheduled
+//     first; the sub-warp that completes the LAST segment of a row (ticket counter) adds the
+//     partial sums in segment order, so there is no separate finalize pass, no float atomics
+//     and the result is bitwise reproducible.
 #include "common.cuh"
 
 namespace gd {
@@ -21,56 +27,93 @@ struct SpmmArgs {
     const float* bias;
     float* out;
     float* scratch;
+    const int32_t* row_perm;
     const int32_t* seg_row;
     const int32_t* seg_beg;
-    const int32_t* heavy_row;
+    const int32_t* seg_heavy;
     const int32_t* heavy_seg_beg;
     const int32_t* heavy_nseg;
+    int32_t* heavy_ticket;
     int64_t ldx, ldo;
     int64_t num_rows;
     int32_t num_seg, num_heavy, seg_len, feat;
     float self_coef;
 };
 
-constexpr int kBatch = 8;   // independent source-row gathers in flight per lane
+template <int VPL>
+__device__ __forceinline__ void zero_acc(float4 (&acc)[VPL]) {
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
 
-template <int LANES, bool WEIGHTED>
-__device__ __forceinline__ float4 gather_range(const SpmmArgs& a, int beg, int end, int sl, unsigned mask) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* xb = a.x + sl * 4;
+template <int LANES, int VPL, bool WEIGHTED>
+__device__ __forceinline__ void gather_range(const SpmmArgs& a, int beg, int end, int sl, unsigned mask,
+                                             float4 (&acc)[VPL]) {
+    const float4* xb = reinterpret_cast<const float4*>(a.x) + sl * VPL;
+    const unsigned ld4 = (unsigned)(a.ldx >> 2);
     for (int base = beg; base < end; base += LANES) {
-        int k = base + sl;
-        int c = 0;
+        const int k = base + sl;
+        unsigned off = 0;
         float w = 0.f;
         if (k < end) {
-            c = __ldg(a.col + k);
+            const int c = __ldg(a.col + k);
+            off = (unsigned)c * ld4;
             if (WEIGHTED) {
                 w = a.val ? __ldg(a.val + k) : 1.0f;
                 if (a.col_scale) w *= __ldg(a.col_scale + c);
             }
         }
-        int cnt = min(LANES, end - base);
-        for (int j = 0; j < cnt; j += kBatch) {
-            float4 v[kBatch];
-            float wj[kBatch];
+        const int cnt = min(LANES, end - base);
 #pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                int idx = j + u;
-                int cj = __shfl_sync(mask, c, idx & (LANES - 1), LANES);
-                if (WEIGHTED) wj[u] = __shfl_sync(mask, w, idx & (LANES - 1), LANES);
-                v[u] = (idx < cnt) ? ldg4(xb + (int64_t)cj * a.ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        for (int j0 = 0; j0 < LANES; j0 += 4) {
+            if (j0 < cnt) {
+                float4 v[4][VPL];
+                float wj[4];
 #pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                if (WEIGHTED) fma4(acc, wj[u], v[u]); else add4(acc, v[u]);
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = j0 + u;                       // < LANES when LANES >= 4
+                    const unsigned oj = __shfl_sync(mask, off, idx & (LANES - 1), LANES);
+                    if (WEIGHTED) wj[u] = __shfl_sync(mask, w, idx & (LANES - 1), LANES);
+                    const bool valid = idx < cnt;
+#pragma unroll
+                    for (int q = 0; q < VPL; ++q)
+                        v[u][q] = valid ? __ldg(xb + oj + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int q = 0; q < VPL; ++q) {
+                        if (WEIGHTED) fma4(acc[q], wj[u], v[u][q]); else add4(acc[q], v[u][q]);
+                    }
             }
         }
     }
-    return acc;
+}
+
+template <int VPL>
+__device__ __forceinline__ void finish_row(const SpmmArgs& a, int64_t row, int sl, float4 (&acc)[VPL]) {
+    if (a.row_scale) {
+        const float s = __ldg(a.row_scale + row);
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) { acc[q].x *= s; acc[q].y *= s; acc[q].z *= s; acc[q].w *= s; }
+    }
+    if (a.self_coef != 0.f) {
+        const float4* xs = reinterpret_cast<const float4*>(a.x + row * a.ldx) + sl * VPL;
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) fma4(acc[q], a.self_coef, __ldg(xs + q));
+    }
+    if (a.bias) {
+        const float4* bp = reinterpret_cast<const float4*>(a.bias) + sl * VPL;
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) add4(acc[q], __ldg(bp + q));
+    }
+    float4* op = reinterpret_cast<float4*>(a.out + row * a.ldo) + sl * VPL;
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) op[q] = acc[q];
 }
 
 // items [0, num_seg) are long-row segments (scheduled first), items [num_seg, num_seg+N) are rows
-template <int LANES, bool WEIGHTED>
+template <int LANES, int VPL, bool WEIGHTED>
 __global__ void __launch_bounds__(256) spmm_vec_kernel(const SpmmArgs a) {
     constexpr int PER_WARP = 32 / LANES;
     const int lane = threadIdx.x & 31;
@@ -79,43 +122,47 @@ __global__ void __launch_bounds__(256) spmm_vec_kernel(const SpmmArgs a) {
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t item = warp * PER_WARP + sub;
     if (item >= a.num_seg + a.num_rows) return;
+    float4 acc[VPL];
+    zero_acc<VPL>(acc);
     if (item < a.num_seg) {
-        int row = a.seg_row[item];
-        int beg = a.seg_beg[item];
-        int end = min(beg + a.seg_len, __ldg(a.rowptr + row + 1));
-        float4 acc = gather_range<LANES, WEIGHTED>(a, beg, end, sl, mask);
-        stg4(a.scratch + item * (int64_t)a.feat + sl * 4, acc);
+        const int row = __ldg(a.seg_row + item);
+        const int beg = __ldg(a.seg_beg + item);
+        const int end = min(beg + a.seg_len, __ldg(a.rowptr + row + 1));
+        gather_range<LANES, VPL, WEIGHTED>(a, beg, end, sl, mask, acc);
+        float4* sp = reinterpret_cast<float4*>(a.scratch + item * (int64_t)a.feat) + sl * VPL;
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) sp[q] = acc[q];
+        // the sub-warp that stores the last segment of the row reduces all of them, in order
+        const int h = __ldg(a.seg_heavy + item);
+        const int ns = __ldg(a.heavy_nseg + h);
+        __threadfence();
+        int ticket = 0;
+        if (sl == 0) ticket = atomicAdd(a.heavy_ticket + h, 1);
+        ticket = __shfl_sync(mask, ticket, 0, LANES);
+        if (ticket != ns - 1) return;
+        __threadfence();
+        if (sl == 0) a.heavy_ticket[h] = 0;                      // re-arm for the next launch
+        const int s0 = __ldg(a.heavy_seg_beg + h);
+        zero_acc<VPL>(acc);
+        const float4* sb = reinterpret_cast<const float4*>(a.scratch) + sl * VPL;
+        const int f4 = a.feat >> 2;
+        for (int s = 0; s < ns; ++s) {
+            const float4* p = sb + (int64_t)(s0 + s) * f4;
+#pragma unroll
+            for (int q = 0; q < VPL; ++q) add4(acc[q], __ldcg(p + q));   // L2: written by other SMs
+        }
+        finish_row<VPL>(a, row, sl, acc);
         return;
     }
-    const int64_t row = item - a.num_seg;
-    int beg = __ldg(a.rowptr + row), end = __ldg(a.rowptr + row + 1);
-    if (a.seg_len > 0 && end - beg > a.seg_len) return;   // finalised from segments
-    float4 acc = gather_range<LANES, WEIGHTED>(a, beg, end, sl, mask);
-    if (a.row_scale) { float s = __ldg(a.row_scale + row); acc.x *= s; acc.y *= s; acc.z *= s; acc.w *= s; }
-    if (a.self_coef != 0.f) fma4(acc, a.self_coef, ldg4(a.x + row * a.ldx + sl * 4));
-    if (a.bias) add4(acc, ldg4(a.bias + sl * 4));
-    stg4(a.out + row * a.ldo + sl * 4, acc);
+    const int64_t i = item - a.num_seg;
+    const int64_t row = a.row_perm ? __ldg(a.row_perm + i) : i;
+    const int beg = __ldg(a.rowptr + row), end = __ldg(a.rowptr + row + 1);
+    if (a.seg_len > 0 && end - beg > a.seg_len) return;          // finished from its segments
+    gather_range<LANES, VPL, WEIGHTED>(a, beg, end, sl, mask, acc);
+    finish_row<VPL>(a, row, sl, acc);
 }
 
-template <int LANES>
-__global__ void __launch_bounds__(256) spmm_vec_finalize_kernel(const SpmmArgs a) {
-    constexpr int PER_WARP = 32 / LANES;
-    const int lane = threadIdx.x & 31;
-    const int sub = lane / LANES, sl = lane % LANES;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t h = warp * PER_WARP + sub;
-    if (h >= a.num_heavy) return;
-    const int64_t row = a.heavy_row[h];
-    const int s0 = a.heavy_seg_beg[h], ns = a.heavy_nseg[h];
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < ns; ++s) add4(acc, ldg4(a.scratch + (int64_t)(s0 + s) * a.feat + sl * 4));
-    if (a.row_scale) { float s = __ldg(a.row_scale + row); acc.x *= s; acc.y *= s; acc.z *= s; acc.w *= s; }
-    if (a.self_coef != 0.f) fma4(acc, a.self_coef, ldg4(a.x + row * a.ldx + sl * 4));
-    if (a.bias) add4(acc, ldg4(a.bias + sl * 4));
-    stg4(a.out + row * a.ldo + sl * 4, acc);
-}
-
-// any feature width: one warp per item, 32-wide scalar strips (coalesced 128 B per source row strip)
+// any feature width / alignment: one warp per item, 32-wide scalar strips (coalesced 128 B)
 __global__ void __launch_bounds__(256) spmm_generic_kernel(const SpmmArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t item = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -168,11 +215,11 @@ __global__ void __launch_bounds__(256) spmm_generic_kernel(const SpmmArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(256) spmm_generic_finalize_kernel(const SpmmArgs a) {
+__global__ void __launch_bounds__(256) spmm_generic_finalize_kernel(const SpmmArgs a, const int32_t* heavy_row) {
     const int lane = threadIdx.x & 31;
     const int64_t h = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (h >= a.num_heavy) return;
-    const int64_t row = a.heavy_row[h];
+    const int64_t row = heavy_row[h];
     const int s0 = a.heavy_seg_beg[h], ns = a.heavy_nseg[h];
     for (int f = lane; f < a.feat; f += 32) {
         float r = 0.f;
@@ -184,20 +231,14 @@ __global__ void __launch_bounds__(256) spmm_generic_finalize_kernel(const SpmmAr
     }
 }
 
-template <int LANES>
+template <int LANES, int VPL>
 static int launch_vec(const SpmmArgs& a, bool weighted, cudaStream_t stream) {
     constexpr int PER_WARP = 32 / LANES;
-    int64_t items = a.num_seg + a.num_rows;
-    int64_t warps = ceil_div<int64_t>(items, PER_WARP);
-    int64_t blocks = ceil_div<int64_t>(warps, 8);
+    const int64_t items = a.num_seg + a.num_rows;
+    const int64_t blocks = ceil_div<int64_t>(ceil_div<int64_t>(items, PER_WARP), 8);
     if (blocks > 0) {
-        if (weighted) spmm_vec_kernel<LANES, true><<<(unsigned)blocks, 256, 0, stream>>>(a);
-        else spmm_vec_kernel<LANES, false><<<(unsigned)blocks, 256, 0, stream>>>(a);
-        GD_LAUNCH_CHECK();
-    }
-    if (a.num_heavy > 0) {
-        int64_t hb = ceil_div<int64_t>(ceil_div<int64_t>(a.num_heavy, PER_WARP), 8);
-        spmm_vec_finalize_kernel<LANES><<<(unsigned)hb, 256, 0, stream>>>(a);
+        if (weighted) spmm_vec_kernel<LANES, VPL, true><<<(unsigned)blocks, 256, 0, stream>>>(a);
+        else spmm_vec_kernel<LANES, VPL, false><<<(unsigned)blocks, 256, 0, stream>>>(a);
         GD_LAUNCH_CHECK();
     }
     return GD_OK;
@@ -217,27 +258,29 @@ extern "C" int gd_spmm(const gd_csr_t* csr, const float* val, const float* col_s
     GD_CHECK_ARG(csr->rowptr && x && out, "null pointer");
     GD_CHECK_ARG(csr->nnz == 0 || csr->col, "null col");
     GD_CHECK_ARG(ldx >= feat && ldo >= feat, "leading dimension smaller than feat");
-    GD_CHECK_ARG(csr->num_seg == 0 || (scratch && csr->seg_row && csr->seg_beg && csr->seg_len > 0), "split plan without scratch");
+    GD_CHECK_ARG(csr->num_seg == 0 || (scratch && csr->seg_row && csr->seg_beg && csr->seg_heavy && csr->heavy_ticket &&
+                                       csr->seg_len > 0), "split plan without scratch / ticket arrays");
     GD_CHECK_ARG(csr->num_heavy == 0 || (csr->heavy_row && csr->heavy_seg_beg && csr->heavy_nseg), "incomplete split plan");
     SpmmArgs a;
     a.rowptr = csr->rowptr; a.col = csr->col; a.val = val; a.col_scale = col_scale; a.row_scale = row_scale;
-    a.x = x; a.bias = bias; a.out = out; a.scratch = scratch;
-    a.seg_row = csr->seg_row; a.seg_beg = csr->seg_beg; a.heavy_row = csr->heavy_row;
-    a.heavy_seg_beg = csr->heavy_seg_beg; a.heavy_nseg = csr->heavy_nseg;
+    a.x = x; a.bias = bias; a.out = out; a.scratch = scratch; a.row_perm = csr->row_perm;
+    a.seg_row = csr->seg_row; a.seg_beg = csr->seg_beg; a.seg_heavy = csr->seg_heavy;
+    a.heavy_seg_beg = csr->heavy_seg_beg; a.heavy_nseg = csr->heavy_nseg; a.heavy_ticket = csr->heavy_ticket;
     a.ldx = ldx; a.ldo = ldo; a.num_rows = csr->num_rows;
     a.num_seg = csr->num_seg; a.num_heavy = csr->num_heavy; a.seg_len = csr->seg_len; a.feat = feat;
     a.self_coef = self_coef;
     const bool weighted = val != nullptr || col_scale != nullptr;
-    const bool vec_ok = (ldx % 4 == 0) && (ldo % 4 == 0) && (((uintptr_t)x | (uintptr_t)out | (uintptr_t)scratch | (uintptr_t)bias) % 16 == 0);
-    if (vec_ok && feat == 128) return launch_vec<32>(a, weighted, stream);
-    if (vec_ok && feat == 64) return launch_vec<16>(a, weighted, stream);
-    if (vec_ok && feat == 32) return launch_vec<8>(a, weighted, stream);
-    int64_t items = a.num_seg + a.num_rows;
-    int64_t blocks = ceil_div<int64_t>(items, 8);
-    spmm_generic_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
+    const bool vec_ok = (ldx % 4 == 0) && (ldo % 4 == 0) &&
+                        (((uintptr_t)x | (uintptr_t)out | (uintptr_t)scratch | (uintptr_t)bias) % 16 == 0) &&
+                        ((double)csr->num_rows * (double)(ldx / 4) < 4.0e9);   // 32-bit float4 offsets
+    if (vec_ok && feat == 128) return launch_vec<8, 4>(a, weighted, stream);
+    if (vec_ok && feat == 64) return launch_vec<4, 4>(a, weighted, stream);
+    if (vec_ok && feat == 32) return launch_vec<4, 2>(a, weighted, stream);
+    const int64_t items = a.num_seg + a.num_rows;
+    spmm_generic_kernel<<<(unsigned)ceil_div<int64_t>(items, 8), 256, 0, stream>>>(a);
     GD_LAUNCH_CHECK();
     if (a.num_heavy > 0) {
-        spmm_generic_finalize_kernel<<<(unsigned)ceil_div<int64_t>(a.num_heavy, 8), 256, 0, stream>>>(a);
+        spmm_generic_finalize_kernel<<<(unsigned)ceil_div<int64_t>(a.num_heavy, 8), 256, 0, stream>>>(a, csr->heavy_row);
         GD_LAUNCH_CHECK();
     }
     return GD_OK;

@@ -16,13 +16,15 @@ import torch
 from . import _lib as L
 
 SEG_LEN = 64     # rows longer than this are split into segments (spmm.cu)
+DEG_SORT_WINDOW = 4096
 
 
 class CSR:
     """Destination-major CSR on the device + the ``gd_csr_t`` the kernels take."""
 
-    def __init__(self, rowptr, col, eid, rel, num_rows, nnz, plan=None):
+    def __init__(self, rowptr, col, eid, rel, num_rows, nnz, plan=None, row_perm=None):
         self.rowptr, self.col, self.eid, self.rel = rowptr, col, eid, rel
+        self.row_perm = row_perm
         self.num_rows, self.nnz = int(num_rows), int(nnz)
         self.plan = plan or {}
         self._scratch = {}
@@ -31,8 +33,10 @@ class CSR:
         s.rowptr, s.col = rowptr.data_ptr(), col.data_ptr()
         if plan:
             s.seg_len, s.num_heavy, s.num_seg = plan['seg_len'], plan['num_heavy'], plan['num_seg']
-            for k in ('heavy_row', 'heavy_seg_beg', 'heavy_nseg', 'seg_row', 'seg_beg'):
+            for k in ('heavy_row', 'heavy_seg_beg', 'heavy_nseg', 'seg_row', 'seg_beg', 'seg_heavy', 'heavy_ticket'):
                 setattr(s, k, plan[k].data_ptr())
+        if row_perm is not None:
+            s.row_perm = row_perm.data_ptr()
         self.struct = s
         self.ref = C.byref(s)
 
@@ -51,7 +55,18 @@ class CSR:
         return buf
 
 
-def build_csr(src, dst, num_nodes, self_loops=False, rel=None, num_rel=1, seg_len=SEG_LEN):
+def degree_window_perm(rowptr, window=DEG_SORT_WINDOW):
+    """Visiting order for the aggregation kernels: rows sorted by degree inside windows of
+    ``window`` consecutive rows, so that the 4-8 rows sharing a warp have similar length
+    (less intra-warp idling) while coarse row locality is kept."""
+    n = rowptr.numel() - 1
+    deg = (rowptr[1:] - rowptr[:-1]).long()
+    ids = torch.arange(n, device=rowptr.device)
+    key = (ids // window) * (int(deg.max().item()) + 1 if n else 1) + deg
+    return torch.argsort(key, stable=True).to(torch.int32)
+
+
+def build_csr(src, dst, num_nodes, self_loops=False, rel=None, num_rel=1, seg_len=SEG_LEN, deg_sort=True):
     """COO (int64, ``src -> dst``) -> :class:`CSR` via ``gd_csr_from_coo`` +
     ``gd_spmm_plan_build``.  Raises on out-of-range endpoints."""
     dev = src.device
@@ -81,15 +96,17 @@ def build_csr(src, dst, num_nodes, self_loops=False, rel=None, num_rel=1, seg_le
     if seg_len and nnz > 0:
         hcap, scap = nnz // seg_len + 1, 2 * nnz // seg_len + 2
         bufs = {k: torch.empty(hcap if k.startswith('heavy') else scap, dtype=torch.int32, device=dev)
-                for k in ('heavy_row', 'heavy_seg_beg', 'heavy_nseg', 'seg_row', 'seg_beg')}
+                for k in ('heavy_row', 'heavy_seg_beg', 'heavy_nseg', 'seg_row', 'seg_beg', 'seg_heavy')}
         counts = torch.zeros(2, dtype=torch.int32, device=dev)
         L.call('gd_spmm_plan_build', L.ptr(rowptr), N, int(seg_len), L.ptr(bufs['heavy_row']),
                L.ptr(bufs['heavy_seg_beg']), L.ptr(bufs['heavy_nseg']), L.ptr(bufs['seg_row']),
-               L.ptr(bufs['seg_beg']), L.ptr(counts), L.stream())
+               L.ptr(bufs['seg_beg']), L.ptr(bufs['seg_heavy']), L.ptr(counts), L.stream())
         nh, ns = counts.tolist()
         if nh > 0:
+            bufs['heavy_ticket'] = torch.zeros(nh, dtype=torch.int32, device=dev)
             plan = dict(seg_len=int(seg_len), num_heavy=nh, num_seg=ns, **bufs)
-    return CSR(rowptr, col, eid, rel_out, N, nnz, plan)
+    perm = degree_window_perm(rowptr) if (deg_sort and N > 0) else None
+    return CSR(rowptr, col, eid, rel_out, N, nnz, plan, perm)
 
 
 def invert_perm(perm, n_out):

@@ -8,10 +8,16 @@ when the corresponding input ``requires_grad``.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib as L
 from .graph import CSR
+
+
+# 'tc': tcgen05 tensor-core path where the shape allows, 'simt': exact-fp32 CUDA-core path only
+GEMM_BACKEND = os.environ.get('GD_GEMM', 'tc')
 
 
 def _f32(t):
@@ -42,7 +48,11 @@ def gemm_rows(a, b, b_is_nk, out=None, rows=None, bias=None, out_scale=None, gat
     m = a.shape[0] if rows is None else rows.numel()
     if out is None:
         out = torch.empty(a.shape[0], n, dtype=torch.float32, device=a.device)
-    L.call('gd_gemm_rows', L.ptr(a), a.stride(0), L.ptr(rows), m, k, L.ptr(b), int(b_is_nk), n,
+    fn = 'gd_gemm_rows'
+    if GEMM_BACKEND != 'simt' and L.load().gd_gemm_rows_tc_supported(k, n, a.stride(0), out.stride(0)) \
+            and (gate is None or gate.stride(0) % 4 == 0):
+        fn = 'gd_gemm_rows_tc'          # tcgen05 + TMEM, 3xTF32 split (fp32-level accuracy)
+    L.call(fn, L.ptr(a), a.stride(0), L.ptr(rows), m, k, L.ptr(b), int(b_is_nk), n,
            L.ptr(bias), L.ptr(out_scale), L.ptr(gate), gate.stride(0) if gate is not None else 0,
            int(relu_in), int(relu_out), L.ptr(out), out.stride(0), L.stream())
     return out

@@ -62,6 +62,10 @@ typedef struct gd_csr {
     const int32_t* heavy_nseg;    /* [num_heavy] */
     const int32_t* seg_row;       /* [num_seg] */
     const int32_t* seg_beg;       /* [num_seg] absolute offset into col */
+    const int32_t* seg_heavy;     /* [num_seg] index of the segment's row in heavy_* */
+    int32_t* heavy_ticket;        /* [num_heavy] zero-initialised; self re-arming completion counters */
+    /* optional visiting order of the rows (e.g. degree-sorted inside windows); NULL = identity */
+    const int32_t* row_perm;      /* [num_rows] */
 } gd_csr_t;
 
 size_t gd_csr_workspace_bytes(int64_t num_edges, int64_t num_nodes);
@@ -95,7 +99,7 @@ int gd_gcn_dinv(const int32_t* rowptr, int64_t num_nodes, float* dinv, gd_stream
  * `counts` (device int32[2]) receives {num_heavy, num_seg}. */
 int gd_spmm_plan_build(const int32_t* rowptr, int64_t num_rows, int32_t seg_len, int32_t* heavy_row,
                        int32_t* heavy_seg_beg, int32_t* heavy_nseg, int32_t* seg_row,
-                       int32_t* seg_beg, int32_t* counts, gd_stream_t stream);
+                       int32_t* seg_beg, int32_t* seg_heavy, int32_t* counts, gd_stream_t stream);
 
 /* ------------------------------------------------------------- aggregation (1)
  * out[i,:] = row_scale[i] * ( sum_{k in row i} val[k] * col_scale[col[k]] * x[col[k],:] )
@@ -174,6 +178,16 @@ int gd_gemm_rows(const float* a, int64_t lda, const int32_t* rows, int64_t m, in
                  const float* b, int32_t b_is_nk, int32_t n, const float* bias,
                  const float* out_scale, const float* gate, int64_t ldgate, int32_t relu_in,
                  int32_t relu_out, float* out, int64_t ldo, gd_stream_t stream);
+
+/* Same contract as gd_gemm_rows on the tensor cores: tcgen05.mma (kind::tf32) with TMEM
+ * accumulators and a 3xTF32 operand split, so results match the fp32 path to ~1e-6 relative.
+ * Supported when gd_gemm_rows_tc_supported() returns 1 (k <= ~128, n in {32, 64, 96, 128},
+ * 16-byte aligned operands); B stays resident in shared memory, one persistent CTA per SM. */
+int gd_gemm_rows_tc_supported(int32_t k, int32_t n, int64_t lda, int64_t ldo);
+int gd_gemm_rows_tc(const float* a, int64_t lda, const int32_t* rows, int64_t m, int32_t k,
+                    const float* b, int32_t b_is_nk, int32_t n, const float* bias,
+                    const float* out_scale, const float* gate, int64_t ldgate, int32_t relu_in,
+                    int32_t relu_out, float* out, int64_t ldo, gd_stream_t stream);
 
 /* c[k1,n2] = sum_i a_scale[r(i)] * a[r(i),:k1]^T (outer) g[r(i),:n2] — weight gradient
  * of the contraction above over the (gathered) rows; relu_a applies ReLU to the `a`
