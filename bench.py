@@ -154,7 +154,7 @@ def time_kernels(eng, steps):
         hoist, eng.hoist = eng.hoist, True
         # forward with the layer-2 aggregation bracketed
         w1 = m.deletion1.deletion_weight.detach(); w2 = m.deletion2.deletion_weight.detach()
-        ops.gemm_rows(eng.a1, w1, False, out=eng.x1, rows=eng.rows1)
+        ops.gemm_rows(eng.a1, w1, False, out=eng.x1, rows=eng.rows1, relu_mask_out=eng.x1_bits)
         ops.copy_rows(eng.a1, eng.x1, eng.comp1)
         ops.gemm_rows(eng.x1, m.conv2.lin.weight.detach(), True, out=eng.h1, out_scale=p.dinv, relu_in=True)
         timed('spmm_l2_f64', lambda: ops.spmm(p.fwd, eng.h1, out=eng.a2, row_scale=p.dinv, bias=m.conv2.bias.detach()))
@@ -167,7 +167,7 @@ def time_kernels(eng, steps):
         ops.copy_rows(eng.dz, eng.da2, eng.comp2)
         timed('spmm_bwd_f64', lambda: ops.spmm(p.bwd, eng.da2, out=eng.dh1, col_scale=p.dinv))
         ops.gemm_rows(eng.dh1, m.conv2.lin.weight.detach(), False, out=eng.dx1, rows=eng.rows1,
-                      out_scale=p.dinv, gate=eng.x1)
+                      out_scale=p.dinv, gate=None if eng.bitmask else eng.x1, gate_bits=eng.x1_bits)
         ops.gemm_tn_rows(eng.a1, eng.dx1, rows=eng.rows1, out=eng.params[0].grad)
         eng.hoist = hoist
     torch.cuda.synchronize()

@@ -8,14 +8,15 @@
 //   a.b ~= a_hi.b_hi + a_lo.b_hi + a_hi.b_lo      (a_hi = a rounded to tf32)
 // which costs 3 MMAs per k-step and still leaves the kernel memory-bound.
 //
-// Structure (one persistent CTA per SM, 288 threads):
-//   warps 0-3  producers : gather 128 rows x 32 k (one 128-byte swizzle row each) per stage with
-//                          128-bit loads, optional ReLU, hi/lo split, st.shared in the canonical
-//                          K-major SWIZZLE_128B layout, fence.proxy.async, arrive on full[stage];
-//   warp  8    MMA issue : one elected lane waits full[stage], issues 12 tcgen05.mma
+// Structure (one persistent CTA per SM, 416 threads):
+//   warps 0-7  producers : gather 128 rows x 32 k (one 128-byte swizzle row each) per stage with
+//                          128-bit loads kept 3 stages ahead in a register ring, optional ReLU,
+//                          hi/lo split, st.shared in the canonical K-major SWIZZLE_128B layout,
+//                          fence.proxy.async, arrive on full[stage];
+//   warp  12   MMA issue : one elected lane waits full[stage], issues 12 tcgen05.mma
 //                          (M=128, N, K=8, kind::tf32) per stage, tcgen05.commit -> empty[stage],
 //                          and -> tmem_full[acc] after the last stage of a tile;
-//   warps 4-7  epilogue  : tcgen05.ld the 128 x N fp32 accumulator (thread = row), bias / row
+//   warps 8-11 epilogue  : tcgen05.ld the 128 x N fp32 accumulators (thread = row), bias / row
 //                          scale / ReLU / gate, 128-bit stores to the (scattered) output rows,
 //                          arrive on tmem_empty[acc].
 // B (<= 128 x 128, hi and lo) is staged once per CTA and stays resident in shared memory; the
@@ -30,7 +31,12 @@ constexpr int BM = 128;            // rows per tile (UMMA M)
 constexpr int KC = 32;             // k per stage: 32 tf32 = one 128-byte swizzle row
 constexpr int MAX_STAGES = 4;      // A ring depth (runtime: as many as shared memory allows)
 constexpr int TILE_BYTES = BM * 128;            // one [128 rows x 128 B] operand tile
-constexpr int NUM_THREADS = 288;
+constexpr int NUM_PRODUCER_WARPS = 8;
+constexpr int MMA_WARP = 12;                     // warps 8-11: epilogue (warp % 4 = TMEM lane quarter)
+constexpr int NUM_THREADS = 13 * 32;
+constexpr int EPI_LD = 36;                       // padded row (floats) of the per-warp epilogue transpose tile
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+constexpr int PREFETCH = 3;                      // producer register ring depth (stages of loads in flight)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -123,6 +129,7 @@ struct Args {
     const float* bias; const float* out_scale; const float* gate; int64_t ldgate;
     int relu_in, relu_out;
     float* out; int64_t ldo;
+    uint32_t* relu_mask_out; const uint32_t* gate_bits;      // [row][n/32] bit c%32 of word c/32 <=> value > 0
     int num_tiles;
     int stages;
 };
@@ -137,10 +144,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rows_tc_kernel(const Args
     uint8_t* b_lo = b_hi + kchunks * b_tile;
     uint8_t* a_ring = b_lo + kchunks * b_tile;                     // [stages][hi 16 KB | lo 16 KB]
     a_ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a_ring) + 1023) & ~(uintptr_t)1023);
+    float* epi_buf = reinterpret_cast<float*>(a_ring + g.stages * 2 * TILE_BYTES);
     __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
     const int STAGES = g.stages;
     __shared__ uint32_t tmem_base_smem;
-    __shared__ int32_t row_id[2][BM];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // per tile: main accumulator (a_hi.b_hi) + correction accumulator (a_lo.b_hi + a_hi.b_lo), double buffered.
@@ -149,11 +156,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rows_tc_kernel(const Args
     const uint32_t tmem_cols = g.n <= 32 ? 128 : (g.n <= 64 ? 256 : 512);
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], NUM_PRODUCER_WARPS * 32); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
                      "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -180,59 +187,87 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rows_tc_kernel(const Args
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    if (warp < 4) {
+    if (warp < NUM_PRODUCER_WARPS) {
         // ================================ producers ================================
-        const int j = tid & 7, r0 = tid >> 3;                      // 8 threads per row, 16 rows per pass
-        uint32_t stage = 0, phase = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-            const int64_t m0 = (int64_t)tile * BM;
-            // row ids of this tile (double buffered: a fast producer thread may already be one tile ahead)
-            int32_t* rid = row_id[it & 1];
-            {
-                const int64_t i = m0 + tid;
-                rid[tid] = i < g.m ? (g.rows ? __ldg(g.rows + i) : (int32_t)i) : -1;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");       // producers only
-            const float* src[8];
+        // 256 threads: 8 threads per row (one 16-byte chunk each), 32 rows per pass, 4 passes per stage.
+        // Loads run PREFETCH stages ahead of the shared-memory stores through a register ring, so
+        // ~48 KB of gathers are in flight per SM while earlier stages are split / stored / consumed.
+        const int j = tid & 7, r0 = tid >> 3;
+        int p_tile = blockIdx.x, p_c = 0;                         // prefetch cursor (tile, k-chunk)
+        const float* psrc[4];
+        int32_t rid_next[4];
+        auto load_rids = [&](int tile, int32_t (&rid)[4]) {
 #pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                const int32_t r = rid[r0 + 16 * p];
-                src[p] = r >= 0 ? g.a + (int64_t)r * g.lda + j * 4 : nullptr;
+            for (int p = 0; p < 4; ++p) {
+                const int64_t i = (int64_t)tile * BM + r0 + 32 * p;
+                rid[p] = (tile < g.num_tiles && i < g.m) ? (g.rows ? __ldg(g.rows + i) : (int32_t)i) : -1;
             }
-            for (int c = 0; c < kchunks; ++c) {
-                const int kbase = c * KC + j * 4;
-                float4 v[8];
+        };
+        auto set_src = [&](const int32_t (&rid)[4]) {
 #pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    v[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (src[p] != nullptr) {
-                        if (kbase + 4 <= g.k) v[p] = __ldg(reinterpret_cast<const float4*>(src[p] + c * KC));
-                        else {
-                            float* vp = reinterpret_cast<float*>(&v[p]);
-                            for (int e = 0; e < 4; ++e) if (kbase + e < g.k) vp[e] = __ldg(src[p] + c * KC + e);
-                        }
+            for (int p = 0; p < 4; ++p) psrc[p] = rid[p] >= 0 ? g.a + (int64_t)rid[p] * g.lda + j * 4 : nullptr;
+        };
+        auto issue = [&](float4 (&buf)[4]) {                       // loads of stage (p_tile, p_c); advance cursor
+            if (p_tile >= g.num_tiles) return;
+            const int kbase = p_c * KC + j * 4;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                buf[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (psrc[p] != nullptr) {
+                    if (kbase + 4 <= g.k) buf[p] = __ldg(reinterpret_cast<const float4*>(psrc[p] + p_c * KC));
+                    else {
+                        float* vp = reinterpret_cast<float*>(&buf[p]);
+                        for (int e = 0; e < 4; ++e) if (kbase + e < g.k) vp[e] = __ldg(psrc[p] + p_c * KC + e);
                     }
                 }
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* ahi = a_ring + stage * 2 * TILE_BYTES;
-                uint8_t* alo = ahi + TILE_BYTES;
+            }
+            if (++p_c == kchunks) {
+                p_c = 0;
+                p_tile += gridDim.x;
+                set_src(rid_next);
+                load_rids(p_tile + gridDim.x, rid_next);           // row ids one tile ahead of the prefetch cursor
+            }
+        };
+        uint32_t stage = 0, phase = 0;
+        auto consume = [&](const float4 (&buf)[4]) {               // split + store one stage
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* ahi = a_ring + stage * 2 * TILE_BYTES;
+            uint8_t* alo = ahi + TILE_BYTES;
 #pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    float4 x = v[p];
-                    if (g.relu_in) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                    float4 hi, lo;
-                    split4(x, hi, lo);
-                    const uint32_t o = swz(r0 + 16 * p, j);
-                    *reinterpret_cast<float4*>(ahi + o) = hi;
-                    *reinterpret_cast<float4*>(alo + o) = lo;
+            for (int p = 0; p < 4; ++p) {
+                float4 x = buf[p];
+                if (g.relu_in) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                float4 hi, lo;
+                split4(x, hi, lo);
+                const uint32_t o = swz(r0 + 32 * p, j);
+                *reinterpret_cast<float4*>(ahi + o) = hi;
+                *reinterpret_cast<float4*>(alo + o) = lo;
+            }
+            fence_proxy_async();
+            mbar_arrive(&full_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        };
+        {
+            int32_t rid0[4];
+            load_rids(p_tile, rid0);
+            set_src(rid0);
+            load_rids(p_tile + gridDim.x, rid_next);
+        }
+        const int my_tiles = blockIdx.x < g.num_tiles ? (g.num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+        const int total = my_tiles * kchunks;
+        float4 buf[PREFETCH][4];
+#pragma unroll
+        for (int d = 0; d < PREFETCH; ++d) issue(buf[d]);
+        for (int s = 0; s < total; s += PREFETCH) {
+#pragma unroll
+            for (int d = 0; d < PREFETCH; ++d) {
+                if (s + d < total) {
+                    consume(buf[d]);
+                    issue(buf[d]);
                 }
-                fence_proxy_async();
-                mbar_arrive(&full_bar[stage]);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == MMA_WARP) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(g.n);
@@ -265,48 +300,70 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rows_tc_kernel(const Args
         __syncwarp();
     } else {
         // ================================ epilogue ================================
+        // thread = accumulator row (TMEM lane); every 32-column chunk is transposed through a per-warp
+        // shared-memory tile so that the (scattered) output rows are written — and the gate rows read —
+        // as full 128-byte segments (8 lanes x 16 B per row, 4 rows per instruction).
         const int q = warp & 3;                                    // TMEM lane quarter of this warp
         const int lr = q * 32 + lane;                              // row inside the tile == TMEM lane
+        float* tbuf = epi_buf + q * (32 * EPI_LD);
+        const int cl = lane & 7, rl = lane >> 3;                   // coalesced phase: column chunk / row-in-group
         int it = 0;
         for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
             const int64_t gi = (int64_t)tile * BM + lr;
             const int32_t r = gi < g.m ? (g.rows ? __ldg(g.rows + gi) : (int32_t)gi) : -1;
             const float sc = (r >= 0 && g.out_scale) ? __ldg(g.out_scale + r) : 1.0f;
+            uint32_t gate_word[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+            if (g.gate_bits && r >= 0) {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) if (w < (g.n >> 5)) gate_word[w] = __ldg(g.gate_bits + (int64_t)r * (g.n >> 5) + w);
+            }
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
             for (int c0 = 0; c0 < g.n; c0 += 32) {
                 uint32_t v[32], vc[32];
                 const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * g.n + c0;
                 tmem_ld32(t0, v);
                 tmem_ld32(t0 + g.n, vc);
+                const uint32_t gbits = (g.gate_bits && r >= 0) ? gate_word[c0 >> 5] : 0xffffffffu;
+                uint32_t pos_bits = 0;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(vc[e]));
-                if (r >= 0) {
-                    float* op = g.out + (int64_t)r * g.ldo + c0;
-                    const float* gp = g.gate ? g.gate + (int64_t)r * g.ldgate + c0 : nullptr;
+                for (int e = 0; e < 32; e += 4) {
+                    float o[4];
 #pragma unroll
-                    for (int e = 0; e < 32; e += 4) {
-                        if (c0 + e >= g.n) break;
-                        float o[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            float x = __uint_as_float(v[e + u]);
-                            if (g.bias) x += __ldg(g.bias + c0 + e + u);
-                            x *= sc;
-                            if (g.relu_out) x = fmaxf(x, 0.f);
-                            o[u] = x;
-                        }
-                        if (gp) {
-                            const float4 gt = __ldg(reinterpret_cast<const float4*>(gp + e));
-                            if (!(gt.x > 0.f)) o[0] = 0.f;
-                            if (!(gt.y > 0.f)) o[1] = 0.f;
-                            if (!(gt.z > 0.f)) o[2] = 0.f;
-                            if (!(gt.w > 0.f)) o[3] = 0.f;
-                        }
-                        *reinterpret_cast<float4*>(op + e) = make_float4(o[0], o[1], o[2], o[3]);
+                    for (int u = 0; u < 4; ++u) {
+                        float x = __uint_as_float(v[e + u]) + __uint_as_float(vc[e + u]);
+                        if (g.bias) x += __ldg(g.bias + c0 + e + u);
+                        x *= sc;
+                        if (g.relu_out) x = fmaxf(x, 0.f);
+                        if (!((gbits >> (e + u)) & 1u)) x = 0.f;
+                        if (x > 0.f) pos_bits |= 1u << (e + u);
+                        o[u] = x;
                     }
+                    *reinterpret_cast<float4*>(tbuf + lane * EPI_LD + e) = make_float4(o[0], o[1], o[2], o[3]);
                 }
+                if (g.relu_mask_out && r >= 0) g.relu_mask_out[(int64_t)r * (g.n >> 5) + (c0 >> 5)] = pos_bits;
+                __syncwarp();
+                // gate rows first (all 8 loads in flight; they may alias `out` as far as the compiler knows)
+                int32_t rr[8];
+                float4 gt[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    rr[i] = __shfl_sync(0xffffffffu, r, i * 4 + rl);
+                    gt[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (g.gate && rr[i] >= 0)
+                        gt[i] = __ldg(reinterpret_cast<const float4*>(g.gate + (int64_t)rr[i] * g.ldgate + c0 + cl * 4));
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 o = *reinterpret_cast<const float4*>(tbuf + (i * 4 + rl) * EPI_LD + cl * 4);
+                    if (!(gt[i].x > 0.f)) o.x = 0.f;
+                    if (!(gt[i].y > 0.f)) o.y = 0.f;
+                    if (!(gt[i].z > 0.f)) o.z = 0.f;
+                    if (!(gt[i].w > 0.f)) o.w = 0.f;
+                    if (rr[i] >= 0) *reinterpret_cast<float4*>(g.out + (int64_t)rr[i] * g.ldo + c0 + cl * 4) = o;
+                }
+                __syncwarp();
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
@@ -315,7 +372,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rows_tc_kernel(const Args
     // ---- teardown
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
     }
@@ -324,7 +381,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rows_tc_kernel(const Args
 constexpr size_t SMEM_LIMIT = 227 * 1024 - 4096;   // leave room for the static barriers / row ids
 static size_t fixed_bytes(int k, int n) {
     const int kchunks = (k + KC - 1) / KC;
-    return 1024 + (size_t)2 * kchunks * n * 128 + 1024;
+    return 1024 + (size_t)2 * kchunks * n * 128 + 1024 + EPI_BYTES;
 }
 static int num_stages(int k, int n) {
     const size_t fixed = fixed_bytes(k, n);
@@ -348,7 +405,8 @@ extern "C" int gd_gemm_rows_tc_supported(int32_t k, int32_t n, int64_t lda, int6
 extern "C" int gd_gemm_rows_tc(const float* a, int64_t lda, const int32_t* rows, int64_t m, int32_t k,
                                const float* b, int32_t b_is_nk, int32_t n, const float* bias,
                                const float* out_scale, const float* gate, int64_t ldgate, int32_t relu_in,
-                               int32_t relu_out, float* out, int64_t ldo, gd_stream_t stream_) {
+                               int32_t relu_out, float* out, int64_t ldo, uint32_t* relu_mask_out,
+                               const uint32_t* gate_bits, gd_stream_t stream_) {
     cudaStream_t stream = as_stream(stream_);
     GD_CHECK_ARG(m >= 0 && k > 0 && n > 0, "bad shape");
     if (m == 0) return GD_OK;
@@ -356,7 +414,7 @@ extern "C" int gd_gemm_rows_tc(const float* a, int64_t lda, const int32_t* rows,
     GD_CHECK_ARG(gd_gemm_rows_tc_supported(k, n, lda, ldo), "shape not supported by the tcgen05 path");
     GD_CHECK_ARG(((uintptr_t)a | (uintptr_t)out | (uintptr_t)gate) % 16 == 0 && (!gate || ldgate % 4 == 0), "operands must be 16-byte aligned");
     tc::Args g{a, lda, rows, m, k, b, b_is_nk, n, bias, out_scale, gate, ldgate, relu_in, relu_out, out, ldo,
-               (int)ceil_div<int64_t>(m, tc::BM), tc::num_stages(k, n)};
+               relu_mask_out, gate_bits, (int)ceil_div<int64_t>(m, tc::BM), tc::num_stages(k, n)};
     const size_t smem = tc::smem_bytes(k, n);
     GD_CUDA(cudaFuncSetAttribute(tc::gemm_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = std::min(g.num_tiles, kNumSMs);

@@ -53,6 +53,10 @@ class GCNDeleteEngine:
         self.da2 = torch.empty(n, out, **f32)
         self.dh1 = torch.empty(n, out, **f32)
         self.dx1 = torch.zeros(n, hid, **f32)       # only the S1 rows are ever written / read
+        # ReLU mask of x1 on the S1 rows as bits (written by the Del1 GEMM, read by the dX1 GEMM)
+        self.bitmask = ops.gemm_tc_available(hid, hid, hid, hid) and ops.gemm_tc_available(out, hid, out, hid) \
+            and hid % 32 == 0
+        self.x1_bits = torch.zeros(n, hid // 32, dtype=torch.int32, device=dev) if self.bitmask else None
         self.hoist = bool(hoist_layer1)
         self._layer1_done = False
         self.params = [model.deletion1.deletion_weight, model.deletion2.deletion_weight]
@@ -77,7 +81,8 @@ class GCNDeleteEngine:
             self.layer1()
         w1 = m.deletion1.deletion_weight.detach()
         w2 = m.deletion2.deletion_weight.detach()
-        ops.gemm_rows(self.a1, w1, False, out=self.x1, rows=self.rows1)            # Del1 on S1
+        ops.gemm_rows(self.a1, w1, False, out=self.x1, rows=self.rows1,           # Del1 on S1
+                      relu_mask_out=self.x1_bits)
         ops.copy_rows(self.a1, self.x1, self.comp1)
         ops.gemm_rows(self.x1, m.conv2.lin.weight.detach(), True, out=self.h1, out_scale=p.dinv, relu_in=True)
         ops.spmm(p.fwd, self.h1, out=self.a2, row_scale=p.dinv, bias=m.conv2.bias.detach())
@@ -96,7 +101,8 @@ class GCNDeleteEngine:
         ops.copy_rows(self.dz, self.da2, self.comp2)
         ops.spmm(p.bwd, self.da2, out=self.dh1, col_scale=p.dinv)                  # A^T D^-1/2 dA2
         ops.gemm_rows(self.dh1, m.conv2.lin.weight.detach(), False, out=self.dx1, rows=self.rows1,
-                      out_scale=p.dinv, gate=self.x1)                              # ReLU' (D^-1/2 dH1) W_2 on S1
+                      out_scale=p.dinv, gate=None if self.bitmask else self.x1,
+                      gate_bits=self.x1_bits)                                      # ReLU' (D^-1/2 dH1) W_2 on S1
         ops.gemm_tn_rows(self.a1, self.dx1, rows=self.rows1, out=g1)               # dW_del1
 
     def forward_backward(self):

@@ -38,8 +38,9 @@ def spmm(csr: CSR, x, out=None, val=None, col_scale=None, row_scale=None, self_c
 
 
 def gemm_rows(a, b, b_is_nk, out=None, rows=None, bias=None, out_scale=None, gate=None,
-              relu_in=False, relu_out=False):
-    """out[r,:] = epi(pro(a[r,:]) . B) over all rows or the ``rows`` list (in place in ``out``)."""
+              relu_in=False, relu_out=False, relu_mask_out=None, gate_bits=None):
+    """out[r,:] = epi(pro(a[r,:]) . B) over all rows or the ``rows`` list (in place in ``out``).
+    ``relu_mask_out`` / ``gate_bits`` (int32 ``[rows, n/32]`` bit masks) are tensor-core-path only."""
     a = _f32(a)
     b = _f32(b)
     k = a.shape[1]
@@ -52,10 +53,19 @@ def gemm_rows(a, b, b_is_nk, out=None, rows=None, bias=None, out_scale=None, gat
     if GEMM_BACKEND != 'simt' and L.load().gd_gemm_rows_tc_supported(k, n, a.stride(0), out.stride(0)) \
             and (gate is None or gate.stride(0) % 4 == 0):
         fn = 'gd_gemm_rows_tc'          # tcgen05 + TMEM, 3xTF32 split (fp32-level accuracy)
-    L.call(fn, L.ptr(a), a.stride(0), L.ptr(rows), m, k, L.ptr(b), int(b_is_nk), n,
-           L.ptr(bias), L.ptr(out_scale), L.ptr(gate), gate.stride(0) if gate is not None else 0,
-           int(relu_in), int(relu_out), L.ptr(out), out.stride(0), L.stream())
+    args = [L.ptr(a), a.stride(0), L.ptr(rows), m, k, L.ptr(b), int(b_is_nk), n,
+            L.ptr(bias), L.ptr(out_scale), L.ptr(gate), gate.stride(0) if gate is not None else 0,
+            int(relu_in), int(relu_out), L.ptr(out), out.stride(0)]
+    if fn == 'gd_gemm_rows_tc':
+        args += [L.ptr(relu_mask_out), L.ptr(gate_bits)]
+    elif relu_mask_out is not None or gate_bits is not None:
+        raise RuntimeError('bit-packed ReLU masks need the tcgen05 GEMM path (shape not supported)')
+    L.call(fn, *args, L.stream())
     return out
+
+
+def gemm_tc_available(k, n, lda, ldo):
+    return GEMM_BACKEND != 'simt' and bool(L.load().gd_gemm_rows_tc_supported(k, n, lda, ldo))
 
 
 _tn_ws = {}

@@ -182,12 +182,17 @@ int gd_gemm_rows(const float* a, int64_t lda, const int32_t* rows, int64_t m, in
 /* Same contract as gd_gemm_rows on the tensor cores: tcgen05.mma (kind::tf32) with TMEM
  * accumulators and a 3xTF32 operand split, so results match the fp32 path to ~1e-6 relative.
  * Supported when gd_gemm_rows_tc_supported() returns 1 (k <= ~128, n in {32, 64, 96, 128},
- * 16-byte aligned operands); B stays resident in shared memory, one persistent CTA per SM. */
+ * 16-byte aligned operands); B stays resident in shared memory, one persistent CTA per SM.
+ * Two optional bit-packed ReLU helpers ([row][n/32] words, bit c%32 of word c/32):
+ *   relu_mask_out : written with (out[r,c] > 0) — the forward records ReLU's mask for free;
+ *   gate_bits     : out[r,c] is kept where the bit is set, else 0 — the backward's ReLU'
+ *                   gate at 1/32 of the traffic of reading the fp32 activations again. */
 int gd_gemm_rows_tc_supported(int32_t k, int32_t n, int64_t lda, int64_t ldo);
 int gd_gemm_rows_tc(const float* a, int64_t lda, const int32_t* rows, int64_t m, int32_t k,
                     const float* b, int32_t b_is_nk, int32_t n, const float* bias,
                     const float* out_scale, const float* gate, int64_t ldgate, int32_t relu_in,
-                    int32_t relu_out, float* out, int64_t ldo, gd_stream_t stream);
+                    int32_t relu_out, float* out, int64_t ldo, uint32_t* relu_mask_out,
+                    const uint32_t* gate_bits, gd_stream_t stream);
 
 /* c[k1,n2] = sum_i a_scale[r(i)] * a[r(i),:k1]^T (outer) g[r(i),:n2] — weight gradient
  * of the contraction above over the (gathered) rows; relu_a applies ReLU to the `a`
