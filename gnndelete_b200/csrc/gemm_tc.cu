@@ -390,6 +390,225 @@ static int num_stages(int k, int n) {
 }
 static size_t smem_bytes(int k, int n) { return fixed_bytes(k, n) + (size_t)num_stages(k, n) * 2 * TILE_BYTES; }
 
+
+// =====================================================================================
+// Weight-gradient contraction  c[k1, n2] = sum_i a_scale[r(i)] * pro(a[r(i), :k1])^T (x) g[r(i), :n2]
+// (dW_del = x[S]^T . dOut[S]) on the tensor cores.  The contraction index is the ROW, so both
+// operands are transposed while they are staged: a stage holds 32 rows as A^T [128 x 32] and
+// G^T [n2 x 32] (K-major, SWIZZLE_128B, hi / lo).  Every CTA owns a contiguous range of rows and
+// accumulates in TMEM; every FLUSH stages the accumulator pair is drained by the epilogue warps
+// into the CTA's partial buffer (plain fp32 adds, fixed order) while the MMAs continue on the
+// other pair — this bounds the tensor core's truncating accumulation chain to 32 steps.  A tiny
+// second kernel adds the per-CTA partials in CTA order: deterministic, no atomics.
+struct TnArgs {
+    const float* a; int64_t lda;
+    const float* g; int64_t ldg;
+    const int32_t* rows; int64_t m;
+    int k1, n2, relu_a;
+    const float* a_scale;
+    float* partial;                 // [gridDim.x][k1][n2]
+    int64_t rows_per_cta;
+    int stages;
+};
+constexpr int TN_FLUSH = 8;         // stages (x32 rows) per accumulator flush
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tn_tc_kernel(const TnArgs t) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int g_tile = t.n2 * 128;                                  // bytes of one [n2 x 128 B] tile
+    const int stage_bytes = 2 * TILE_BYTES + 2 * g_tile;            // A^T hi | A^T lo | G^T hi | G^T lo
+    const int STAGES = t.stages;
+    float* epi_buf = reinterpret_cast<float*>(smem + STAGES * stage_bytes);
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tmem_cols = t.n2 <= 32 ? 128 : (t.n2 <= 64 ? 256 : 512);
+    if (tid == 0) {
+        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full_bar[s], NUM_PRODUCER_WARPS * 32); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"(tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // rows k1..127 of the A^T tiles are never written by the producers: zero every A^T tile once
+    for (int i = tid; i < STAGES * 2 * TILE_BYTES / 16; i += NUM_THREADS) {
+        const int s = i / (2 * TILE_BYTES / 16), o = i - s * (2 * TILE_BYTES / 16);
+        *reinterpret_cast<float4*>(smem + s * stage_bytes + o * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    const int64_t r_beg = (int64_t)blockIdx.x * t.rows_per_cta;
+    const int64_t r_end = min(t.m, r_beg + t.rows_per_cta);
+    const int nstages = r_end > r_beg ? (int)((r_end - r_beg + KC - 1) / KC) : 0;   // 32 rows per stage
+    const int ngroups = (nstages + TN_FLUSH - 1) / TN_FLUSH;
+
+    if (warp < NUM_PRODUCER_WARPS) {
+        // ------------------------------ producers: transposing stage fill ------------------------------
+        // thread -> (row rr of the stage, 16-byte column lane cl); a warp covers 8 rows x 4 column lanes,
+        // which spreads the 4-byte transposed stores over 16 banks
+        const int rr = (tid >> 2) & 31, cl = (tid & 3) + 4 * (tid >> 7);
+        const int a4 = t.k1 >> 2, g4 = t.n2 >> 2;                   // float4 per row
+        uint32_t stage = 0, phase = 0;
+        auto fetch_rid = [&](int s) -> int32_t {
+            const int64_t i = r_beg + (int64_t)s * KC + rr;
+            return (s < nstages && i < r_end) ? (t.rows ? __ldg(t.rows + i) : (int32_t)i) : -1;
+        };
+        int32_t rid = fetch_rid(0), rid_nxt = fetch_rid(1);
+        float4 va[4], vg[4];
+        float sc = 1.f;
+        auto issue = [&](int32_t r) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                vg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r >= 0) {
+                    if (cl + 8 * i < a4) va[i] = __ldg(reinterpret_cast<const float4*>(t.a + (int64_t)r * t.lda) + cl + 8 * i);
+                    if (cl + 8 * i < g4) vg[i] = __ldg(reinterpret_cast<const float4*>(t.g + (int64_t)r * t.ldg) + cl + 8 * i);
+                }
+            }
+            sc = (r >= 0 && t.a_scale) ? __ldg(t.a_scale + r) : 1.f;
+        };
+        issue(rid);
+        for (int s = 0; s < nstages; ++s) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* at_hi = smem + stage * stage_bytes;
+            uint8_t* at_lo = at_hi + TILE_BYTES;
+            uint8_t* gt_hi = at_lo + TILE_BYTES;
+            uint8_t* gt_lo = gt_hi + g_tile;
+            const uint32_t kq = rr >> 2, kr = (rr & 3) * 4;        // 16-byte chunk / byte offset of row rr along K
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int cc = cl + 8 * i;
+                if (cc < a4) {
+                    float x[4] = {va[i].x, va[i].y, va[i].z, va[i].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float v = t.relu_a ? fmaxf(x[e], 0.f) : x[e];
+                        v *= sc;
+                        float hi, lo;
+                        split_tf32(v, hi, lo);
+                        const int f = cc * 4 + e;
+                        const uint32_t o = (uint32_t)(f * 128 + ((kq ^ (f & 7)) << 4) + kr);
+                        *reinterpret_cast<float*>(at_hi + o) = hi;
+                        *reinterpret_cast<float*>(at_lo + o) = lo;
+                    }
+                }
+                if (cc < g4) {
+                    float x[4] = {vg[i].x, vg[i].y, vg[i].z, vg[i].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float hi, lo;
+                        split_tf32(x[e], hi, lo);
+                        const int f = cc * 4 + e;
+                        const uint32_t o = (uint32_t)(f * 128 + ((kq ^ (f & 7)) << 4) + kr);
+                        *reinterpret_cast<float*>(gt_hi + o) = hi;
+                        *reinterpret_cast<float*>(gt_lo + o) = lo;
+                    }
+                }
+            }
+            // next stage's loads go out before this stage is published, so they overlap the MMAs
+            rid = rid_nxt;
+            rid_nxt = fetch_rid(s + 2);
+            if (s + 1 < nstages) issue(rid);
+            fence_proxy_async();
+            mbar_arrive(&full_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == MMA_WARP) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(t.n2);
+            uint32_t stage = 0, phase = 0;
+            for (int grp = 0; grp < ngroups; ++grp) {
+                const uint32_t acc = grp & 1, acc_phase = (grp >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + acc * 2 * t.n2, dc = d + t.n2;
+                const int s_end = min(nstages, (grp + 1) * TN_FLUSH);
+                for (int s = grp * TN_FLUSH; s < s_end; ++s) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t ahi = smem_u32(smem + stage * stage_bytes), alo = ahi + TILE_BYTES;
+                    const uint32_t ghi = alo + TILE_BYTES, glo = ghi + g_tile;
+                    const bool first = (s == grp * TN_FLUSH);
+#pragma unroll
+                    for (int ks = 0; ks < KC / 8; ++ks) {
+                        const uint64_t da_hi = make_desc(ahi + ks * 32), da_lo = make_desc(alo + ks * 32);
+                        const uint64_t db_hi = make_desc(ghi + ks * 32), db_lo = make_desc(glo + ks * 32);
+                        const uint32_t accum = !(first && ks == 0);
+                        umma_tf32(dc, da_lo, db_hi, idesc, accum);
+                        umma_tf32(dc, da_hi, db_lo, idesc, 1);
+                        umma_tf32(d, da_hi, db_hi, idesc, accum);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------ epilogue: drain a flush group into the CTA's partial ------------------------------
+        const int q = warp & 3;
+        const int f = q * 32 + lane;                               // TMEM lane == row of c
+        float* tbuf = epi_buf + q * (32 * EPI_LD);
+        const int cl = lane & 7, rl = lane >> 3;
+        float* part = t.partial + (int64_t)blockIdx.x * t.k1 * t.n2;
+        for (int grp = 0; grp < ngroups; ++grp) {
+            const uint32_t acc = grp & 1, acc_phase = (grp >> 1) & 1;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            for (int c0 = 0; c0 < t.n2; c0 += 32) {
+                uint32_t v[32], vc[32];
+                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * t.n2 + c0;
+                tmem_ld32(t0, v);
+                tmem_ld32(t0 + t.n2, vc);
+#pragma unroll
+                for (int e = 0; e < 32; e += 4)
+                    *reinterpret_cast<float4*>(tbuf + lane * EPI_LD + e) =
+                        make_float4(__uint_as_float(v[e]) + __uint_as_float(vc[e]), __uint_as_float(v[e + 1]) + __uint_as_float(vc[e + 1]),
+                                    __uint_as_float(v[e + 2]) + __uint_as_float(vc[e + 2]), __uint_as_float(v[e + 3]) + __uint_as_float(vc[e + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = q * 32 + i * 4 + rl;
+                    if (row < t.k1) {
+                        float4 o = *reinterpret_cast<const float4*>(tbuf + (i * 4 + rl) * EPI_LD + cl * 4);
+                        float4* dst = reinterpret_cast<float4*>(part + (int64_t)row * t.n2 + c0 + cl * 4);
+                        if (grp > 0) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                        *dst = o;
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+        }
+        if (ngroups == 0) {                                         // CTA without rows: its partial is zero
+            if (f < t.k1) for (int c = 0; c < t.n2; ++c) part[(int64_t)f * t.n2 + c] = 0.f;
+        }
+        (void)f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+    }
+}
+
+static int tn_stages(int n2) {
+    const size_t stage = 2 * TILE_BYTES + (size_t)2 * n2 * 128;
+    return (int)std::min<size_t>(MAX_STAGES, (SMEM_LIMIT - 1024 - EPI_BYTES) / stage);
+}
+
 }  // namespace tc
 }  // namespace gd
 
@@ -419,6 +638,48 @@ extern "C" int gd_gemm_rows_tc(const float* a, int64_t lda, const int32_t* rows,
     GD_CUDA(cudaFuncSetAttribute(tc::gemm_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = std::min(g.num_tiles, kNumSMs);
     tc::gemm_rows_tc_kernel<<<grid, tc::NUM_THREADS, smem, stream>>>(g);
+    GD_LAUNCH_CHECK();
+    return GD_OK;
+}
+
+__global__ void tn_reduce_kernel(const float* __restrict__ partial, int nparts, int64_t count, float* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int p = 0; p < nparts; ++p) s += partial[(int64_t)p * count + i];
+        out[i] = s;
+    }
+}
+
+extern "C" int gd_gemm_tn_rows_tc_supported(int32_t k1, int32_t n2, int64_t lda, int64_t ldg) {
+    if (k1 <= 0 || k1 > 128 || k1 % 4 != 0 || n2 <= 0 || n2 > 128 || n2 % 32 != 0) return 0;
+    if (lda % 4 != 0 || ldg % 4 != 0) return 0;
+    return tc::tn_stages(n2) >= 2 ? 1 : 0;
+}
+
+extern "C" size_t gd_gemm_tn_tc_workspace_bytes(int32_t k1, int32_t n2) { return (size_t)kNumSMs * k1 * n2 * sizeof(float); }
+
+extern "C" int gd_gemm_tn_rows_tc(const float* a, int64_t lda, const float* g, int64_t ldg, const int32_t* rows,
+                                  int64_t m, int32_t k1, int32_t n2, int32_t relu_a, const float* a_scale, float* c,
+                                  void* workspace, size_t workspace_bytes, gd_stream_t stream_) {
+    cudaStream_t stream = as_stream(stream_);
+    GD_CHECK_ARG(m >= 0 && k1 > 0 && n2 > 0, "bad shape");
+    GD_CHECK_ARG(c != nullptr, "null output");
+    if (m == 0) { GD_CUDA(cudaMemsetAsync(c, 0, (size_t)k1 * n2 * sizeof(float), stream)); return GD_OK; }
+    GD_CHECK_ARG(a && g, "null pointer");
+    GD_CHECK_ARG(gd_gemm_tn_rows_tc_supported(k1, n2, lda, ldg), "shape not supported by the tcgen05 path");
+    GD_CHECK_ARG(((uintptr_t)a | (uintptr_t)g) % 16 == 0, "operands must be 16-byte aligned");
+    if (!workspace || workspace_bytes < gd_gemm_tn_tc_workspace_bytes(k1, n2))
+        return fail(GD_ERR_WORKSPACE, "gd_gemm_tn_rows_tc: workspace too small");
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(kNumSMs, ceil_div<int64_t>(m, 32 * tc::TN_FLUSH)));
+    const int64_t rows_per_cta = ceil_div<int64_t>(ceil_div<int64_t>(m, grid), 32) * 32;
+    tc::TnArgs t{a, lda, g, ldg, rows, m, k1, n2, relu_a, a_scale, static_cast<float*>(workspace), rows_per_cta,
+                 tc::tn_stages(n2)};
+    const size_t smem = 1024 + (size_t)t.stages * (2 * tc::TILE_BYTES + 2 * n2 * 128) + tc::EPI_BYTES;
+    GD_CUDA(cudaFuncSetAttribute(tc::gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc::gemm_tn_tc_kernel<<<grid, tc::NUM_THREADS, smem, stream>>>(t);
+    GD_LAUNCH_CHECK();
+    const int64_t count = (int64_t)k1 * n2;
+    tn_reduce_kernel<<<(unsigned)ceil_div<int64_t>(count, 256), 256, 0, stream>>>(t.partial, grid, count, c);
     GD_LAUNCH_CHECK();
     return GD_OK;
 }

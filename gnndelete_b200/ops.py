@@ -79,13 +79,17 @@ def gemm_tn_rows(a, g, rows=None, relu_a=False, a_scale=None, out=None):
     m = a.shape[0] if rows is None else rows.numel()
     if out is None:
         out = torch.empty(k1, n2, dtype=torch.float32, device=a.device)
+    fn = 'gd_gemm_tn_rows'
     nbytes = L.load().gd_gemm_tn_workspace_bytes(m, k1, n2)
+    if GEMM_BACKEND != 'simt' and L.load().gd_gemm_tn_rows_tc_supported(k1, n2, a.stride(0), g.stride(0)):
+        fn = 'gd_gemm_tn_rows_tc'
+        nbytes = L.load().gd_gemm_tn_tc_workspace_bytes(k1, n2)
     key = (a.device, nbytes)
     ws = _tn_ws.get(key)
     if ws is None:
         ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=a.device)
         _tn_ws[key] = ws
-    L.call('gd_gemm_tn_rows', L.ptr(a), a.stride(0), L.ptr(g), g.stride(0), L.ptr(rows), m, k1, n2,
+    L.call(fn, L.ptr(a), a.stride(0), L.ptr(g), g.stride(0), L.ptr(rows), m, k1, n2,
            int(relu_a), L.ptr(a_scale), L.ptr(out), L.ptr(ws), nbytes, L.stream())
     return out
 

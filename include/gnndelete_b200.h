@@ -203,6 +203,15 @@ int gd_gemm_tn_rows(const float* a, int64_t lda, const float* g, int64_t ldg, co
                     int64_t m, int32_t k1, int32_t n2, int32_t relu_a, const float* a_scale, float* c,
                     void* workspace, size_t workspace_bytes, gd_stream_t stream);
 
+/* gd_gemm_tn_rows on the tensor cores (tcgen05, 3xTF32): rows are transposed while they are
+ * staged, every CTA accumulates a contiguous range of rows in TMEM and flushes to its own
+ * partial every 256 rows, a second kernel adds the partials in order (deterministic). */
+int gd_gemm_tn_rows_tc_supported(int32_t k1, int32_t n2, int64_t lda, int64_t ldg);
+size_t gd_gemm_tn_tc_workspace_bytes(int32_t k1, int32_t n2);
+int gd_gemm_tn_rows_tc(const float* a, int64_t lda, const float* g, int64_t ldg, const int32_t* rows,
+                       int64_t m, int32_t k1, int32_t n2, int32_t relu_a, const float* a_scale, float* c,
+                       void* workspace, size_t workspace_bytes, gd_stream_t stream);
+
 /* dst[rows[i], :] = src[rows[i], :]  (the unmasked rows of DeletionLayer.forward's clone). */
 int gd_copy_rows(const float* src, int64_t lds, const int32_t* rows, int64_t m, int32_t feat,
                  float* dst, int64_t ldd, gd_stream_t stream);
