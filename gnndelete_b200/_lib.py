@@ -23,6 +23,7 @@ class CsrStruct(C.Structure):
         ('seg_len', _i32), ('num_heavy', _i32), ('num_seg', _i32),
         ('heavy_row', _vp), ('heavy_seg_beg', _vp), ('heavy_nseg', _vp),
         ('seg_row', _vp), ('seg_beg', _vp), ('seg_heavy', _vp), ('heavy_ticket', _vp), ('row_perm', _vp),
+        ('grp_row', _vp), ('num_grp', _i32),
     ]
 
 

@@ -15,16 +15,18 @@ import torch
 
 from . import _lib as L
 
-SEG_LEN = 64     # rows longer than this are split into segments (spmm.cu)
+SEG_LEN = 128    # rows longer than this are split into segments (spmm.cu)
+GROUP_NNZ = 128  # target entries per row group of the streaming aggregation kernel
 DEG_SORT_WINDOW = 4096
 
 
 class CSR:
     """Destination-major CSR on the device + the ``gd_csr_t`` the kernels take."""
 
-    def __init__(self, rowptr, col, eid, rel, num_rows, nnz, plan=None, row_perm=None):
+    def __init__(self, rowptr, col, eid, rel, num_rows, nnz, plan=None, row_perm=None, grp_row=None):
         self.rowptr, self.col, self.eid, self.rel = rowptr, col, eid, rel
         self.row_perm = row_perm
+        self.grp_row = grp_row
         self.num_rows, self.nnz = int(num_rows), int(nnz)
         self.plan = plan or {}
         self._scratch = {}
@@ -37,6 +39,9 @@ class CSR:
                 setattr(s, k, plan[k].data_ptr())
         if row_perm is not None:
             s.row_perm = row_perm.data_ptr()
+        if grp_row is not None and grp_row.numel() > 1:
+            s.grp_row = grp_row.data_ptr()
+            s.num_grp = grp_row.numel() - 1
         self.struct = s
         self.ref = C.byref(s)
 
@@ -64,6 +69,21 @@ def degree_window_perm(rowptr, window=DEG_SORT_WINDOW):
     ids = torch.arange(n, device=rowptr.device)
     key = (ids // window) * (int(deg.max().item()) + 1 if n else 1) + deg
     return torch.argsort(key, stable=True).to(torch.int32)
+
+
+def row_groups(rowptr, seg_len, target=GROUP_NNZ):
+    """``grp_row`` of the streaming aggregation kernel: consecutive rows are grouped until
+    they hold ~``target`` entries; a row longer than ``seg_len`` forms a group of its own."""
+    n = rowptr.numel() - 1
+    deg = (rowptr[1:] - rowptr[:-1]).long()
+    heavy = deg > seg_len if seg_len else torch.zeros_like(deg, dtype=torch.bool)
+    light = torch.where(heavy, torch.zeros_like(deg), deg)
+    bucket = (torch.cumsum(light, 0) - light) // target
+    start = torch.ones(n, dtype=torch.bool, device=rowptr.device)
+    if n > 1:
+        start[1:] = heavy[1:] | heavy[:-1] | (bucket[1:] != bucket[:-1])
+    first = start.nonzero().squeeze(1)
+    return torch.cat([first, first.new_tensor([n])]).to(torch.int32)
 
 
 def build_csr(src, dst, num_nodes, self_loops=False, rel=None, num_rel=1, seg_len=SEG_LEN, deg_sort=True):
@@ -106,7 +126,8 @@ def build_csr(src, dst, num_nodes, self_loops=False, rel=None, num_rel=1, seg_le
             bufs['heavy_ticket'] = torch.zeros(nh, dtype=torch.int32, device=dev)
             plan = dict(seg_len=int(seg_len), num_heavy=nh, num_seg=ns, **bufs)
     perm = degree_window_perm(rowptr) if (deg_sort and N > 0) else None
-    return CSR(rowptr, col, eid, rel_out, N, nnz, plan, perm)
+    groups = row_groups(rowptr, int(seg_len) if seg_len else 0) if N > 0 else None
+    return CSR(rowptr, col, eid, rel_out, N, nnz, plan, perm, groups)
 
 
 def invert_perm(perm, n_out):
