@@ -27,31 +27,118 @@ __device__ __forceinline__ float pair_dot(const float* z, int64_t ldz, int u, in
     return s;
 }
 
-// LANES == 0: generic width, one warp per item with scalar strips
+// Vector path (dim = 4 * LANES): a sub-warp of LANES lanes handles TWO decoder items per step, i.e.
+// the Df pair i and its negative (4 rows) twice, or four NI pairs (8 rows): 8 independent 128-bit
+// row gathers in flight per lane.  The pair endpoints / incidence slots of the NEXT step are
+// fetched while the rows of the current step are in flight (software pipeline across steps), so a
+// step costs one memory latency instead of two.
 template <int LANES>
 __global__ void __launch_bounds__(256) edge_loss_fwd_kernel(const EdgeLossArgs a) {
-    constexpr int L = LANES == 0 ? 32 : LANES;
-    constexpr int PER_WARP = 32 / L;
+    constexpr int PER_WARP = 32 / LANES;
     const int lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5;
-    const int sub = lane / L, sl = lane % L;
-    const unsigned mask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (sub * L));
-    const int64_t items = a.n_df + a.n_ni;
-    const int64_t stride = (int64_t)gridDim.x * 8 * PER_WARP;
+    const int sub = lane / LANES, sl = lane % LANES;
+    const unsigned mask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (sub * LANES));
+    // steps: [0, S_dec) handle Df items 2s, 2s+1 (pairs i and n_df + i); [S_dec, S_dec + S_ni) handle 4 NI pairs each
+    const int64_t S_dec = (a.n_df + 1) / 2, S_ni = (a.n_ni + 3) / 4, S = S_dec + S_ni;
+    const int64_t G = (int64_t)gridDim.x * 8 * PER_WARP;
+    int64_t st = ((int64_t)blockIdx.x * 8 + warp_in_block) * PER_WARP + sub;
     float sum_r = 0.f, sum_l = 0.f;
+    const float4* zb = reinterpret_cast<const float4*>(a.z) + sl;
+    const int64_t ld4 = a.ldz >> 2;
 
+    // lane q < 4 owns pair slot q of a step: slots (0,1) = Df items (2s, 2s+1), slots (2,3) = their negatives;
+    // for NI steps the four slots are four consecutive NI pairs
+    auto pair_of = [&](int64_t s, int q) -> int64_t {
+        if (s >= S) return -1;
+        if (s < S_dec) { const int64_t i = 2 * s + (q & 1); return i < a.n_df ? ((q & 2) ? a.n_df + i : i) : -1; }
+        const int64_t j = 4 * (s - S_dec) + q;
+        return j < a.n_ni ? 2 * a.n_df + j : -1;
+    };
+    auto fetch = [&](int64_t s, int& u, int& v, int& pu_, int& pv_, float& tgt) {
+        u = 0; v = 0; pu_ = 0; pv_ = 0; tgt = 0.f;
+        const int64_t p = sl < 4 ? pair_of(s, sl) : -1;
+        if (p >= 0) {
+            u = __ldg(a.pu + p); v = __ldg(a.pv + p);
+            pu_ = __ldg(a.pos_u + p); pv_ = __ldg(a.pos_v + p);
+            if (s >= S_dec) tgt = __ldg(a.target + (p - 2 * a.n_df));
+        }
+    };
+    int u0, v0, pu0, pv0; float t0;
+    fetch(st, u0, v0, pu0, pv0, t0);
+    while (st < S) {
+        int u1, v1, pu1, pv1; float t1;
+        fetch(st + G, u1, v1, pu1, pv1, t1);                       // prefetch the next step's indices
+        float4 ra[4], rb[4];
+        bool valid[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            valid[q] = pair_of(st, q) >= 0;
+            const int uu = __shfl_sync(mask, u0, q, LANES), vv = __shfl_sync(mask, v0, q, LANES);
+            ra[q] = valid[q] ? __ldg(zb + (int64_t)uu * ld4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            rb[q] = valid[q] ? __ldg(zb + (int64_t)vv * ld4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float d[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float s = ra[q].x * rb[q].x + ra[q].y * rb[q].y + ra[q].z * rb[q].z + ra[q].w * rb[q].w;
+#pragma unroll
+            for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(mask, s, o, LANES);
+            d[q] = s;
+        }
+        // lane q writes the outputs of pair slot q
+        if (sl < 4) {
+            const int64_t p = pair_of(st, sl);
+            if (p >= 0) {
+                const float mine = sl == 0 ? d[0] : (sl == 1 ? d[1] : (sl == 2 ? d[2] : d[3]));
+                float c;
+                if (st < S_dec) {
+                    const float other = sl == 0 ? d[2] : (sl == 1 ? d[3] : (sl == 2 ? d[0] : d[1]));
+                    const float r = (sl < 2) ? mine - other : other - mine;      // pos - neg
+                    c = (sl < 2) ? a.c_r * r : -a.c_r * r;
+                    if (sl < 2) sum_r += r * r;
+                } else {
+                    const float r = mine - t0;
+                    c = a.c_l * r;
+                    sum_l += r * r;
+                }
+                a.logits[p] = mine;
+                a.inc_val[pu0] = c;
+                a.inc_val[pv0] = c;
+            }
+        }
+        st += G; u0 = u1; v0 = v1; pu0 = pu1; pv0 = pv1; t0 = t1;
+    }
+    // deterministic block reduction: lanes -> warp -> block (fixed order)
+    sum_r = warp_sum(sum_r);
+    sum_l = warp_sum(sum_l);
+    __shared__ float red[8][2];
+    if (lane == 0) { red[warp_in_block][0] = sum_r; red[warp_in_block][1] = sum_l; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float r = 0.f, l = 0.f;
+        for (int w = 0; w < 8; ++w) { r += red[w][0]; l += red[w][1]; }
+        a.partial[2 * blockIdx.x] = r;
+        a.partial[2 * blockIdx.x + 1] = l;
+    }
+}
+
+// any width: one warp per item, scalar strips
+__global__ void __launch_bounds__(256) edge_loss_fwd_generic_kernel(const EdgeLossArgs a) {
+    const int lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5;
+    const int64_t items = a.n_df + a.n_ni;
+    const int64_t stride = (int64_t)gridDim.x * 8;
+    float sum_r = 0.f, sum_l = 0.f;
     auto dot = [&](int u, int v) -> float {
-        if (LANES != 0) return pair_dot<L>(a.z, a.ldz, u, v, sl, mask);
         float s = 0.f;
         for (int f = lane; f < a.dim; f += 32) s = fmaf(a.z[(int64_t)u * a.ldz + f], a.z[(int64_t)v * a.ldz + f], s);
         return warp_sum(s);
     };
-
-    for (int64_t item = ((int64_t)blockIdx.x * 8 + warp_in_block) * PER_WARP + sub; item < items; item += stride) {
+    for (int64_t item = (int64_t)blockIdx.x * 8 + warp_in_block; item < items; item += stride) {
         if (item < a.n_df) {
             const int64_t p = item, q = a.n_df + item;
             const float lp = dot(a.pu[p], a.pv[p]);
             const float ln = dot(a.pu[q], a.pv[q]);
-            if (sl == 0) {
+            if (lane == 0) {
                 const float r = lp - ln;
                 const float c = a.c_r * r;
                 a.logits[p] = lp; a.logits[q] = ln;
@@ -62,7 +149,7 @@ __global__ void __launch_bounds__(256) edge_loss_fwd_kernel(const EdgeLossArgs a
         } else {
             const int64_t j = item - a.n_df, p = 2 * a.n_df + j;
             const float l = dot(a.pu[p], a.pv[p]);
-            if (sl == 0) {
+            if (lane == 0) {
                 const float r = l - a.target[j];
                 const float c = a.c_l * r;
                 a.logits[p] = l;
@@ -71,7 +158,6 @@ __global__ void __launch_bounds__(256) edge_loss_fwd_kernel(const EdgeLossArgs a
             }
         }
     }
-    // deterministic block reduction: lanes -> warp -> block (fixed order)
     sum_r = warp_sum(sum_r);
     sum_l = warp_sum(sum_l);
     __shared__ float red[8][2];
@@ -168,10 +254,11 @@ extern "C" int gd_edge_loss_fwd(const float* z, int64_t ldz, int32_t dim, const 
     a.c_l = (1.0f - alpha) * 2.0f * inv_nni;
     const bool vec = (ldz % 4 == 0) && ((uintptr_t)z % 16 == 0);
     int grid;
-    if (vec && dim == 64) { grid = edge_loss_grid(items, 2); edge_loss_fwd_kernel<16><<<grid, 256, 0, stream>>>(a); }
-    else if (vec && dim == 128) { grid = edge_loss_grid(items, 1); edge_loss_fwd_kernel<32><<<grid, 256, 0, stream>>>(a); }
-    else if (vec && dim == 32) { grid = edge_loss_grid(items, 4); edge_loss_fwd_kernel<8><<<grid, 256, 0, stream>>>(a); }
-    else { grid = edge_loss_grid(items, 1); edge_loss_fwd_kernel<0><<<grid, 256, 0, stream>>>(a); }
+    const int64_t steps = (n_df + 1) / 2 + (n_ni + 3) / 4;
+    if (vec && dim == 64) { grid = edge_loss_grid(steps, 2); edge_loss_fwd_kernel<16><<<grid, 256, 0, stream>>>(a); }
+    else if (vec && dim == 128) { grid = edge_loss_grid(steps, 1); edge_loss_fwd_kernel<32><<<grid, 256, 0, stream>>>(a); }
+    else if (vec && dim == 32) { grid = edge_loss_grid(steps, 4); edge_loss_fwd_kernel<8><<<grid, 256, 0, stream>>>(a); }
+    else { grid = edge_loss_grid(items, 1); edge_loss_fwd_generic_kernel<<<grid, 256, 0, stream>>>(a); }
     GD_LAUNCH_CHECK();
     edge_loss_finalize_kernel<<<1, 1024, 0, stream>>>(a.partial, grid, inv_ndf, inv_nni, alpha, losses);
     GD_LAUNCH_CHECK();
