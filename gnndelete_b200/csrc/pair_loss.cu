@@ -14,7 +14,8 @@ struct EdgeLossArgs {
     const float* target;
     const int32_t* pos_u; const int32_t* pos_v;
     float* logits; float* inc_val; float* partial;   // partial[gridDim.x][2]
-    float c_r, c_l;                                    // alpha*2/n_df, (1-alpha)*2/n_ni
+    float c_r, c_l;                                    // alpha*2/norm_df, (1-alpha)*2/norm_ni
+    int64_t own_df, own_ni;                            // leading items whose squared residual this caller counts
 };
 
 template <int LANES>
@@ -95,11 +96,11 @@ __global__ void __launch_bounds__(256) edge_loss_fwd_kernel(const EdgeLossArgs a
                     const float other = sl == 0 ? d[2] : (sl == 1 ? d[3] : (sl == 2 ? d[0] : d[1]));
                     const float r = (sl < 2) ? mine - other : other - mine;      // pos - neg
                     c = (sl < 2) ? a.c_r * r : -a.c_r * r;
-                    if (sl < 2) sum_r += r * r;
+                    if (sl < 2 && 2 * st + (sl & 1) < a.own_df) sum_r += r * r;
                 } else {
                     const float r = mine - t0;
                     c = a.c_l * r;
-                    sum_l += r * r;
+                    if (4 * (st - S_dec) + sl < a.own_ni) sum_l += r * r;
                 }
                 a.logits[p] = mine;
                 a.inc_val[pu0] = c;
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(256) edge_loss_fwd_generic_kernel(const EdgeLo
                 a.logits[p] = lp; a.logits[q] = ln;
                 a.inc_val[a.pos_u[p]] = c;  a.inc_val[a.pos_v[p]] = c;
                 a.inc_val[a.pos_u[q]] = -c; a.inc_val[a.pos_v[q]] = -c;
-                sum_r += r * r;
+                if (item < a.own_df) sum_r += r * r;
             }
         } else {
             const int64_t j = item - a.n_df, p = 2 * a.n_df + j;
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(256) edge_loss_fwd_generic_kernel(const EdgeLo
                 const float c = a.c_l * r;
                 a.logits[p] = l;
                 a.inc_val[a.pos_u[p]] = c; a.inc_val[a.pos_v[p]] = c;
-                sum_l += r * r;
+                if (j < a.own_ni) sum_l += r * r;
             }
         }
     }
@@ -233,6 +234,16 @@ extern "C" int gd_edge_loss_fwd(const float* z, int64_t ldz, int32_t dim, const 
                                 float alpha, const int32_t* pos_u, const int32_t* pos_v, float* logits,
                                 float* inc_val, float* losses, void* workspace, size_t workspace_bytes,
                                 gd_stream_t stream_) {
+    return gd_edge_loss_fwd_part(z, ldz, dim, pair_u, pair_v, n_df, n_ni, target, alpha, pos_u, pos_v, logits, inc_val,
+                                 losses, n_df, n_ni, n_df, n_ni, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int gd_edge_loss_fwd_part(const float* z, int64_t ldz, int32_t dim, const int32_t* pair_u,
+                                     const int32_t* pair_v, int64_t n_df, int64_t n_ni, const float* target,
+                                     float alpha, const int32_t* pos_u, const int32_t* pos_v, float* logits,
+                                     float* inc_val, float* losses, int64_t own_df, int64_t own_ni,
+                                     int64_t norm_df, int64_t norm_ni, void* workspace, size_t workspace_bytes,
+                                     gd_stream_t stream_) {
     cudaStream_t stream = as_stream(stream_);
     GD_CHECK_ARG(n_df >= 0 && n_ni >= 0 && dim > 0, "bad shape");
     GD_CHECK_ARG(losses != nullptr, "null losses");
@@ -248,8 +259,9 @@ extern "C" int gd_edge_loss_fwd(const float* z, int64_t ldz, int32_t dim, const 
     a.target = target; a.pos_u = pos_u; a.pos_v = pos_v; a.logits = logits; a.inc_val = inc_val;
     a.partial = static_cast<float*>(workspace);
     // mean over an empty set is taken as 0 (the reference substitutes torch.tensor(0), gnndelete.py:244-246)
-    const float inv_ndf = n_df > 0 ? 1.0f / (float)n_df : 0.f;
-    const float inv_nni = n_ni > 0 ? 1.0f / (float)n_ni : 0.f;
+    const float inv_ndf = norm_df > 0 ? 1.0f / (float)norm_df : 0.f;
+    const float inv_nni = norm_ni > 0 ? 1.0f / (float)norm_ni : 0.f;
+    a.own_df = own_df; a.own_ni = own_ni;
     a.c_r = alpha * 2.0f * inv_ndf;
     a.c_l = (1.0f - alpha) * 2.0f * inv_nni;
     const bool vec = (ldz % 4 == 0) && ((uintptr_t)z % 16 == 0);

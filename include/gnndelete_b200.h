@@ -245,6 +245,17 @@ int gd_edge_loss_fwd(const float* z, int64_t ldz, int32_t dim, const int32_t* pa
                      float* inc_val, float* losses, void* workspace, size_t workspace_bytes,
                      gd_stream_t stream);
 
+/* Row-partitioned variant: this caller holds a SUBSET of the Df items / NI pairs (those touching
+ * its rows).  Only the first own_df items / own_ni pairs contribute their squared residual to
+ * `losses` (every pair is counted by exactly one rank) and the means use the GLOBAL counts
+ * norm_df / norm_ni, so summing `losses` over ranks gives the global loss. */
+int gd_edge_loss_fwd_part(const float* z, int64_t ldz, int32_t dim, const int32_t* pair_u,
+                          const int32_t* pair_v, int64_t n_df, int64_t n_ni, const float* target,
+                          float alpha, const int32_t* pos_u, const int32_t* pos_v, float* logits,
+                          float* inc_val, float* losses, int64_t own_df, int64_t own_ni,
+                          int64_t norm_df, int64_t norm_ni, void* workspace, size_t workspace_bytes,
+                          gd_stream_t stream);
+
 /* logits[p] = sum_d z[u_p,d] * w[t_p,d] * z[v_p,d]  (w, t nullable => plain dot).
  * GCN.decode (gcn.py:26-35) / RGCN.decode DistMult (rgcn.py:40-47). */
 int gd_pair_decode(const float* z, int64_t ldz, int32_t dim, const int32_t* pair_u,
