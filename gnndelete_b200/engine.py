@@ -22,12 +22,14 @@ import torch
 
 from . import ops
 from .graph import plan_for, rows_of
-from .losses import EdgeLossPlan
+from .losses import DenseNIPlan, EdgeLossPlan
 
 
 class GCNDeleteEngine:
     def __init__(self, model, data, neg_edge_index, z_ori=None, ni_target=None, hoist_layer1=True,
-                 lr=1e-3, betas=(0.9, 0.999), eps=1e-8, alpha=0.5):
+                 lr=1e-3, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, logits_ori=None):
+        """``logits_ori`` (dense ``[N, N]``, the original model's ``z z^T`` as saved in
+        ``pred_proba.pt``) selects ``train_fullbatch``'s dense-block NI loss instead of the edge form."""
         self.model = model
         dev = data.x.device
         self.x = data.x.contiguous()
@@ -39,9 +41,15 @@ class GCNDeleteEngine:
         self.rows2, self.comp2 = rows_of(data.sdf_node_2hop_mask.to(dev), n)
         sdf = ei[:, data.sdf_mask]
         ni = sdf[:, sdf[0] < sdf[1]]                                   # gnndelete.py:379-381
+        hid, out = model.conv1.out_channels, model.conv2.out_channels
+        self.dense = None
+        if logits_ori is not None:                                     # gnndelete.py:163-193, 239-241
+            self.dense = DenseNIPlan(data.sdf_node_2hop_mask, ei[:, data.df_mask], logits_ori, n, out, weight=1.0 - alpha)
+            ni = ni[:, :0]
         self.loss = EdgeLossPlan(ei[:, data.df_mask], neg_edge_index, ni, n, z_ori=z_ori,
                                  target=ni_target, alpha=alpha)
-        hid, out = model.conv1.out_channels, model.conv2.out_channels
+        self.losses_total = torch.zeros(3, dtype=torch.float32, device=dev)
+        self.alpha = float(alpha)
         f32 = dict(dtype=torch.float32, device=dev)
         self.h0 = torch.empty(n, hid, **f32)
         self.a1 = torch.empty(n, hid, **f32)
@@ -96,6 +104,11 @@ class GCNDeleteEngine:
         g1, g2 = self.params[0].grad, self.params[1].grad
         w2 = m.deletion2.deletion_weight.detach()
         self.loss.backward(self.z, out=self.dz)
+        if self.dense is not None:
+            loss_l = self.dense.forward_backward(self.z, self.dz)
+            self.losses_total[1:2].copy_(self.loss.losses[1:2])
+            self.losses_total[2:3].copy_(loss_l)
+            torch.add(self.loss.losses[0:1], loss_l, alpha=1.0 - self.alpha, out=self.losses_total[0:1])
         ops.gemm_tn_rows(self.a2, self.dz, rows=self.rows2, out=g2)                # dW_del2
         ops.gemm_rows(self.dz, w2, True, out=self.da2, rows=self.rows2)            # dz[S2] @ W2^T
         ops.copy_rows(self.dz, self.da2, self.comp2)
@@ -108,7 +121,7 @@ class GCNDeleteEngine:
     def forward_backward(self):
         losses = self.forward()
         self.backward()
-        return losses
+        return self.losses_total if self.dense is not None else losses
 
     def adam_step(self):
         for p, st in zip(self.params, self.state):
@@ -118,7 +131,7 @@ class GCNDeleteEngine:
         """forward + backward + Adam; returns the persistent device tensor (loss, loss_r, loss_l)."""
         if self.graph is not None:
             self.graph.replay()
-            return self.loss.losses
+            return self.losses_total if self.dense is not None else self.loss.losses
         losses = self.forward_backward()
         self.adam_step()
         return losses

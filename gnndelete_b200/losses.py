@@ -112,3 +112,53 @@ class EdgeLossFn(torch.autograd.Function):
 def edge_loss(z, plan):
     out = EdgeLossFn.apply(z, plan)
     return out[0], out[1].detach(), out[2].detach()
+
+
+class DenseNIPlan:
+    """Dense-block Neighbourhood-Influence term of ``train_fullbatch`` (gnndelete.py:163-193,
+    239-241): ``MSE(sigmoid(z z^T)[M], sigmoid(logits_ori)[M])`` with ``M`` = strictly-lower node
+    pairs inside the 2-hop node set minus the Df pairs.  Only the ``S x S`` block is ever
+    touched (``gd_dense_ni_fwd_bwd``); the target block ``sigmoid(logits_ori[S][:, S])`` and the
+    excluded-pair bitmap are built once."""
+
+    def __init__(self, node_mask, df_edges, logits_ori, num_nodes, dim, weight=0.5):
+        dev = df_edges.device
+        node_mask = node_mask.to(dev)
+        self.S = node_mask.nonzero().squeeze(1)
+        self.S32 = self.S.to(torch.int32)
+        n_s = self.S.numel()
+        self.n_s, self.dim = n_s, int(dim)
+        pos = torch.full((int(num_nodes),), -1, dtype=torch.int64, device=dev)
+        pos[self.S] = torch.arange(n_s, device=dev)
+        lo = logits_ori.to(dev) if logits_ori.device != dev else logits_ori
+        self.tgt = torch.sigmoid(lo[self.S][:, self.S].float()).contiguous()
+        pu, pv = pos[df_edges[0]], pos[df_edges[1]]
+        ok = (pu >= 0) & (pv >= 0) & (pu != pv)
+        pu, pv = pu[ok], pv[ok]
+        idx = torch.unique(torch.cat([pu * n_s + pv, pv * n_s + pu]))
+        words = torch.zeros((n_s * n_s + 31) // 32 + 1, dtype=torch.int64, device=dev)
+        words.index_add_(0, idx >> 5, torch.ones_like(idx) << (idx & 31))
+        self.excl = (words & 0xFFFFFFFF).to(torch.int64)
+        self.excl = torch.where(self.excl >= 2 ** 31, self.excl - 2 ** 32, self.excl).to(torch.int32).contiguous()
+        self.num_pairs = n_s * (n_s - 1) // 2 - idx.numel() // 2
+        self.weight = float(weight)
+        self.scale = self.weight / self.num_pairs if self.num_pairs > 0 else 0.0
+        self.zs = torch.empty(max(n_s, 1), self.dim, dtype=torch.float32, device=dev)
+        self.dzs = torch.empty(max(n_s, 1), self.dim, dtype=torch.float32, device=dev)
+        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ws_bytes = L.load().gd_dense_ni_workspace_bytes(n_s)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+
+    def forward_backward(self, z, dz):
+        """Adds ``weight * d loss_l / d z`` into ``dz`` (rows of S) and returns ``loss_l`` (device scalar)."""
+        if self.n_s == 0 or self.num_pairs <= 0:
+            return self.loss_sum * 0.0
+        L.call('gd_gather_rows', L.ptr(z, 'f32'), z.stride(0), z.shape[0], L.ptr(self.S, 'i64'), self.n_s, self.dim,
+               L.ptr(self.zs), self.zs.stride(0), L.ptr(self.status), L.stream())
+        L.call('gd_dense_ni_fwd_bwd', L.ptr(self.zs), self.zs.stride(0), self.dim, self.n_s, L.ptr(self.tgt),
+               self.tgt.stride(0), L.ptr(self.excl), self.scale, L.ptr(self.dzs), self.dzs.stride(0), L.ptr(self.loss_sum),
+               L.ptr(self.ws), self.ws_bytes, L.stream())
+        L.call('gd_add_rows', L.ptr(self.dzs), self.dzs.stride(0), L.ptr(self.S32), self.n_s, self.dim, L.ptr(dz),
+               dz.stride(0), L.stream())
+        return self.loss_sum / self.num_pairs

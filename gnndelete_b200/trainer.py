@@ -139,7 +139,12 @@ class GNNDeleteTrainer(Trainer):
         if not hasattr(model, 'deletion1') or type(model).__name__ != 'GCNDelete':
             raise NotImplementedError('the fused epoch engine currently drives GCNDelete; other *Delete models '
                                       'train through the autograd modules')
-        return self.train_edge_form(model, data, optimizer, args)
+        # reference dispatch (gnndelete.py:39-44): 'ogbl' datasets take the mini-batch loop (edge-form NI),
+        # everything else the full-batch loop whose NI term is the dense S_Df x S_Df block against the
+        # original model's pair logits (`logits_ori`, pred_proba.pt).  Without `logits_ori` the edge form
+        # is used for every graph.
+        dense = logits_ori is not None and 'ogbl' not in self.args.dataset
+        return self.train_edge_form(model, data, optimizer, args, logits_ori if dense else None)
 
     def _negatives(self, data, count, generator):
         """Uniform random pairs (``negative_sampling`` is randomised rejection sampling in
@@ -147,7 +152,7 @@ class GNNDeleteTrainer(Trainer):
         needs parity supplies ``data.neg_edge_index``."""
         return torch.randint(0, data.num_nodes, (2, count), generator=generator, device=data.x.device)
 
-    def train_edge_form(self, model, data, optimizer, args):
+    def train_edge_form(self, model, data, optimizer, args, logits_ori=None):
         dev = torch.device('cuda')
         model = model.to(dev)
         data = data.to(dev)
@@ -157,10 +162,11 @@ class GNNDeleteTrainer(Trainer):
         neg = fixed_neg if fixed_neg is not None else self._negatives(data, n_df, gen)
         with torch.no_grad():
             z_ori = getattr(data, 'z_ori', None)
-            if z_ori is None:
+            if z_ori is None and logits_ori is None:
                 z_ori = model.get_original_embeddings(data.x, data.train_pos_edge_index[:, data.dr_mask])
         group = optimizer.param_groups[0]
-        eng = GCNDeleteEngine(model, data, neg, z_ori=z_ori, lr=group['lr'], betas=group['betas'], eps=group['eps'])
+        eng = GCNDeleteEngine(model, data, neg, z_ori=z_ori, lr=group['lr'], betas=group['betas'], eps=group['eps'],
+                              hoist_layer1=True, logits_ori=logits_ori)
         best_metric = 0
         ring = []
         t0 = time.time()

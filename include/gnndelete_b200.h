@@ -256,6 +256,24 @@ int gd_edge_loss_fwd_part(const float* z, int64_t ldz, int32_t dim, const int32_
                           int64_t norm_df, int64_t norm_ni, void* workspace, size_t workspace_bytes,
                           gd_stream_t stream);
 
+/* Dense-block Neighbourhood-Influence loss of train_fullbatch (gnndelete.py:163-193, 239-241):
+ *   sum over pairs i > j inside the S_Df node set S (minus the excluded Df pairs) of
+ *   (sigmoid(<z_i, z_j>) - sigmoid(logits_ori[i, j]))^2
+ * on the S x S block only, tile by tile, nothing N x N is materialised.
+ *   zs        [n_s, 64]   rows of z for the nodes of S (ascending node id)
+ *   tgt_sig   [n_s, n_s]  sigmoid(logits_ori[S][:, S])
+ *   excl_bits n_s*n_s bits (row-major), 1 = pair excluded (set for both orders of a Df pair)
+ *   dzs       [n_s, 64]   = coef_scale * d(sum of squared residuals)/d zs   (coef_scale = weight / |M|)
+ *   loss_sum  device float, the un-normalised sum.  Deterministic (no atomics). */
+size_t gd_dense_ni_workspace_bytes(int64_t n_s);
+int gd_dense_ni_fwd_bwd(const float* zs, int64_t ldz, int32_t dim, int64_t n_s, const float* tgt_sig,
+                        int64_t ldt, const uint32_t* excl_bits, float coef_scale, float* dzs,
+                        int64_t lddz, float* loss_sum, void* workspace, size_t workspace_bytes,
+                        gd_stream_t stream);
+/* dst[rows[i], :] += src[i, :]   (rows unique) */
+int gd_add_rows(const float* src, int64_t lds, const int32_t* rows, int64_t m, int32_t feat, float* dst,
+                int64_t ldd, gd_stream_t stream);
+
 /* logits[p] = sum_d z[u_p,d] * w[t_p,d] * z[v_p,d]  (w, t nullable => plain dot).
  * GCN.decode (gcn.py:26-35) / RGCN.decode DistMult (rgcn.py:40-47). */
 int gd_pair_decode(const float* z, int64_t ldz, int32_t dim, const int32_t* pair_u,

@@ -54,3 +54,33 @@ def test_engine_first_step_tight(lib):
     """One epoch at the 1e-5 bar: losses and both Del gradients."""
     import __graft_entry__ as G
     G.smoke()
+
+
+def test_dense_block_ni_matches_fullbatch_oracle(lib):
+    """train_fullbatch's dense NI (gnndelete.py:163-193, 239-241): losses and Del gradients against the
+    oracle's N x N formulation; the CUDA path only ever touches the S2 x S2 block."""
+    from gnndelete_b200 import models as M
+    from gnndelete_b200.engine import GCNDeleteEngine
+    from oracle import unlearn as OU
+    shape, raw, df, data, neg = U.make_case('cora', 0.03)
+    om = U.oracle_model('gcn', shape, data, dtype=torch.float64)
+    d64 = data.clone(); d64.x = data.x.double()
+    with torch.no_grad():
+        zo = om.get_original_embeddings(d64.x, d64.train_pos_edge_index[:, d64.dr_mask])
+    logits_ori = zo @ zo.t()                                   # what base.py:288 stores in pred_proba.pt
+    pm = OU.dense_pair_mask(d64, d64.sdf_node_2hop_mask)
+    loss_o, lr_o, ll_o, _ = OU.fullbatch_loss(om, d64, neg, logits_ori, pm)
+    loss_o.backward()
+    m = M.GCNDelete(U.args_for(shape), data.sdf_node_1hop_mask, data.sdf_node_2hop_mask)
+    m.load_state_dict({k: v.float() for k, v in om.state_dict().items()})
+    m = m.to(DEV)
+    eng = GCNDeleteEngine(m, data.clone().to(DEV), neg.to(DEV), logits_ori=logits_ori.float().to(DEV), hoist_layer1=False)
+    assert eng.dense.num_pairs == int(pm.sum())
+    losses = eng.forward_backward()
+    U.assert_close(losses, torch.stack([loss_o, lr_o, ll_o]), what='dense NI losses')
+    U.assert_close(m.deletion2.deletion_weight.grad, om.deletion2.deletion_weight.grad, what='dense NI dW2')
+    U.assert_close(m.deletion1.deletion_weight.grad, om.deletion1.deletion_weight.grad, what='dense NI dW1')
+    # CUDA-graph replay gives the same numbers
+    eng.capture()
+    l2 = eng.epoch().clone()
+    U.assert_close(l2, torch.stack([loss_o, lr_o, ll_o]), what='dense NI losses (graph)')
