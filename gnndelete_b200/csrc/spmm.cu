@@ -1,18 +1,18 @@
-// CSR aggregation (SpMM): the GCN / GIN neighbourhood sum, its transpose-backward and
-// the loss backward gather.  Gather kernel bound by L2 / HBM bandwidth once the instruction
-// stream is thin enough, so the design minimises warp-instructions per gathered row:
-//   * LANES lanes own one destination row and each lane reads VPL consecutive 128-bit words
-//     of every source row (F=64: 4 lanes x 64 B, F=128: 8 lanes x 64 B), so a warp works on
-//     8 / 4 destination rows at once and one index shuffle + one address computation are
-//     amortised over VPL loads;
-//   * column ids are fetched LANES at a time with one coalesced load and broadcast by
-//     shuffle; 4 edges x VPL loads (16 x 16 B) are in flight per lane;
-//   * rows can be visited through a (windowed, degree-sorted) permutation so that the rows
-//     sharing a warp have similar length;
-//   * rows longer than seg_len are cut into segments (gd_spmm_plan_build) that are scheduled
-//     first; the sub-warp that completes the LAST segment of a row (ticket counter) adds the
-//     partial sums in segment order, so there is no separate finalize pass, no float atomics
-//     and the result is bitwise reproducible.
+// CSR aggregation (SpMM): the GCN / GIN neighbourhood sum, its transpose-backward and the loss
+// backward gather.  A gather kernel: every non-zero reads one 256 B / 512 B source row that is
+// (mostly) L2 resident, so the bound is how many row gathers the SMs keep in flight.
+//
+// Measured on B200 (tools/gather_bench.cu): random 256-byte row gathers from an L2-resident
+// matrix sustain ~18 TB/s (7 TB/s from HBM) when ~250 KB of loads are in flight per SM.
+// Kernels in this file, Collab shape, F = 64 (tools/spmm_bench.py):
+//   spmm_pipe_kernel   (default)  123 us  5.4 TB/s gathered   row-pipelined persistent sub-warps
+//   spmm_stream_kernel (GD_SPMM=stream) 152 us              cp.async ring in shared memory
+// Variants that were measured and dropped: sub-warp per row without cross-row prefetch (131 us +
+// 22 us finalize pass), 4 lanes x 4 loads per row (144 us), register streaming over row groups
+// (184 us, 100+ registers), forcing 5 CTAs/SM on the pipeline (spills, 133 us).
+// Rows longer than seg_len are cut into segments (gd_spmm_plan_build) that are scheduled first;
+// the sub-warp that completes the LAST segment of a row (ticket counter) adds the partial sums in
+// segment order: no separate finalize pass, no float atomics, bitwise reproducible results.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -41,128 +41,6 @@ struct SpmmArgs {
     int32_t num_seg, num_heavy, seg_len, feat;
     float self_coef;
 };
-
-template <int VPL>
-__device__ __forceinline__ void zero_acc(float4 (&acc)[VPL]) {
-#pragma unroll
-    for (int q = 0; q < VPL; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-}
-
-template <int LANES, int VPL, bool WEIGHTED>
-__device__ __forceinline__ void gather_range(const SpmmArgs& a, int beg, int end, int sl, unsigned mask,
-                                             float4 (&acc)[VPL]) {
-    const float4* xb = reinterpret_cast<const float4*>(a.x) + sl * VPL;
-    const unsigned ld4 = (unsigned)(a.ldx >> 2);
-    for (int base = beg; base < end; base += LANES) {
-        const int k = base + sl;
-        unsigned off = 0;
-        float w = 0.f;
-        if (k < end) {
-            const int c = __ldg(a.col + k);
-            off = (unsigned)c * ld4;
-            if (WEIGHTED) {
-                w = a.val ? __ldg(a.val + k) : 1.0f;
-                if (a.col_scale) w *= __ldg(a.col_scale + c);
-            }
-        }
-        const int cnt = min(LANES, end - base);
-#pragma unroll
-        for (int j0 = 0; j0 < LANES; j0 += 4) {
-            if (j0 < cnt) {
-                float4 v[4][VPL];
-                float wj[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int idx = j0 + u;                       // < LANES when LANES >= 4
-                    const unsigned oj = __shfl_sync(mask, off, idx & (LANES - 1), LANES);
-                    if (WEIGHTED) wj[u] = __shfl_sync(mask, w, idx & (LANES - 1), LANES);
-                    const bool valid = idx < cnt;
-#pragma unroll
-                    for (int q = 0; q < VPL; ++q)
-                        v[u][q] = valid ? __ldg(xb + oj + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                    for (int q = 0; q < VPL; ++q) {
-                        if (WEIGHTED) fma4(acc[q], wj[u], v[u][q]); else add4(acc[q], v[u][q]);
-                    }
-            }
-        }
-    }
-}
-
-template <int VPL>
-__device__ __forceinline__ void finish_row(const SpmmArgs& a, int64_t row, int sl, float4 (&acc)[VPL]) {
-    if (a.row_scale) {
-        const float s = __ldg(a.row_scale + row);
-#pragma unroll
-        for (int q = 0; q < VPL; ++q) { acc[q].x *= s; acc[q].y *= s; acc[q].z *= s; acc[q].w *= s; }
-    }
-    if (a.self_coef != 0.f) {
-        const float4* xs = reinterpret_cast<const float4*>(a.x + row * a.ldx) + sl * VPL;
-#pragma unroll
-        for (int q = 0; q < VPL; ++q) fma4(acc[q], a.self_coef, __ldg(xs + q));
-    }
-    if (a.bias) {
-        const float4* bp = reinterpret_cast<const float4*>(a.bias) + sl * VPL;
-#pragma unroll
-        for (int q = 0; q < VPL; ++q) add4(acc[q], __ldg(bp + q));
-    }
-    float4* op = reinterpret_cast<float4*>(a.out + row * a.ldo) + sl * VPL;
-#pragma unroll
-    for (int q = 0; q < VPL; ++q) op[q] = acc[q];
-}
-
-// items [0, num_seg) are long-row segments (scheduled first), items [num_seg, num_seg+N) are rows
-template <int LANES, int VPL, bool WEIGHTED>
-__global__ void __launch_bounds__(256) spmm_vec_kernel(const SpmmArgs a) {
-    constexpr int PER_WARP = 32 / LANES;
-    const int lane = threadIdx.x & 31;
-    const int sub = lane / LANES, sl = lane % LANES;
-    const unsigned mask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (sub * LANES));
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t item = warp * PER_WARP + sub;
-    if (item >= a.num_seg + a.num_rows) return;
-    float4 acc[VPL];
-    zero_acc<VPL>(acc);
-    if (item < a.num_seg) {
-        const int row = __ldg(a.seg_row + item);
-        const int beg = __ldg(a.seg_beg + item);
-        const int end = min(beg + a.seg_len, __ldg(a.rowptr + row + 1));
-        gather_range<LANES, VPL, WEIGHTED>(a, beg, end, sl, mask, acc);
-        float4* sp = reinterpret_cast<float4*>(a.scratch + item * (int64_t)a.feat) + sl * VPL;
-#pragma unroll
-        for (int q = 0; q < VPL; ++q) sp[q] = acc[q];
-        // the sub-warp that stores the last segment of the row reduces all of them, in order
-        const int h = __ldg(a.seg_heavy + item);
-        const int ns = __ldg(a.heavy_nseg + h);
-        __threadfence();
-        int ticket = 0;
-        if (sl == 0) ticket = atomicAdd(a.heavy_ticket + h, 1);
-        ticket = __shfl_sync(mask, ticket, 0, LANES);
-        if (ticket != ns - 1) return;
-        __threadfence();
-        if (sl == 0) a.heavy_ticket[h] = 0;                      // re-arm for the next launch
-        const int s0 = __ldg(a.heavy_seg_beg + h);
-        zero_acc<VPL>(acc);
-        const float4* sb = reinterpret_cast<const float4*>(a.scratch) + sl * VPL;
-        const int f4 = a.feat >> 2;
-        for (int s = 0; s < ns; ++s) {
-            const float4* p = sb + (int64_t)(s0 + s) * f4;
-#pragma unroll
-            for (int q = 0; q < VPL; ++q) add4(acc[q], __ldcg(p + q));   // L2: written by other SMs
-        }
-        finish_row<VPL>(a, row, sl, acc);
-        return;
-    }
-    const int64_t i = item - a.num_seg;
-    const int64_t row = a.row_perm ? __ldg(a.row_perm + i) : i;
-    const int beg = __ldg(a.rowptr + row), end = __ldg(a.rowptr + row + 1);
-    if (a.seg_len > 0 && end - beg > a.seg_len) return;          // finished from its segments
-    gather_range<LANES, VPL, WEIGHTED>(a, beg, end, sl, mask, acc);
-    finish_row<VPL>(a, row, sl, acc);
-}
 
 // any feature width / alignment: one warp per item, 32-wide scalar strips (coalesced 128 B)
 __global__ void __launch_bounds__(256) spmm_generic_kernel(const SpmmArgs a) {
@@ -253,9 +131,9 @@ template <int F>
 struct StreamCfg {
     static constexpr int LPE = F / 4;                    // lanes per edge in the async copy (16 B each)
     static constexpr int EPI = 32 / LPE;                 // edges per cp.async instruction
-    static constexpr int CHUNK = F >= 128 ? 16 : 32;     // edges per chunk (8 KB for F = 64 / 128)
+    static constexpr int CHUNK = F >= 128 ? 8 : 16;      // edges per chunk (4 KB for F = 64 / 128)
     static constexpr int VPT = F / 32;                   // floats per lane in the consume phase
-    static constexpr int WARPS = 4;
+    static constexpr int WARPS = 8;
     static constexpr int RING = 2;
     static constexpr int SMEM_BYTES = WARPS * RING * CHUNK * F * 4;
 };
@@ -269,7 +147,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int F, bool WEIGHTED>
-__global__ void __launch_bounds__(128) spmm_stream_kernel(const SpmmArgs a, const int32_t* __restrict__ grp_row, int num_grp) {
+__global__ void __launch_bounds__(256) spmm_stream_kernel(const SpmmArgs a, const int32_t* __restrict__ grp_row, int num_grp) {
     using C = StreamCfg<F>;
     extern __shared__ __align__(16) float smem_f[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -378,20 +256,27 @@ __global__ void __launch_bounds__(128) spmm_stream_kernel(const SpmmArgs a, cons
                 run = min(run, cur_end - (base + j));
                 if (run <= 0) { flush(); continue; }
             }
-#pragma unroll 4
-            for (int t = 0; t < run; ++t) {
-                const float w = WEIGHTED ? __shfl_sync(0xffffffffu, wreg, j + t) : 1.0f;
-                const float* q = sp + (j + t) * F;
-                if (C::VPT == 4) {
-                    const float4 v = *reinterpret_cast<const float4*>(q);
-                    acc[0] = fmaf(w, v.x, acc[0]); acc[1 % C::VPT] = fmaf(w, v.y, acc[1 % C::VPT]);
-                    acc[2 % C::VPT] = fmaf(w, v.z, acc[2 % C::VPT]); acc[3 % C::VPT] = fmaf(w, v.w, acc[3 % C::VPT]);
-                } else if (C::VPT == 2) {
-                    const float2 v = *reinterpret_cast<const float2*>(q);
-                    acc[0] = fmaf(w, v.x, acc[0]); acc[1 % C::VPT] = fmaf(w, v.y, acc[1 % C::VPT]);
-                } else {
-                    acc[0] = fmaf(w, q[0], acc[0]);
+            for (int t0 = 0; t0 < run; t0 += 8) {
+                float vv[8][C::VPT], ww[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int t = t0 + u;
+                    ww[u] = (t < run) ? (WEIGHTED ? __shfl_sync(0xffffffffu, wreg, (j + t) & 31) : 1.0f) : 0.f;
+                    const float* q = sp + (j + min(t, run - 1)) * F;
+                    if (C::VPT == 4) {
+                        const float4 v = *reinterpret_cast<const float4*>(q);
+                        vv[u][0] = v.x; vv[u][1 % C::VPT] = v.y; vv[u][2 % C::VPT] = v.z; vv[u][3 % C::VPT] = v.w;
+                    } else if (C::VPT == 2) {
+                        const float2 v = *reinterpret_cast<const float2*>(q);
+                        vv[u][0] = v.x; vv[u][1 % C::VPT] = v.y;
+                    } else {
+                        vv[u][0] = q[0];
+                    }
                 }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+#pragma unroll
+                    for (int v = 0; v < C::VPT; ++v) acc[v] = fmaf(ww[u], vv[u][v], acc[v]);
             }
             j += run;
         }
@@ -448,10 +333,10 @@ static int launch_stream(const SpmmArgs& a, const int32_t* grp_row, int num_grp,
     if (blocks == 0) return GD_OK;
     if (weighted) {
         GD_CUDA(cudaFuncSetAttribute(spmm_stream_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        spmm_stream_kernel<F, true><<<blocks, 128, C::SMEM_BYTES, stream>>>(a, grp_row, num_grp);
+        spmm_stream_kernel<F, true><<<blocks, 32 * C::WARPS, C::SMEM_BYTES, stream>>>(a, grp_row, num_grp);
     } else {
         GD_CUDA(cudaFuncSetAttribute(spmm_stream_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        spmm_stream_kernel<F, false><<<blocks, 128, C::SMEM_BYTES, stream>>>(a, grp_row, num_grp);
+        spmm_stream_kernel<F, false><<<blocks, 32 * C::WARPS, C::SMEM_BYTES, stream>>>(a, grp_row, num_grp);
     }
     GD_LAUNCH_CHECK();
     return GD_OK;
@@ -469,7 +354,8 @@ static int launch_stream(const SpmmArgs& a, const int32_t* grp_row, int num_grp,
 // steady state a row costs one memory latency instead of three and the resident warps keep the
 // gather queue full.  Long rows are cut into segments (scheduled first, ticket finalize).
 template <int LANES, bool WEIGHTED>
-__global__ void __launch_bounds__(256) spmm_pipe_kernel(const SpmmArgs a) {
+__global__ void __launch_bounds__(256) spmm_pipe_kernel(   // (256, 5) would spill at 48 regs and is slower (measured)
+    const SpmmArgs a) {
     constexpr int PER_WARP = 32 / LANES;
     constexpr int B = 8;                                       // gathers in flight per lane and batch
     const int lane = threadIdx.x & 31;
@@ -594,19 +480,6 @@ static int launch_pipe(const SpmmArgs& a, bool weighted, cudaStream_t stream) {
     return GD_OK;
 }
 
-template <int LANES, int VPL>
-static int launch_vec(const SpmmArgs& a, bool weighted, cudaStream_t stream) {
-    constexpr int PER_WARP = 32 / LANES;
-    const int64_t items = a.num_seg + a.num_rows;
-    const int64_t blocks = ceil_div<int64_t>(ceil_div<int64_t>(items, PER_WARP), 8);
-    if (blocks > 0) {
-        if (weighted) spmm_vec_kernel<LANES, VPL, true><<<(unsigned)blocks, 256, 0, stream>>>(a);
-        else spmm_vec_kernel<LANES, VPL, false><<<(unsigned)blocks, 256, 0, stream>>>(a);
-        GD_LAUNCH_CHECK();
-    }
-    return GD_OK;
-}
-
 }  // namespace gd
 
 using namespace gd;
@@ -636,10 +509,10 @@ extern "C" int gd_spmm(const gd_csr_t* csr, const float* val, const float* col_s
     const bool vec_ok = (ldx % 4 == 0) && (ldo % 4 == 0) &&
                         (((uintptr_t)x | (uintptr_t)out | (uintptr_t)scratch | (uintptr_t)bias) % 16 == 0) &&
                         ((double)csr->num_rows * (double)(ldx / 4) < 4.0e9);   // 32-bit float4 offsets
-    // GD_SPMM = pipe (default) | stream | vec selects the aggregation kernel (for A/B measurements)
+    // GD_SPMM = pipe (default) | stream selects the aggregation kernel (for A/B measurements)
     static const int mode = [] {
         const char* e = getenv("GD_SPMM");
-        return !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'v' ? 2 : 0));
+        return (e && e[0] == 's') ? 1 : 0;
     }();
     if (vec_ok && mode == 0) {
         if (feat == 128) return launch_pipe<32>(a, weighted, stream);
@@ -651,9 +524,6 @@ extern "C" int gd_spmm(const gd_csr_t* csr, const float* val, const float* col_s
         if (feat == 64) return launch_stream<64>(a, csr->grp_row, csr->num_grp, weighted, stream);
         if (feat == 32) return launch_stream<32>(a, csr->grp_row, csr->num_grp, weighted, stream);
     }
-    if (vec_ok && feat == 128) return launch_vec<8, 4>(a, weighted, stream);
-    if (vec_ok && feat == 64) return launch_vec<4, 4>(a, weighted, stream);
-    if (vec_ok && feat == 32) return launch_vec<4, 2>(a, weighted, stream);
     const int64_t items = a.num_seg + a.num_rows;
     spmm_generic_kernel<<<(unsigned)ceil_div<int64_t>(items, 8), 256, 0, stream>>>(a);
     GD_LAUNCH_CHECK();

@@ -86,7 +86,7 @@ def row_groups(rowptr, seg_len, target=GROUP_NNZ):
     return torch.cat([first, first.new_tensor([n])]).to(torch.int32)
 
 
-def build_csr(src, dst, num_nodes, self_loops=False, rel=None, num_rel=1, seg_len=SEG_LEN, deg_sort=True):
+def build_csr(src, dst, num_nodes, self_loops=False, rel=None, num_rel=1, seg_len=SEG_LEN, deg_sort=False):
     """COO (int64, ``src -> dst``) -> :class:`CSR` via ``gd_csr_from_coo`` +
     ``gd_spmm_plan_build``.  Raises on out-of-range endpoints."""
     dev = src.device
@@ -125,7 +125,7 @@ def build_csr(src, dst, num_nodes, self_loops=False, rel=None, num_rel=1, seg_le
         if nh > 0:
             bufs['heavy_ticket'] = torch.zeros(nh, dtype=torch.int32, device=dev)
             plan = dict(seg_len=int(seg_len), num_heavy=nh, num_seg=ns, **bufs)
-    perm = degree_window_perm(rowptr) if (deg_sort and N > 0) else None
+    perm = None      # visiting-order permutation: unused by the row-pipelined kernel (kept in the ABI)
     groups = row_groups(rowptr, int(seg_len) if seg_len else 0) if N > 0 else None
     return CSR(rowptr, col, eid, rel_out, N, nnz, plan, perm, groups)
 
