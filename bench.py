@@ -30,6 +30,7 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 METRIC = 'Del-training epochs/s on OGB-Collab shape'
+NCU_DRAM_BYTES_SPMM_L2 = 98_713_856 + 43_857_408      # profiles/r1_spmm_pipe_ncu_full.md
 UNIT = 'epochs/s'
 
 
@@ -389,8 +390,12 @@ def main():
     b128 = spmm_algo_bytes(n, nnz, shape.hidden_dim)
     achieved = b64 / (kt['spmm_l2_f64'] * 1e-3) / 1e9
     roofline = {
-        'kernel': 'spmm_vec_kernel<16> (GCN layer-2 aggregation, F=64)', 'bound': 'hbm',
-        'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+        'kernel': 'gd::spmm_pipe_kernel<16,false> (GCN layer-2 aggregation, F=64)', 'bound': 'hbm',
+        'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one
+        # `ncu --set full` capture (profiles/r1_spmm_pipe_ncu_full.md); only meaningful for the Collab shape
+        'traffic': NCU_DRAM_BYTES_SPMM_L2 if shape.name == 'collab' else None,
+        'gather_ceiling_tbs': 18.0, 'gathered_tbs': (4 * nnz * shape.out_dim) / (kt['spmm_l2_f64'] * 1e-3) / 1e12,
         'peak_source': peak_src, 'algorithmic_bytes_per_launch': b64, 'kernel_ms': kt['spmm_l2_f64'],
         'bytes_gather_per_launch': b64 - 4 * n * shape.out_dim + 4 * nnz * shape.out_dim,
         'other_kernels': {
@@ -405,14 +410,13 @@ def main():
     # ---- e2e: public API with host buffers — per step: pinned negatives -> device, plan
     #      refresh, epoch, losses -> host
     eng_e = GCNDeleteEngine(model, data, neg, z_ori=z_ori, hoist_layer1=False)
+    eng_e.capture(warmup=2, dynamic_negatives=True)      # the graph rebuilds the negative incidence from a staging buffer
     neg_host = neg.cpu().pin_memory()
-    neg_dev = torch.empty_like(neg)
     out_host = torch.empty(3, dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        neg_dev.copy_(neg_host, non_blocking=True)
-        eng_e.set_negatives(neg_dev)
-        out_host.copy_(eng_e.epoch(), non_blocking=True)
+        eng_e.set_negatives(neg_host)                     # pinned host -> device staging buffer (async H2D)
+        out_host.copy_(eng_e.epoch(), non_blocking=True)  # one graph launch, then losses -> pinned host
         torch.cuda.current_stream().synchronize()
 
     for _ in range(3):
@@ -426,7 +430,8 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0, world, dev)
     e2e = {'value': world * e2e_steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': neg_host.numel() * 8,
            'd2h_bytes_per_step': 12, 'steps': e2e_steps,
-           'what': 'per step: supplied negatives pinned-host->device, pair-plan refresh, epoch, losses->host'}
+           'what': 'per step through GCNDeleteEngine: supplied negatives pinned-host -> device, in-graph rebuild of the '
+                   'negative-pair incidence (radix sort), epoch (one CUDA-graph launch), losses -> pinned host, sync'}
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,

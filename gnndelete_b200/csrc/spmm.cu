@@ -40,6 +40,7 @@ struct SpmmArgs {
     int64_t num_rows;
     int32_t num_seg, num_heavy, seg_len, feat;
     float self_coef;
+    int accumulate;          // out += result instead of out = result
 };
 
 // any feature width / alignment: one warp per item, 32-wide scalar strips (coalesced 128 B)
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(256) spmm_generic_kernel(const SpmmArgs a) {
             if (a.row_scale) r *= a.row_scale[row];
             if (a.self_coef != 0.f) r = fmaf(a.self_coef, a.x[row * a.ldx + f], r);
             if (a.bias) r += a.bias[f];
+            if (a.accumulate) r += a.out[row * a.ldo + f];
             a.out[row * a.ldo + f] = r;
         }
     }
@@ -107,6 +109,7 @@ __global__ void __launch_bounds__(256) spmm_generic_finalize_kernel(const SpmmAr
         if (a.row_scale) r *= a.row_scale[row];
         if (a.self_coef != 0.f) r = fmaf(a.self_coef, a.x[row * a.ldx + f], r);
         if (a.bias) r += a.bias[f];
+        if (a.accumulate) r += a.out[row * a.ldo + f];
         a.out[row * a.ldo + f] = r;
     }
 }
@@ -454,7 +457,9 @@ __global__ void __launch_bounds__(256) spmm_pipe_kernel(   // (256, 5) would spi
                 if (a.row_scale) { const float s = __ldg(a.row_scale + r0); acc.x *= s; acc.y *= s; acc.z *= s; acc.w *= s; }
                 if (a.self_coef != 0.f) fma4(acc, a.self_coef, __ldg(reinterpret_cast<const float4*>(a.x + (int64_t)r0 * a.ldx) + sl));
                 if (a.bias) add4(acc, __ldg(reinterpret_cast<const float4*>(a.bias) + sl));
-                stg4(a.out + (int64_t)r0 * a.ldo + sl * 4, acc);
+                float* op = a.out + (int64_t)r0 * a.ldo + sl * 4;
+                if (a.accumulate) add4(acc, *reinterpret_cast<const float4*>(op));
+                stg4(op, acc);
             }
         }
         // ---- rotate the pipeline
@@ -487,6 +492,12 @@ using namespace gd;
 extern "C" int gd_spmm(const gd_csr_t* csr, const float* val, const float* col_scale, const float* row_scale,
                        const float* x, int64_t ldx, int32_t feat, float self_coef, const float* bias,
                        float* out, int64_t ldo, float* scratch, gd_stream_t stream_) {
+    return gd_spmm_acc(csr, val, col_scale, row_scale, x, ldx, feat, self_coef, bias, out, ldo, scratch, 0, stream_);
+}
+
+extern "C" int gd_spmm_acc(const gd_csr_t* csr, const float* val, const float* col_scale, const float* row_scale,
+                           const float* x, int64_t ldx, int32_t feat, float self_coef, const float* bias,
+                           float* out, int64_t ldo, float* scratch, int32_t accumulate, gd_stream_t stream_) {
     cudaStream_t stream = as_stream(stream_);
     GD_CHECK_ARG(csr != nullptr, "null csr");
     GD_CHECK_ARG(feat > 0, "feat must be positive");
@@ -505,6 +516,7 @@ extern "C" int gd_spmm(const gd_csr_t* csr, const float* val, const float* col_s
     a.ldx = ldx; a.ldo = ldo; a.num_rows = csr->num_rows;
     a.num_seg = csr->num_seg; a.num_heavy = csr->num_heavy; a.seg_len = csr->seg_len; a.feat = feat;
     a.self_coef = self_coef;
+    a.accumulate = accumulate;
     const bool weighted = val != nullptr || col_scale != nullptr;
     const bool vec_ok = (ldx % 4 == 0) && (ldo % 4 == 0) &&
                         (((uintptr_t)x | (uintptr_t)out | (uintptr_t)scratch | (uintptr_t)bias) % 16 == 0) &&
@@ -519,7 +531,7 @@ extern "C" int gd_spmm(const gd_csr_t* csr, const float* val, const float* col_s
         if (feat == 64) return launch_pipe<16>(a, weighted, stream);
         if (feat == 32) return launch_pipe<8>(a, weighted, stream);
     }
-    if (vec_ok && mode == 1 && csr->grp_row && csr->num_grp > 0) {
+    if (vec_ok && mode == 1 && !accumulate && csr->grp_row && csr->num_grp > 0) {
         if (feat == 128) return launch_stream<128>(a, csr->grp_row, csr->num_grp, weighted, stream);
         if (feat == 64) return launch_stream<64>(a, csr->grp_row, csr->num_grp, weighted, stream);
         if (feat == 32) return launch_stream<32>(a, csr->grp_row, csr->num_grp, weighted, stream);

@@ -74,6 +74,7 @@ class GCNDeleteEngine:
         self.state = [dict(m=torch.zeros_like(p), v=torch.zeros_like(p), step=torch.zeros(1, **f32))
                       for p in self.params]
         self.graph = None
+        self._graph_dynamic_neg = False
         self.launches_per_epoch = None
 
     # ------------------------------------------------------------------ forward
@@ -137,7 +138,7 @@ class GCNDeleteEngine:
         return losses
 
     # --------------------------------------------------------------- CUDA graph
-    def capture(self, warmup=2):
+    def capture(self, warmup=2, dynamic_negatives=False):
         """Capture one epoch into a CUDA graph.  Warm-up epochs run first (module loading
         and workspace allocation are not capturable) and are undone, so the captured
         graph starts from the current parameters and optimizer state."""
@@ -153,8 +154,11 @@ class GCNDeleteEngine:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
+            if dynamic_negatives:
+                self.loss.update_negatives()          # rebuild the negative incidence from the staging buffer
             self.forward_backward()
             self.adam_step()
+        self._graph_dynamic_neg = bool(dynamic_negatives)
         self._restore(snap_p, snap_s)
         self.graph = g
         return g
@@ -168,12 +172,11 @@ class GCNDeleteEngine:
                     st[k].copy_(ss[k])
 
     def set_negatives(self, neg_edge_index):
-        """New supplied negatives (the reference resamples them every epoch,
-        gnndelete.py:221-225).  Rebuilds the pair plan; invalidates a captured graph."""
-        old = self.loss
-        n_df = old.n_df
-        p = old.pairs
-        df = torch.stack([p.pu[:n_df], p.pv[:n_df]]).long()
-        ni = torch.stack([p.pu[2 * n_df:], p.pv[2 * n_df:]]).long()
-        self.loss = EdgeLossPlan(df, neg_edge_index, ni, self.n, target=old.target, alpha=old.alpha)
-        self.graph = None
+        """New supplied negatives (the reference resamples them every epoch, gnndelete.py:221-225).
+        Eager mode: the negative incidence is rebuilt in place right away.  After ``capture(
+        dynamic_negatives=True)`` the rebuild is part of the graph: only the staging buffer is
+        overwritten here (host or device source) and the next ``epoch()`` picks it up."""
+        if self.graph is not None and self._graph_dynamic_neg:
+            self.loss.neg_buf.copy_(neg_edge_index, non_blocking=True)
+        else:
+            self.loss.update_negatives(neg_edge_index)

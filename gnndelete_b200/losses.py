@@ -48,44 +48,109 @@ class EdgeLossPlan:
 
     ``target`` are the original model's logits on the NI pairs
     (``(z_ori[row] * z_ori[col]).sum(-1)``, gnndelete.py:383); they are constant over
-    the run, so they are computed once (with the decode kernel) instead of per step."""
+    the run, so they are computed once (with the decode kernel) instead of per step.
+
+    The incidence structure is split in two: a FIXED CSR over the Df + NI pairs (built once)
+    and a small CSR over the negative pairs that :meth:`update_negatives` rebuilds in place —
+    the reference draws new negatives every epoch (gnndelete.py:221-225).  The update is a
+    radix sort of ``2 n_df`` keys into preallocated buffers with no host synchronisation, so it
+    can live inside the epoch's CUDA graph; ``dz`` is the fixed gather plus the accumulated
+    negative gather."""
 
     def __init__(self, df_edges, neg_edges, ni_edges, num_nodes, z_ori=None, target=None, alpha=0.5):
-        self.n_df = df_edges.shape[1]
-        assert neg_edges.shape[1] == self.n_df, 'one negative per Df entry (gnndelete.py:221-228)'
-        self.n_ni = ni_edges.shape[1]
-        pu = torch.cat([df_edges[0], neg_edges[0], ni_edges[0]])
-        pv = torch.cat([df_edges[1], neg_edges[1], ni_edges[1]])
-        self.pairs = PairPlan(pu, pv, num_nodes)
-        dev = pu.device
+        dev = df_edges.device
+        n_df, n_ni, n = df_edges.shape[1], ni_edges.shape[1], int(num_nodes)
+        assert neg_edges.shape[1] == n_df, 'one negative per Df entry (gnndelete.py:221-228)'
+        self.n_df, self.n_ni, self.num_nodes = n_df, n_ni, n
+        P = 2 * n_df + n_ni
+        self.num_pairs = P
+        self.pu = torch.cat([df_edges[0], neg_edges[0], ni_edges[0]]).to(torch.int32).contiguous()
+        self.pv = torch.cat([df_edges[1], neg_edges[1], ni_edges[1]]).to(torch.int32).contiguous()
+        if self.pu.numel() == 0:
+            self.pu = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.pv = torch.zeros(1, dtype=torch.int32, device=dev)
+        # ---- fixed incidence: entry e < Pf is the u side of fixed pair e, entry Pf + e its v side
+        fu = torch.cat([df_edges[0], ni_edges[0]]).long()
+        fv = torch.cat([df_edges[1], ni_edges[1]]).long()
+        Pf = n_df + n_ni
+        self.inc_fixed = build_csr(torch.cat([fv, fu]), torch.cat([fu, fv]), n, self_loops=False)
+        posf = invert_perm(self.inc_fixed.eid, max(2 * Pf, 1))
+        self.nnz_fixed = 2 * Pf
+        self.pos_u = torch.zeros(max(P, 1), dtype=torch.int32, device=dev)
+        self.pos_v = torch.zeros(max(P, 1), dtype=torch.int32, device=dev)
+        self.pos_u[:n_df] = posf[:n_df]
+        self.pos_v[:n_df] = posf[Pf:Pf + n_df]
+        self.pos_u[2 * n_df:P] = posf[n_df:Pf]
+        self.pos_v[2 * n_df:P] = posf[Pf + n_df:2 * Pf]
+        # ---- negative incidence: persistent buffers, rebuilt by update_negatives
+        m = 2 * n_df
+        self.neg_src = torch.zeros(max(m, 1), dtype=torch.int64, device=dev)
+        self.neg_dst = torch.zeros(max(m, 1), dtype=torch.int64, device=dev)
+        self.neg_rowptr = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+        self.neg_col = torch.zeros(max(m, 1), dtype=torch.int32, device=dev)
+        self.neg_eid = torch.zeros(max(m, 1), dtype=torch.int32, device=dev)
+        self.neg_pos = torch.zeros(max(m, 1), dtype=torch.int32, device=dev)
+        self.neg_status = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.neg_ws_bytes = L.load().gd_csr_workspace_bytes(m, n)
+        self.neg_ws = torch.empty(self.neg_ws_bytes, dtype=torch.uint8, device=dev)
+        from .graph import CSR
+        self.inc_neg = CSR(self.neg_rowptr, self.neg_col, self.neg_eid, None, n, m)
+        self.inc_val = torch.zeros(max(self.nnz_fixed + m, 1), dtype=torch.float32, device=dev)
+        self.neg_buf = neg_edges.clone()             # staging buffer a caller may overwrite (H2D) before a graph replay
+        self.update_negatives()
         if target is None:
-            if self.n_ni > 0:
-                p = self.pairs
-                target = ops.pair_decode(z_ori, p.pu[2 * self.n_df:].contiguous(), p.pv[2 * self.n_df:].contiguous())
+            if n_ni > 0:
+                target = ops.pair_decode(z_ori, self.pu[2 * n_df:P].contiguous(), self.pv[2 * n_df:P].contiguous())
             else:
                 target = torch.zeros(1, dtype=torch.float32, device=dev)
         self.target = target.contiguous()
         self.alpha = float(alpha)
-        P = self.pairs.num_pairs
         self.logits = torch.empty(max(P, 1), dtype=torch.float32, device=dev)
-        self.inc_val = torch.zeros(max(2 * P, 1), dtype=torch.float32, device=dev)
         self.losses = torch.zeros(3, dtype=torch.float32, device=dev)
         self.ws_bytes = L.load().gd_edge_loss_workspace_bytes(P)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
 
+    def update_negatives(self, neg_edges=None):
+        """Install new negatives (default: whatever is in ``self.neg_buf``).  No allocation, no host sync."""
+        n_df = self.n_df
+        if n_df == 0:
+            return
+        if neg_edges is not None:
+            self.neg_buf.copy_(neg_edges)
+        nu, nv = self.neg_buf[0], self.neg_buf[1]
+        self.pu[n_df:2 * n_df].copy_(nu)
+        self.pv[n_df:2 * n_df].copy_(nv)
+        self.neg_dst[:n_df].copy_(nu); self.neg_dst[n_df:].copy_(nv)
+        self.neg_src[:n_df].copy_(nv); self.neg_src[n_df:].copy_(nu)
+        m = 2 * n_df
+        L.call('gd_csr_from_coo', L.ptr(self.neg_src), L.ptr(self.neg_dst), None, m, self.num_nodes, 1, 0,
+               L.ptr(self.neg_rowptr), L.ptr(self.neg_col), L.ptr(self.neg_eid), None, L.ptr(self.neg_status),
+               L.ptr(self.neg_ws), self.neg_ws_bytes, L.stream())
+        L.call('gd_invert_perm', L.ptr(self.neg_eid), m, L.ptr(self.neg_pos), L.stream())
+        torch.add(self.neg_pos[:n_df], self.nnz_fixed, out=self.pos_u[n_df:2 * n_df])
+        torch.add(self.neg_pos[n_df:m], self.nnz_fixed, out=self.pos_v[n_df:2 * n_df])
+
+    def check_negatives(self):
+        """Host-side validation of the last update (synchronises): raises on out-of-range endpoints."""
+        bad = int(self.neg_status[1].item())
+        if bad:
+            raise ValueError(f'negative edges hold {bad} endpoints outside [0, {self.num_nodes})')
+
     def forward(self, z):
         """Fills ``self.losses`` = (loss, loss_r, loss_l), ``self.logits`` and the incidence
         values; returns ``self.losses`` (a persistent device tensor, no host sync)."""
-        p = self.pairs
-        L.call('gd_edge_loss_fwd', L.ptr(z, 'f32'), z.stride(0), z.shape[1], L.ptr(p.pu), L.ptr(p.pv),
-               self.n_df, self.n_ni, L.ptr(self.target), self.alpha, L.ptr(p.pos_u), L.ptr(p.pos_v),
+        L.call('gd_edge_loss_fwd', L.ptr(z, 'f32'), z.stride(0), z.shape[1], L.ptr(self.pu), L.ptr(self.pv),
+               self.n_df, self.n_ni, L.ptr(self.target), self.alpha, L.ptr(self.pos_u), L.ptr(self.pos_v),
                L.ptr(self.logits), L.ptr(self.inc_val), L.ptr(self.losses), L.ptr(self.ws), self.ws_bytes,
                L.stream())
         return self.losses
 
     def backward(self, z, out=None):
         """dz = d loss / d z for the ``z`` last given to :meth:`forward`."""
-        return ops.spmm(self.pairs.inc, z, out=out, val=self.inc_val)
+        out = ops.spmm(self.inc_fixed, z, out=out, val=self.inc_val[:max(self.nnz_fixed, 1)])
+        if self.n_df > 0:
+            ops.spmm(self.inc_neg, z, out=out, val=self.inc_val[self.nnz_fixed:], accumulate=True)
+        return out
 
 
 class EdgeLossFn(torch.autograd.Function):

@@ -27,13 +27,16 @@ def _f32(t):
 
 
 # ------------------------------------------------------------------ raw kernels
-def spmm(csr: CSR, x, out=None, val=None, col_scale=None, row_scale=None, self_coef=0.0, bias=None):
+def spmm(csr: CSR, x, out=None, val=None, col_scale=None, row_scale=None, self_coef=0.0, bias=None,
+         accumulate=False):
     x = _f32(x)
     n, f = csr.num_rows, x.shape[1]
     if out is None:
+        assert not accumulate, 'accumulate needs an output buffer'
         out = torch.empty(n, f, dtype=torch.float32, device=x.device)
-    L.call('gd_spmm', csr.ref, L.ptr(val), L.ptr(col_scale), L.ptr(row_scale), L.ptr(x), x.stride(0), f,
-           float(self_coef), L.ptr(bias), L.ptr(out), out.stride(0), L.ptr(csr.scratch(f)), L.stream())
+    L.call('gd_spmm_acc', csr.ref, L.ptr(val), L.ptr(col_scale), L.ptr(row_scale), L.ptr(x), x.stride(0), f,
+           float(self_coef), L.ptr(bias), L.ptr(out), out.stride(0), L.ptr(csr.scratch(f)), int(bool(accumulate)),
+           L.stream())
     return out
 
 

@@ -119,6 +119,12 @@ int gd_spmm(const gd_csr_t* csr, const float* val, const float* col_scale, const
             const float* x, int64_t ldx, int32_t feat, float self_coef, const float* bias,
             float* out, int64_t ldo, float* scratch, gd_stream_t stream);
 
+/* gd_spmm with out += result when `accumulate` is non-zero (the loss gradient is the sum of the
+ * gather over the fixed pairs and the gather over this step's negative pairs). */
+int gd_spmm_acc(const gd_csr_t* csr, const float* val, const float* col_scale, const float* row_scale,
+                const float* x, int64_t ldx, int32_t feat, float self_coef, const float* bias,
+                float* out, int64_t ldo, float* scratch, int32_t accumulate, gd_stream_t stream);
+
 /* GATConv(heads=1) edge-softmax aggregation (gat.py:11-12; defaults negative_slope=0.2,
  * add_self_loops=True — the CSR must be built with self_loops=1):
  *   a_src[k] = <h_k, att_src>, a_dst[i] = <h_i, att_dst>                 (gd_gat_scores)
