@@ -29,6 +29,18 @@ class CsrStruct(C.Structure):
 
 _csr_p = C.POINTER(CsrStruct)
 
+
+class BplanStruct(C.Structure):
+    """``gd_spmm_bplan_t``"""
+    _fields_ = [
+        ('num_rows', _i64), ('num_batches', _i64), ('num_workers', _i32), ('batches_per_worker', _i32),
+        ('desc', _vp), ('colp', _vp), ('num_split', _i32), ('num_piece', _i32),
+        ('piece_split', _vp), ('split_row', _vp), ('split_piece_beg', _vp), ('split_npiece', _vp), ('split_ticket', _vp),
+    ]
+
+
+_bplan_p = C.POINTER(BplanStruct)
+
 # name -> (restype, argtypes); must list every symbol the header declares
 SIGNATURES = {
     'gd_version': (C.c_int, []),
@@ -41,6 +53,8 @@ SIGNATURES = {
     'gd_spmm_plan_build': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'gd_spmm': (C.c_int, [_csr_p, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _vp]),
     'gd_spmm_acc': (C.c_int, [_csr_p, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _i32, _vp]),
+    'gd_spmm_batched_workers': (_i32, [_i32, _i32]),
+    'gd_spmm_batched': (C.c_int, [_bplan_p, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _i32, _vp]),
     'gd_gat_scores': (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     'gd_gat_fwd': (C.c_int, [_csr_p, _vp, _i64, _i32, _vp, _vp, _vp, _f32, _vp, _i64, _vp, _vp, _vp]),
     'gd_gat_bwd_dst': (C.c_int, [_csr_p, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _f32,

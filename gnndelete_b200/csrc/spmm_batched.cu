@@ -1,0 +1,212 @@
+// Batched CSR aggregation: the same contract as gd_spmm on a BATCH PLAN built once per edge set.
+//
+// Why: tools/gather_bench.cu shows that a loop of "8 independent 128-bit row gathers per lane,
+// then add" sustains 16-18 TB/s of L2-resident row gathers on B200, while the row-pipelined
+// kernel in spmm.cu reaches 5.2-5.7 TB/s: ncu (profiles/r1_spmm_pipe_ncu_full.md) shows it
+// executing ~23 warp instructions per non-zero (row bookkeeping, per-element predicates, shuffles)
+// with the issue slots 50-64 % busy, i.e. it is instruction bound, not bandwidth bound.
+//
+// The batch plan removes all row bookkeeping from the kernel:
+//   * every row is cut into BATCHES of 8 column slots (the last one padded with -1; an empty row
+//     is one all-padding batch), stored in a padded column array colp[num_batches][8] so that the
+//     slots of batch b are two aligned 128-bit loads whose address depends on b only;
+//   * desc[b] says whether the batch ends its row (FLUSH) and which row that is;
+//   * the flat batch list is cut into `num_workers` contiguous ranges of EQUAL length, one per
+//     resident sub-warp (F/4 lanes), so the load balance is exact by construction whatever the
+//     degree distribution.  A row that straddles a range boundary becomes PIECES: partial sums go
+//     to scratch and the sub-warp that completes the row's last piece (ticket counter) adds them
+//     in piece order - deterministic, no float atomics, a 7000-neighbour hub is simply spread
+//     over ~25 workers.
+// Per batch a sub-warp issues 8 independent LDG.128 (the column ids, descriptor and row scale of
+// the NEXT batch are already in flight), adds, and flushes when the descriptor says so.
+#include "common.cuh"
+
+namespace gd {
+
+constexpr int kDescFlush = (int)0x80000000u;
+constexpr int kDescPiece = 0x40000000;
+constexpr int kDescId = 0x3fffffff;
+
+struct BArgs {
+    const int32_t* desc;
+    const int4* colp;
+    const float4* valp;
+    const float* row_scale;
+    const float* x;
+    const float* bias;
+    float* out;
+    float* scratch;
+    const int32_t* piece_split;
+    const int32_t* split_row;
+    const int32_t* split_piece_beg;
+    const int32_t* split_npiece;
+    int32_t* split_ticket;
+    int64_t ldx, ldo;
+    int32_t num_batches, per_worker, feat, accumulate;
+    float self_coef;
+};
+
+template <int LANES, bool WEIGHTED>
+__global__ void __launch_bounds__(256) spmm_batched_kernel(const BArgs a) {
+    constexpr int PER_WARP = 32 / LANES;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LANES, sl = lane % LANES;
+    const unsigned mask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (sub * LANES));
+    const int64_t worker = ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5) * PER_WARP + sub;
+    const int64_t b0 = worker * a.per_worker;
+    if (b0 >= a.num_batches) return;
+    int b = (int)b0;
+    const int bend = (int)min(b0 + (int64_t)a.per_worker, (int64_t)a.num_batches);
+    const float4* xb = reinterpret_cast<const float4*>(a.x) + sl;
+    const unsigned ld4 = (unsigned)(a.ldx >> 2);
+
+    auto scale_of = [&](int d) -> float {      // row scale of a batch that flushes a whole row
+        return (a.row_scale && d < 0 && !(d & kDescPiece)) ? __ldg(a.row_scale + (d & kDescId)) : 1.0f;
+    };
+
+    int4 c0 = __ldg(a.colp + 2 * (int64_t)b), c1 = __ldg(a.colp + 2 * (int64_t)b + 1);
+    float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+    if (WEIGHTED) { w0 = __ldg(a.valp + 2 * (int64_t)b); w1 = __ldg(a.valp + 2 * (int64_t)b + 1); }
+    int d_cur = __ldg(a.desc + b);
+    int d_nxt = (b + 1 < bend) ? __ldg(a.desc + b + 1) : 0;
+    float rs_cur = scale_of(d_cur);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (; b < bend; ++b) {
+        // ---- 8 independent row gathers
+        float4 v[8];
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c1.w >= 0) {                        // padding is at the end of a batch: last slot valid = all valid
+            v[0] = __ldg(xb + (unsigned)c0.x * ld4); v[1] = __ldg(xb + (unsigned)c0.y * ld4);
+            v[2] = __ldg(xb + (unsigned)c0.z * ld4); v[3] = __ldg(xb + (unsigned)c0.w * ld4);
+            v[4] = __ldg(xb + (unsigned)c1.x * ld4); v[5] = __ldg(xb + (unsigned)c1.y * ld4);
+            v[6] = __ldg(xb + (unsigned)c1.z * ld4); v[7] = __ldg(xb + (unsigned)c1.w * ld4);
+        } else {
+            v[0] = c0.x >= 0 ? __ldg(xb + (unsigned)c0.x * ld4) : z4; v[1] = c0.y >= 0 ? __ldg(xb + (unsigned)c0.y * ld4) : z4;
+            v[2] = c0.z >= 0 ? __ldg(xb + (unsigned)c0.z * ld4) : z4; v[3] = c0.w >= 0 ? __ldg(xb + (unsigned)c0.w * ld4) : z4;
+            v[4] = c1.x >= 0 ? __ldg(xb + (unsigned)c1.x * ld4) : z4; v[5] = c1.y >= 0 ? __ldg(xb + (unsigned)c1.y * ld4) : z4;
+            v[6] = c1.z >= 0 ? __ldg(xb + (unsigned)c1.z * ld4) : z4; v[7] = z4;
+        }
+        const float4 wc0 = w0, wc1 = w1;
+        // ---- next batch: column ids (+ weights), the descriptor after it, its row scale
+        const int bn = b + 1;
+        int d_n2 = 0;
+        float rs_nxt = 1.0f;
+        if (bn < bend) {
+            c0 = __ldg(a.colp + 2 * (int64_t)bn); c1 = __ldg(a.colp + 2 * (int64_t)bn + 1);
+            if (WEIGHTED) { w0 = __ldg(a.valp + 2 * (int64_t)bn); w1 = __ldg(a.valp + 2 * (int64_t)bn + 1); }
+            if (bn + 1 < bend) d_n2 = __ldg(a.desc + bn + 1);
+            rs_nxt = scale_of(d_nxt);
+        }
+        // ---- accumulate
+        if (WEIGHTED) {
+            fma4(acc, wc0.x, v[0]); fma4(acc, wc0.y, v[1]); fma4(acc, wc0.z, v[2]); fma4(acc, wc0.w, v[3]);
+            fma4(acc, wc1.x, v[4]); fma4(acc, wc1.y, v[5]); fma4(acc, wc1.z, v[6]); fma4(acc, wc1.w, v[7]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) add4(acc, v[u]);
+        }
+        // ---- end of a row (or of this worker's piece of it)
+        if (d_cur < 0) {
+            int row = d_cur & kDescId;
+            float rs = rs_cur;
+            bool write = true;
+            if (d_cur & kDescPiece) {
+                const int piece = row;
+                stg4(a.scratch + (int64_t)piece * a.feat + sl * 4, acc);
+                const int h = __ldg(a.piece_split + piece);
+                const int np = __ldg(a.split_npiece + h);
+                __threadfence();
+                int ticket = 0;
+                if (sl == 0) ticket = atomicAdd(a.split_ticket + h, 1);
+                ticket = __shfl_sync(mask, ticket, 0, LANES);
+                write = ticket == np - 1;
+                if (write) {                     // last piece to arrive: add the partial sums in piece order
+                    __threadfence();
+                    if (sl == 0) a.split_ticket[h] = 0;
+                    const int p0 = __ldg(a.split_piece_beg + h);
+                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int p = 0; p < np; ++p)
+                        add4(acc, __ldcg(reinterpret_cast<const float4*>(a.scratch + (int64_t)(p0 + p) * a.feat) + sl));
+                    row = __ldg(a.split_row + h);
+                    rs = a.row_scale ? __ldg(a.row_scale + row) : 1.0f;
+                }
+            }
+            if (write) {
+                if (a.row_scale) { acc.x *= rs; acc.y *= rs; acc.z *= rs; acc.w *= rs; }
+                if (a.self_coef != 0.f) fma4(acc, a.self_coef, __ldg(xb + (unsigned)row * ld4));
+                if (a.bias) add4(acc, __ldg(reinterpret_cast<const float4*>(a.bias) + sl));
+                float* op = a.out + (int64_t)row * a.ldo + sl * 4;
+                if (a.accumulate) add4(acc, *reinterpret_cast<const float4*>(op));
+                stg4(op, acc);
+            }
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        d_cur = d_nxt; d_nxt = d_n2; rs_cur = rs_nxt;
+    }
+}
+
+template <int LANES, bool WEIGHTED>
+static int resident_workers() {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmm_batched_kernel<LANES, WEIGHTED>, 256, 0) != cudaSuccess) {
+        cudaGetLastError();
+        per_sm = 0;
+    }
+    if (per_sm <= 0) per_sm = 3;                 // no device in this process (plan built for a later run): assume 64-80 registers
+    return kNumSMs * per_sm * 8 * (32 / LANES);
+}
+
+template <int LANES>
+static int launch_batched(const BArgs& a, int64_t workers, bool weighted, cudaStream_t stream) {
+    const int per_cta = 8 * (32 / LANES);
+    const unsigned blocks = (unsigned)ceil_div<int64_t>(workers, per_cta);
+    if (blocks == 0) return GD_OK;
+    if (weighted) spmm_batched_kernel<LANES, true><<<blocks, 256, 0, stream>>>(a);
+    else spmm_batched_kernel<LANES, false><<<blocks, 256, 0, stream>>>(a);
+    GD_LAUNCH_CHECK();
+    return GD_OK;
+}
+
+}  // namespace gd
+
+using namespace gd;
+
+extern "C" int32_t gd_spmm_batched_workers(int32_t feat, int32_t weighted) {
+    switch (feat) {
+        case 128: return weighted ? resident_workers<32, true>() : resident_workers<32, false>();
+        case 64: return weighted ? resident_workers<16, true>() : resident_workers<16, false>();
+        case 32: return weighted ? resident_workers<8, true>() : resident_workers<8, false>();
+        default: return 0;
+    }
+}
+
+extern "C" int gd_spmm_batched(const gd_spmm_bplan_t* plan, const float* valp, const float* row_scale, const float* x,
+                               int64_t ldx, int32_t feat, float self_coef, const float* bias, float* out, int64_t ldo,
+                               float* scratch, int32_t accumulate, gd_stream_t stream_) {
+    cudaStream_t stream = as_stream(stream_);
+    GD_CHECK_ARG(plan != nullptr, "null plan");
+    GD_CHECK_ARG(feat == 32 || feat == 64 || feat == 128, "feat must be 32, 64 or 128");
+    if (plan->num_rows == 0 || plan->num_batches == 0) return GD_OK;
+    GD_CHECK_ARG(plan->desc && plan->colp && x && out, "null pointer");
+    GD_CHECK_ARG(plan->num_workers > 0 && plan->batches_per_worker > 0 &&
+                     (int64_t)plan->num_workers * plan->batches_per_worker >= plan->num_batches, "inconsistent worker partition");
+    GD_CHECK_ARG(plan->num_piece == 0 || (scratch && plan->piece_split && plan->split_row && plan->split_piece_beg &&
+                                          plan->split_npiece && plan->split_ticket), "split rows without scratch / ticket arrays");
+    GD_CHECK_ARG(ldx >= feat && ldo >= feat && ldx % 4 == 0 && ldo % 4 == 0, "leading dimensions must be multiples of 4 and >= feat");
+    GD_CHECK_ARG((((uintptr_t)x | (uintptr_t)out | (uintptr_t)scratch | (uintptr_t)bias | (uintptr_t)valp | (uintptr_t)plan->colp) % 16) == 0,
+                 "operands must be 16-byte aligned");
+    GD_CHECK_ARG((double)plan->num_rows * (double)(ldx / 4) < 4.0e9 && plan->num_rows < kDescId, "too many rows for 32-bit row offsets");
+    BArgs a;
+    a.desc = plan->desc; a.colp = reinterpret_cast<const int4*>(plan->colp); a.valp = reinterpret_cast<const float4*>(valp);
+    a.row_scale = row_scale; a.x = x; a.bias = bias; a.out = out; a.scratch = scratch;
+    a.piece_split = plan->piece_split; a.split_row = plan->split_row; a.split_piece_beg = plan->split_piece_beg;
+    a.split_npiece = plan->split_npiece; a.split_ticket = plan->split_ticket;
+    a.ldx = ldx; a.ldo = ldo;
+    a.num_batches = (int32_t)plan->num_batches; a.per_worker = plan->batches_per_worker; a.feat = feat; a.accumulate = accumulate;
+    a.self_coef = self_coef;
+    const bool weighted = valp != nullptr;
+    if (feat == 128) return launch_batched<32>(a, plan->num_workers, weighted, stream);
+    if (feat == 64) return launch_batched<16>(a, plan->num_workers, weighted, stream);
+    return launch_batched<8>(a, plan->num_workers, weighted, stream);
+}

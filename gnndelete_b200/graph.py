@@ -10,6 +10,7 @@ gnndelete.py:215), so the structures are built once by the CUDA builders in
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -18,6 +19,9 @@ from . import _lib as L
 SEG_LEN = 128    # rows longer than this are split into segments (spmm.cu)
 GROUP_NNZ = 128  # target entries per row group of the streaming aggregation kernel
 DEG_SORT_WINDOW = 4096
+# GD_SPMM=pipe|stream selects the older row-walking kernels (A/B measurements); default: batched
+BATCHED = os.environ.get('GD_SPMM', 'batched')[0] == 'b'
+OVERSUB = int(os.environ.get('GD_SPMM_OVERSUB', '1'))
 
 
 class CSR:
@@ -30,6 +34,8 @@ class CSR:
         self.num_rows, self.nnz = int(num_rows), int(nnz)
         self.plan = plan or {}
         self._scratch = {}
+        self._bplans = {}
+        self.dynamic = False     # True: the arrays are rewritten in place (no cached batch plan)
         s = L.CsrStruct()
         s.num_rows, s.nnz = self.num_rows, self.nnz
         s.rowptr, s.col = rowptr.data_ptr(), col.data_ptr()
@@ -49,6 +55,19 @@ class CSR:
     def num_seg(self):
         return self.plan.get('num_seg', 0)
 
+    def bplan(self, feat, weighted=False):
+        """Batch plan balanced for the sub-warps resident at this width (built on first use);
+        ``None`` when the batched kernel does not cover the width."""
+        if feat not in (32, 64, 128) or self.num_rows == 0 or self.num_rows >= (1 << 30) or not BATCHED or self.dynamic \
+                or self.nnz == 0:
+            return None
+        workers = L.load().gd_spmm_batched_workers(int(feat), int(bool(weighted))) * OVERSUB
+        bp = self._bplans.get(workers)
+        if bp is None:
+            bp = BatchPlan(self.rowptr, self.col, self.num_rows, self.nnz, workers)
+            self._bplans[workers] = bp
+        return bp
+
     def scratch(self, feat):
         """Per-width scratch for the split-row partial sums (allocated once)."""
         if self.num_seg == 0:
@@ -58,6 +77,117 @@ class CSR:
             buf = torch.empty(self.num_seg * feat, dtype=torch.float32, device=self.rowptr.device)
             self._scratch[feat] = buf
         return buf
+
+
+class BatchPlan:
+    """Batch plan of a CSR for ``gd_spmm_batched`` (csrc/spmm_batched.cu): rows cut into batches of
+    8 padded column slots, the batch list cut into ``num_workers`` equal contiguous ranges, rows
+    straddling a range boundary cut into pieces.  Built once per edge set with tensor ops on the
+    device (plan time, not on the epoch path).
+
+    ``slot_of_entry[k]`` is the padded slot of CSR entry ``k``: callers that produce per-entry
+    values (the loss backward) write them straight into the padded layout."""
+
+    SLOTS = 8
+    FLUSH, PIECE = -(1 << 31), 1 << 30
+
+    def __init__(self, rowptr, col, num_rows, nnz, num_workers):
+        dev = rowptr.device
+        n, S = int(num_rows), self.SLOTS
+        rp = rowptr.long()
+        deg = rp[1:] - rp[:-1]
+        nbr = torch.clamp((deg + S - 1) // S, min=1)            # an empty row is one all-padding batch
+        bptr = torch.cumsum(nbr, 0) - nbr
+        nb = int(nbr.sum().item()) if n else 0
+        self.num_rows, self.num_batches = n, nb
+        self.num_workers = max(1, min(int(num_workers), max(nb, 1)))
+        per = -(-nb // self.num_workers) if nb else 1
+        self.batches_per_worker = per
+        self.num_workers = -(-nb // per) if nb else 1
+        ar = torch.arange(nb, device=dev)
+        row_of = torch.repeat_interleave(torch.arange(n, device=dev), nbr)
+        k_in = ar - bptr[row_of]
+        ebase = rp[row_of] + S * k_in
+        slot_e = ebase[:, None] + torch.arange(S, device=dev)[None, :]
+        valid = slot_e < rp[row_of + 1][:, None]
+        colp = torch.full((nb, S), -1, dtype=torch.int32, device=dev)
+        colp[valid] = col[:nnz][slot_e[valid]]
+        self.colp = colp.reshape(-1).contiguous()
+        soe = torch.empty(max(int(nnz), 1), dtype=torch.int64, device=dev)
+        soe[slot_e[valid]] = (ar[:, None] * S + torch.arange(S, device=dev)[None, :])[valid]
+        self.slot_of_entry = soe[:nnz]
+        # ---- flush points: end of a row, or end of a worker's range inside a row
+        last_in_row = k_in == nbr[row_of] - 1
+        wk = ar // per
+        range_end = torch.ones(nb, dtype=torch.bool, device=dev)
+        if nb > 1:
+            range_end[:-1] = wk[1:] != wk[:-1]
+        flush = last_in_row | range_end
+        first_b = bptr
+        last_b = bptr + nbr - 1
+        split = wk[first_b] != wk[last_b] if nb else torch.zeros(0, dtype=torch.bool, device=dev)
+        split_rows = split.nonzero().squeeze(1)
+        self.num_split = int(split_rows.numel())
+        in_split = split[row_of] if nb else split
+        piece_flush = flush & in_split
+        piece_id = torch.cumsum(piece_flush.long(), 0) - 1
+        self.num_piece = int(piece_flush.sum().item()) if nb else 0
+        desc = torch.zeros(nb, dtype=torch.int64, device=dev)
+        desc = torch.where(flush & ~in_split, row_of + self.FLUSH, desc)
+        desc = torch.where(piece_flush, piece_id + self.PIECE + self.FLUSH, desc)
+        self.desc = desc.to(torch.int32).contiguous()
+        i32 = dict(dtype=torch.int32, device=dev)
+        if self.num_split:
+            hid = torch.cumsum(split.long(), 0) - 1                   # row -> split index
+            self.piece_split = hid[row_of[piece_flush]].to(torch.int32).contiguous()
+            npiece = (wk[last_b[split_rows]] - wk[first_b[split_rows]] + 1)
+            self.split_row = split_rows.to(torch.int32).contiguous()
+            self.split_npiece = npiece.to(torch.int32).contiguous()
+            self.split_piece_beg = (torch.cumsum(npiece, 0) - npiece).to(torch.int32).contiguous()
+            self.split_ticket = torch.zeros(self.num_split, **i32)
+        else:
+            self.piece_split = self.split_row = self.split_npiece = self.split_piece_beg = self.split_ticket = None
+        self._scratch = {}
+        self._cs = {}
+        s = L.BplanStruct()
+        s.num_rows, s.num_batches = n, nb
+        s.num_workers, s.batches_per_worker = self.num_workers, per
+        s.desc, s.colp = self.desc.data_ptr(), self.colp.data_ptr()
+        s.num_split, s.num_piece = self.num_split, self.num_piece
+        if self.num_split:
+            for k in ('piece_split', 'split_row', 'split_piece_beg', 'split_npiece', 'split_ticket'):
+                setattr(s, k, getattr(self, k).data_ptr())
+        self.struct = s
+        self.ref = C.byref(s)
+
+    def scratch(self, feat):
+        if self.num_piece == 0:
+            return None
+        buf = self._scratch.get(feat)
+        if buf is None:
+            buf = torch.empty(self.num_piece * feat, dtype=torch.float32, device=self.desc.device)
+            self._scratch[feat] = buf
+        return buf
+
+    def col_scale_weights(self, col_scale):
+        """Padded per-slot weights ``col_scale[colp]`` of a constant column scale (GCN's D^-1/2 on the
+        transpose-backward), cached per scale tensor."""
+        key = (col_scale.data_ptr(), col_scale._version)
+        hit = self._cs.get(key)
+        if hit is None:
+            w = torch.zeros(max(self.num_batches * self.SLOTS, 1), dtype=torch.float32, device=col_scale.device)
+            ok = self.colp >= 0
+            w[:self.colp.numel()][ok] = col_scale[self.colp[ok].long()]
+            self._cs = {key: (w, col_scale)}          # the cached entry keeps the source tensor alive (pointer reuse)
+            hit = self._cs[key]
+        return hit[0]
+
+    def pad_values(self, val, out=None):
+        """Per-entry values (CSR order) -> padded slot layout (padding slots 0)."""
+        if out is None:
+            out = torch.zeros(max(self.num_batches * self.SLOTS, 1), dtype=torch.float32, device=val.device)
+        out[self.slot_of_entry] = val[:self.slot_of_entry.numel()]
+        return out
 
 
 def degree_window_perm(rowptr, window=DEG_SORT_WINDOW):

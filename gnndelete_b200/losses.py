@@ -76,12 +76,9 @@ class EdgeLossPlan:
         self.inc_fixed = build_csr(torch.cat([fv, fu]), torch.cat([fu, fv]), n, self_loops=False)
         posf = invert_perm(self.inc_fixed.eid, max(2 * Pf, 1))
         self.nnz_fixed = 2 * Pf
+        self._posf = posf
         self.pos_u = torch.zeros(max(P, 1), dtype=torch.int32, device=dev)
         self.pos_v = torch.zeros(max(P, 1), dtype=torch.int32, device=dev)
-        self.pos_u[:n_df] = posf[:n_df]
-        self.pos_v[:n_df] = posf[Pf:Pf + n_df]
-        self.pos_u[2 * n_df:P] = posf[n_df:Pf]
-        self.pos_v[2 * n_df:P] = posf[Pf + n_df:2 * Pf]
         # ---- negative incidence: persistent buffers, rebuilt by update_negatives
         m = 2 * n_df
         self.neg_src = torch.zeros(max(m, 1), dtype=torch.int64, device=dev)
@@ -95,8 +92,10 @@ class EdgeLossPlan:
         self.neg_ws = torch.empty(self.neg_ws_bytes, dtype=torch.uint8, device=dev)
         from .graph import CSR
         self.inc_neg = CSR(self.neg_rowptr, self.neg_col, self.neg_eid, None, n, m)
-        self.inc_val = torch.zeros(max(self.nnz_fixed + m, 1), dtype=torch.float32, device=dev)
+        self.inc_neg.dynamic = True                  # rebuilt in place every step: no cached batch plan
         self.neg_buf = neg_edges.clone()             # staging buffer a caller may overwrite (H2D) before a graph replay
+        self._feat = None
+        self._layout(z_ori.shape[1] if z_ori is not None else 0)
         self.update_negatives()
         if target is None:
             if n_ni > 0:
@@ -109,6 +108,32 @@ class EdgeLossPlan:
         self.losses = torch.zeros(3, dtype=torch.float32, device=dev)
         self.ws_bytes = L.load().gd_edge_loss_workspace_bytes(P)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+
+    def _layout(self, feat):
+        """Lay out the per-entry gradient buffer ``inc_val`` = [fixed incidence | negative incidence].
+        When the batched aggregation covers ``feat`` the fixed part is in the padded slot layout of its
+        batch plan (the loss kernel scatters d loss / d logit through ``pos_u`` / ``pos_v``, so the
+        remap is free); otherwise it is in CSR order for the row-walking kernel."""
+        if self._feat == feat:
+            return
+        self._feat = feat
+        n_df, P, Pf = self.n_df, self.num_pairs, self.n_df + self.n_ni
+        bp = self.inc_fixed.bplan(feat, True) if (feat and self.nnz_fixed) else None
+        self.bplan_fixed = bp
+        posf = self._posf
+        if bp is not None:
+            posf = bp.slot_of_entry[posf[:2 * Pf].long()].to(torch.int32)
+            self.val_off = bp.num_batches * bp.SLOTS
+        else:
+            self.val_off = max(self.nnz_fixed, 1)
+        self.pos_u[:n_df] = posf[:n_df]
+        self.pos_v[:n_df] = posf[Pf:Pf + n_df]
+        self.pos_u[2 * n_df:P] = posf[n_df:Pf]
+        self.pos_v[2 * n_df:P] = posf[Pf + n_df:2 * Pf]
+        self.inc_val = torch.zeros(self.val_off + max(2 * n_df, 1), dtype=torch.float32, device=self.pos_u.device)
+        if n_df:
+            torch.add(self.neg_pos[:n_df], self.val_off, out=self.pos_u[n_df:2 * n_df])
+            torch.add(self.neg_pos[n_df:2 * n_df], self.val_off, out=self.pos_v[n_df:2 * n_df])
 
     def update_negatives(self, neg_edges=None):
         """Install new negatives (default: whatever is in ``self.neg_buf``).  No allocation, no host sync."""
@@ -127,8 +152,8 @@ class EdgeLossPlan:
                L.ptr(self.neg_rowptr), L.ptr(self.neg_col), L.ptr(self.neg_eid), None, L.ptr(self.neg_status),
                L.ptr(self.neg_ws), self.neg_ws_bytes, L.stream())
         L.call('gd_invert_perm', L.ptr(self.neg_eid), m, L.ptr(self.neg_pos), L.stream())
-        torch.add(self.neg_pos[:n_df], self.nnz_fixed, out=self.pos_u[n_df:2 * n_df])
-        torch.add(self.neg_pos[n_df:m], self.nnz_fixed, out=self.pos_v[n_df:2 * n_df])
+        torch.add(self.neg_pos[:n_df], self.val_off, out=self.pos_u[n_df:2 * n_df])
+        torch.add(self.neg_pos[n_df:m], self.val_off, out=self.pos_v[n_df:2 * n_df])
 
     def check_negatives(self):
         """Host-side validation of the last update (synchronises): raises on out-of-range endpoints."""
@@ -139,6 +164,7 @@ class EdgeLossPlan:
     def forward(self, z):
         """Fills ``self.losses`` = (loss, loss_r, loss_l), ``self.logits`` and the incidence
         values; returns ``self.losses`` (a persistent device tensor, no host sync)."""
+        self._layout(z.shape[1])
         L.call('gd_edge_loss_fwd', L.ptr(z, 'f32'), z.stride(0), z.shape[1], L.ptr(self.pu), L.ptr(self.pv),
                self.n_df, self.n_ni, L.ptr(self.target), self.alpha, L.ptr(self.pos_u), L.ptr(self.pos_v),
                L.ptr(self.logits), L.ptr(self.inc_val), L.ptr(self.losses), L.ptr(self.ws), self.ws_bytes,
@@ -147,9 +173,12 @@ class EdgeLossPlan:
 
     def backward(self, z, out=None):
         """dz = d loss / d z for the ``z`` last given to :meth:`forward`."""
-        out = ops.spmm(self.inc_fixed, z, out=out, val=self.inc_val[:max(self.nnz_fixed, 1)])
+        if self.bplan_fixed is not None:
+            out = ops.spmm(self.inc_fixed, z, out=out, valp=self.inc_val[:self.val_off])
+        else:
+            out = ops.spmm(self.inc_fixed, z, out=out, val=self.inc_val[:self.val_off])
         if self.n_df > 0:
-            ops.spmm(self.inc_neg, z, out=out, val=self.inc_val[self.nnz_fixed:], accumulate=True)
+            ops.spmm(self.inc_neg, z, out=out, val=self.inc_val[self.val_off:], accumulate=True)
         return out
 
 

@@ -28,12 +28,27 @@ def _f32(t):
 
 # ------------------------------------------------------------------ raw kernels
 def spmm(csr: CSR, x, out=None, val=None, col_scale=None, row_scale=None, self_coef=0.0, bias=None,
-         accumulate=False):
+         accumulate=False, valp=None):
+    """``out = row_scale * (A . x) + self_coef * x + bias`` with optional per-entry weights.
+
+    Default kernel: the batched aggregation on the CSR's batch plan (``gd_spmm_batched``).  ``valp`` are
+    per-slot weights already in the plan's padded layout (``csr.bplan(f, True).slot_of_entry``); a
+    constant ``col_scale`` is folded into cached padded weights once.  Per-entry ``val`` in CSR order
+    (or a CSR without a plan-able width) goes through the row-walking kernel ``gd_spmm_acc``."""
     x = _f32(x)
     n, f = csr.num_rows, x.shape[1]
     if out is None:
         assert not accumulate, 'accumulate needs an output buffer'
         out = torch.empty(n, f, dtype=torch.float32, device=x.device)
+    weighted = valp is not None or col_scale is not None
+    bp = csr.bplan(f, weighted) if val is None and x.stride(0) % 4 == 0 and out.stride(0) % 4 == 0 else None
+    if bp is not None:
+        if valp is None and col_scale is not None:
+            valp = bp.col_scale_weights(col_scale)
+        L.call('gd_spmm_batched', bp.ref, L.ptr(valp), L.ptr(row_scale), L.ptr(x), x.stride(0), f, float(self_coef),
+               L.ptr(bias), L.ptr(out), out.stride(0), L.ptr(bp.scratch(f)), int(bool(accumulate)), L.stream())
+        return out
+    assert valp is None, 'padded weights need a batch plan'
     L.call('gd_spmm_acc', csr.ref, L.ptr(val), L.ptr(col_scale), L.ptr(row_scale), L.ptr(x), x.stride(0), f,
            float(self_coef), L.ptr(bias), L.ptr(out), out.stride(0), L.ptr(csr.scratch(f)), int(bool(accumulate)),
            L.stream())

@@ -125,6 +125,43 @@ int gd_spmm_acc(const gd_csr_t* csr, const float* val, const float* col_scale, c
                 const float* x, int64_t ldx, int32_t feat, float self_coef, const float* bias,
                 float* out, int64_t ldo, float* scratch, int32_t accumulate, gd_stream_t stream);
 
+/* Batch plan of the same aggregation (gnndelete_b200/csrc/spmm_batched.cu): every row is cut into
+ * batches of 8 column slots (padded with -1), the flat batch list is cut into `num_workers` equal
+ * contiguous ranges (one per resident sub-warp of feat/4 lanes), rows straddling a range boundary
+ * become pieces that are reduced through `scratch` by a ticket counter.  Built once per edge set by
+ * the host (gnndelete_b200/graph.py::BatchPlan); all arrays are device pointers owned by the caller.
+ *   desc[b]  : bit 31 = batch ends its row / piece (flush); bit 30 = the flush is a piece;
+ *              low 30 bits = row id, or piece id when bit 30 is set;
+ *   colp     : [num_batches][8] source ids, -1 = padding (only at the end of a row's last batch). */
+typedef struct gd_spmm_bplan {
+    int64_t num_rows;
+    int64_t num_batches;
+    int32_t num_workers;
+    int32_t batches_per_worker;
+    const int32_t* desc;             /* [num_batches] */
+    const int32_t* colp;             /* [num_batches * 8], 16-byte aligned */
+    int32_t num_split;               /* rows cut into pieces */
+    int32_t num_piece;
+    const int32_t* piece_split;      /* [num_piece] index of the piece's row in split_* */
+    const int32_t* split_row;        /* [num_split] */
+    const int32_t* split_piece_beg;  /* [num_split] first piece of the row (pieces of a row are consecutive) */
+    const int32_t* split_npiece;     /* [num_split] */
+    int32_t* split_ticket;           /* [num_split] zero-initialised; self re-arming */
+} gd_spmm_bplan_t;
+
+/* Number of workers (sub-warps of feat/4 lanes) the device keeps resident for the batched kernel:
+ * the plan is balanced for exactly this many.  feat in {32, 64, 128}; 0 otherwise. */
+int32_t gd_spmm_batched_workers(int32_t feat, int32_t weighted);
+
+/* out[i,:] = row_scale[i] * ( sum_{slots s of row i} valp[s] * x[colp[s],:] ) + self_coef * x[i,:] + bias[:]
+ * (out += ... when `accumulate`).  `valp` (nullable = unit weights) is in the PADDED slot layout of the
+ * plan ([num_batches * 8], padding slots ignored).  `scratch` holds num_piece * feat floats.
+ * Same call sites as gd_spmm: GCNConv/GINConv propagate (gcn.py:11-12, gin.py:11-12), the transpose
+ * backward and the loss backward gather. */
+int gd_spmm_batched(const gd_spmm_bplan_t* plan, const float* valp, const float* row_scale, const float* x,
+                    int64_t ldx, int32_t feat, float self_coef, const float* bias, float* out, int64_t ldo,
+                    float* scratch, int32_t accumulate, gd_stream_t stream);
+
 /* GATConv(heads=1) edge-softmax aggregation (gat.py:11-12; defaults negative_slope=0.2,
  * add_self_loops=True — the CSR must be built with self_loops=1):
  *   a_src[k] = <h_k, att_src>, a_dst[i] = <h_i, att_dst>                 (gd_gat_scores)

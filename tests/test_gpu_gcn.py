@@ -68,6 +68,55 @@ def test_spmm_matches_dense(lib, case, feat):
     U.assert_close(out2, ref2, what=f'spmm unweighted F={feat}')
 
 
+@pytest.mark.parametrize('feat', [128, 64, 32])
+@pytest.mark.parametrize('workers', [7, 1000, 0])
+def test_spmm_batched_matches_dense(lib, case, feat, workers):
+    """gd_spmm_batched on plans balanced for few / very many (rows cut into pieces) / the resident
+    number of workers; unweighted, padded weights, accumulate, empty rows."""
+    from gnndelete_b200 import _lib as L
+    from gnndelete_b200.graph import BatchPlan, build_csr
+    shape, raw, df, data, neg = case
+    n = data.num_nodes
+    ei = data.train_pos_edge_index
+    ei = ei[:, ei[1] % 5 != 0]                       # rows 0, 5, 10, ... are empty
+    csr = build_csr(ei[0].to(DEV), ei[1].to(DEV), n, self_loops=False)
+    if workers == 0:
+        workers = lib.gd_spmm_batched_workers(feat, 1)
+        assert workers >= 148 * 8
+    bp = BatchPlan(csr.rowptr, csr.col, n, csr.nnz, workers)
+    if workers == 1000:
+        assert bp.num_split > 0
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, feat, generator=g)
+    rs = torch.rand(n, generator=g) + 0.5
+    bias = torch.randn(feat, generator=g)
+    val = torch.randn(csr.nnz, generator=g)
+    A = torch.zeros(n, n, dtype=torch.float64)
+    A.index_put_((ei[1], ei[0]), torch.ones(ei.shape[1], dtype=torch.float64), accumulate=True)
+    xd = x.to(DEV)
+
+    def run(valp, row_scale, self_coef, b, out, acc):
+        L.call('gd_spmm_batched', bp.ref, L.ptr(valp), L.ptr(row_scale), L.ptr(xd), xd.stride(0), feat, self_coef,
+               L.ptr(b), L.ptr(out), out.stride(0), L.ptr(bp.scratch(feat)), acc, L.stream())
+        return out
+
+    out = run(None, rs.to(DEV), 0.5, bias.to(DEV), torch.empty(n, feat, device=DEV), 0)
+    ref = rs.double().view(-1, 1) * (A @ x.double()) + 0.5 * x.double() + bias.double()
+    U.assert_close(out, ref, what=f'batched F={feat} W={workers}')
+    assert torch.equal(out.cpu()[0], (0.5 * x[0] + bias)), 'empty row = self term + bias'
+    # per-entry weights in CSR order -> padded layout; twice into the same buffer = accumulate
+    src, dst = csr.col.cpu().long(), torch.repeat_interleave(torch.arange(n), (csr.rowptr[1:] - csr.rowptr[:-1]).cpu().long())
+    Aw = torch.zeros(n, n, dtype=torch.float64)
+    Aw.index_put_((dst, src), val.double(), accumulate=True)
+    valp = bp.pad_values(val.to(DEV))
+    out2 = run(valp, None, 0.0, None, torch.empty(n, feat, device=DEV), 0)
+    U.assert_close(out2, Aw @ x.double(), what=f'batched weighted F={feat} W={workers}')
+    again = run(valp, None, 0.0, None, out2.clone(), 1)
+    U.assert_close(again, 2 * (Aw @ x.double()), what='batched accumulate')
+    # bitwise reproducible (piece order is fixed by the plan, not by arrival)
+    assert torch.equal(run(valp, None, 0.0, None, torch.empty(n, feat, device=DEV), 0), out2)
+
+
 @pytest.mark.parametrize('m,k,n,nk', [(300, 128, 128, True), (1000, 128, 64, True), (257, 500, 128, True),
                                       (513, 64, 64, False), (100, 30, 17, False)])
 def test_gemm_rows(lib, m, k, n, nk):

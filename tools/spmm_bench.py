@@ -12,7 +12,8 @@ ei = data.train_pos_edge_index[:, data.sdf_mask].contiguous()
 n = shape.num_nodes
 plan = plan_for(ei, n, 'gcn')
 nnz = plan.fwd.nnz
-print('nnz', nnz, 'segments', plan.fwd.num_seg)
+import gnndelete_b200.graph as G
+print('nnz', nnz, 'segments', plan.fwd.num_seg, 'mode', 'batched' if G.BATCHED else 'rows', 'oversub', G.OVERSUB)
 for f in (64, 128):
     x = torch.randn(n, f, device=dev); out = torch.empty(n, f, device=dev); bias = torch.randn(f, device=dev)
     for name, kw in (('plain', dict(row_scale=plan.dinv, bias=bias)), ('col_scale', dict(col_scale=plan.dinv))):
