@@ -22,6 +22,8 @@
 // B (<= 128 x 128, hi and lo) is staged once per CTA and stays resident in shared memory; the
 // accumulator is double buffered in TMEM so the epilogue of tile i overlaps the loads and MMAs
 // of tile i+1.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gd {
@@ -105,11 +107,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// hi = v rounded to tf32 (10-bit mantissa), lo = the remainder rounded to tf32
+// hi = v rounded to tf32 (10-bit mantissa), lo = the remainder rounded to tf32.
+// Round-to-nearest (ties away from zero, what cvt.rna.tf32.f32 does) on the integer pipe: add half an
+// ulp of the 10-bit mantissa to the magnitude bits and clear the 13 low bits.  cvt.rna.tf32.f32 itself
+// issues on the quarter-rate conversion pipe: with 2 conversions per element the producers spent
+// ~1500 cycles per 128 x 32 stage on it and bounded the whole kernel (tools/gemm_sweep.py, GD_TC_DEBUG=30).
 __device__ __forceinline__ float round_tf32(float v) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));     // round-to-nearest: unbiased, unlike the
-    return __uint_as_float(u);                               // truncation the MMA applies to raw fp32
+    return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
     hi = round_tf32(v);
@@ -132,18 +136,45 @@ struct Args {
     uint32_t* relu_mask_out; const uint32_t* gate_bits;      // [row][n/32] bit c%32 of word c/32 <=> value > 0
     int num_tiles;
     int stages;
+    int debug;          // GD_TC_DEBUG bit mask (measurement only): 1 = no epilogue work, 2 = producers do not load, 4 = no MMAs, 8 = epilogue without global stores, 16 = epilogue without TMEM loads
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rows_tc_kernel(const Args g) {
+// Warp roles of gemm_rows_tc_kernel: 8 producers, 8 epilogue warps (two per TMEM lane quarter, each
+// taking every other 32-column group), 1 MMA issuer.  Measured (tools/gemm_sweep.py with GD_TC_DEBUG):
+// with 4 epilogue warps running a flag-generic epilogue the kernel was epilogue bound at 5.5 us per
+// 128 x 128 tile whatever the producers did; the epilogue is therefore specialised at compile time
+// (EPI_* bits) and spread over twice the warps.
+constexpr int ROWS_EPI_WARPS = 8;
+constexpr int ROWS_MMA_WARP = NUM_PRODUCER_WARPS + ROWS_EPI_WARPS;
+constexpr int ROWS_THREADS = (ROWS_MMA_WARP + 1) * 32;
+constexpr int RE_COLS = 16;                                   // columns per epilogue step
+constexpr int RE_LD = RE_COLS + 4;                            // padded row (floats) of the per-warp transpose tile
+constexpr int ROWS_EPI_BYTES = ROWS_EPI_WARPS * 32 * RE_LD * 4;
+enum : int { EPI_BIAS = 1, EPI_SCALE = 2, EPI_RELU = 4, EPI_BITS = 8, EPI_GATE = 16, EPI_ALL = 31 };
+
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int EPI>
+__global__ void __launch_bounds__(ROWS_THREADS, 1) gemm_rows_tc_kernel(const Args g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve (all operand tiles 1024-byte aligned)
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // align by OFFSET (not through an integer cast) so the compiler keeps the shared address space: the cast version
+    // compiled every tile store to a generic ST.E and the proxy fence to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int kchunks = (g.k + KC - 1) / KC;
     const int b_tile = g.n * 128;                                  // bytes of one [n x 128 B] B tile
     uint8_t* b_hi = smem;                                          // [kchunks][n x 128 B]
     uint8_t* b_lo = b_hi + kchunks * b_tile;
     uint8_t* a_ring = b_lo + kchunks * b_tile;                     // [stages][hi 16 KB | lo 16 KB]
-    a_ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a_ring) + 1023) & ~(uintptr_t)1023);
+    a_ring += (1024u - (smem_u32(a_ring) & 1023u)) & 1023u;
     float* epi_buf = reinterpret_cast<float*>(a_ring + g.stages * 2 * TILE_BYTES);
     __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
     const int STAGES = g.stages;
@@ -156,30 +187,54 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rows_tc_kernel(const Args
     const uint32_t tmem_cols = g.n <= 32 ? 128 : (g.n <= 64 ? 256 : 512);
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], NUM_PRODUCER_WARPS * 32); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+        // one arrival per warp (after a __syncwarp): 256 per-thread arrivals on one mbarrier serialise
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], NUM_PRODUCER_WARPS); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], ROWS_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == MMA_WARP) {
+    if (warp == ROWS_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
                      "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    // ---- stage B once (hi / lo, K-major SWIZZLE_128B), all threads
-    for (int idx = tid; idx < kchunks * g.n * 8; idx += NUM_THREADS) {
-        const int c = idx / (g.n * 8), rem = idx - c * g.n * 8;
-        const int nn = rem >> 3, j = rem & 7;
-        float4 v;
-        float* vp = reinterpret_cast<float*>(&v);
+    // ---- stage B once (hi / lo, K-major SWIZZLE_128B), all threads; 4 chunks per thread in flight
+    {
+        const int total = kchunks * g.n * 8;
+        const bool vec = g.b_is_nk && (g.k & 3) == 0 && ((uintptr_t)g.b & 15) == 0;
+        for (int base = tid; base < total; base += 4 * ROWS_THREADS) {
+            float4 v[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int kk = c * KC + j * 4 + e;
-            vp[e] = kk < g.k ? (g.b_is_nk ? __ldg(g.b + (int64_t)nn * g.k + kk) : __ldg(g.b + (int64_t)kk * g.n + nn)) : 0.f;
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * ROWS_THREADS;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (idx < total) {
+                    const int c = idx / (g.n * 8), rem = idx - c * g.n * 8;
+                    const int nn = rem >> 3, j = rem & 7;
+                    const int kk0 = c * KC + j * 4;
+                    if (vec && kk0 + 4 <= g.k) v[u] = __ldg(reinterpret_cast<const float4*>(g.b + (int64_t)nn * g.k + kk0));
+                    else {
+                        float* vp = reinterpret_cast<float*>(&v[u]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int kk = kk0 + e;
+                            if (kk < g.k) vp[e] = g.b_is_nk ? __ldg(g.b + (int64_t)nn * g.k + kk) : __ldg(g.b + (int64_t)kk * g.n + nn);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * ROWS_THREADS;
+                if (idx < total) {
+                    const int c = idx / (g.n * 8), rem = idx - c * g.n * 8;
+                    const int nn = rem >> 3, j = rem & 7;
+                    float4 hi, lo;
+                    split4(v[u], hi, lo);
+                    *reinterpret_cast<float4*>(b_hi + c * b_tile + swz(nn, j)) = hi;
+                    *reinterpret_cast<float4*>(b_lo + c * b_tile + swz(nn, j)) = lo;
+                }
+            }
         }
-        float4 hi, lo;
-        split4(v, hi, lo);
-        *reinterpret_cast<float4*>(b_hi + c * b_tile + swz(nn, j)) = hi;
-        *reinterpret_cast<float4*>(b_lo + c * b_tile + swz(nn, j)) = lo;
     }
     fence_proxy_async();
     tc_fence_before();
@@ -207,13 +262,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rows_tc_kernel(const Args
 #pragma unroll
             for (int p = 0; p < 4; ++p) psrc[p] = rid[p] >= 0 ? g.a + (int64_t)rid[p] * g.lda + j * 4 : nullptr;
         };
+        // Whole rows of the tile after next are pulled into L2 with one bulk prefetch per row: the stage loads
+        // below touch a row in four 128-byte pieces spread over time, which DRAM serves poorly on its own.
+        const bool pf_ok = (g.k & 3) == 0 && !(g.debug & 32);
+        auto l2_prefetch_rows = [&](const int32_t (&rid)[4]) {
+            if (j != 0 || !pf_ok) return;
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                if (rid[p] >= 0)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g.a + (int64_t)rid[p] * g.lda), "r"(g.k * 4) : "memory");
+        };
         auto issue = [&](float4 (&buf)[4]) {                       // loads of stage (p_tile, p_c); advance cursor
             if (p_tile >= g.num_tiles) return;
             const int kbase = p_c * KC + j * 4;
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 buf[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (psrc[p] != nullptr) {
+                if (psrc[p] != nullptr && !(g.debug & 2)) {
                     if (kbase + 4 <= g.k) buf[p] = __ldg(reinterpret_cast<const float4*>(psrc[p] + p_c * KC));
                     else {
                         float* vp = reinterpret_cast<float*>(&buf[p]);
@@ -226,6 +291,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rows_tc_kernel(const Args
                 p_tile += gridDim.x;
                 set_src(rid_next);
                 load_rids(p_tile + gridDim.x, rid_next);           // row ids one tile ahead of the prefetch cursor
+                l2_prefetch_rows(rid_next);
             }
         };
         uint32_t stage = 0, phase = 0;
@@ -243,8 +309,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rows_tc_kernel(const Args
                 *reinterpret_cast<float4*>(ahi + o) = hi;
                 *reinterpret_cast<float4*>(alo + o) = lo;
             }
-            fence_proxy_async();
-            mbar_arrive(&full_bar[stage]);
+            fence_proxy_async();                                   // every writer orders its own stores for the async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         };
         {
@@ -252,6 +319,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rows_tc_kernel(const Args
             load_rids(p_tile, rid0);
             set_src(rid0);
             load_rids(p_tile + gridDim.x, rid_next);
+            l2_prefetch_rows(rid_next);
         }
         const int my_tiles = blockIdx.x < g.num_tiles ? (g.num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
         const int total = my_tiles * kchunks;
@@ -267,7 +335,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rows_tc_kernel(const Args
                 }
             }
         }
-    } else if (warp == MMA_WARP) {
+    } else if (warp == ROWS_MMA_WARP) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(g.n);
@@ -287,6 +355,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rows_tc_kernel(const Args
                     for (int ks = 0; ks < KC / 8; ++ks) {
                         const uint64_t da_hi = make_desc(ahi + ks * 32), da_lo = make_desc(alo + ks * 32);
                         const uint64_t db_hi = make_desc(bhi + ks * 32), db_lo = make_desc(blo + ks * 32);
+                        if (g.debug & 4) continue;
                         umma_tf32(dc, da_lo, db_hi, idesc, (c | ks) != 0);
                         umma_tf32(dc, da_hi, db_lo, idesc, 1);
                         umma_tf32(d, da_hi, db_hi, idesc, (c | ks) != 0);
@@ -300,79 +369,105 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rows_tc_kernel(const Args
         __syncwarp();
     } else {
         // ================================ epilogue ================================
-        // thread = accumulator row (TMEM lane); every 32-column chunk is transposed through a per-warp
-        // shared-memory tile so that the (scattered) output rows are written — and the gate rows read —
-        // as full 128-byte segments (8 lanes x 16 B per row, 4 rows per instruction).
-        const int q = warp & 3;                                    // TMEM lane quarter of this warp
+        // thread = accumulator row (TMEM lane).  A warp owns one TMEM lane quarter and every other
+        // 32-column group; each 16-column step is transposed through a per-warp shared-memory tile so
+        // that the (scattered) output rows are written as 64-byte runs (4 lanes x 16 B per row, 8 rows
+        // per instruction).
+        const int ew = warp - NUM_PRODUCER_WARPS;
+        const int q = warp & 3;                                    // TMEM lane quarter (hardware: warp id % 4)
+        const int half = ew >> 2;                                  // which 32-column groups: half, half + 2, ...
         const int lr = q * 32 + lane;                              // row inside the tile == TMEM lane
-        float* tbuf = epi_buf + q * (32 * EPI_LD);
-        const int cl = lane & 7, rl = lane >> 3;                   // coalesced phase: column chunk / row-in-group
+        float* tbuf = epi_buf + ew * (32 * RE_LD);
+        const int cl = lane & 3, rl = lane >> 2;                   // coalesced phase: 16-byte chunk / row-in-group
+        const bool has_bias = (EPI & EPI_BIAS) && g.bias != nullptr;
+        const bool has_scale = (EPI & EPI_SCALE) && g.out_scale != nullptr;
+        const bool relu_out = (EPI & EPI_RELU) && g.relu_out;
+        const bool has_gbits = (EPI & EPI_BITS) && g.gate_bits != nullptr;
+        const bool has_mask = (EPI & EPI_BITS) && g.relu_mask_out != nullptr;
+        const bool has_gate = (EPI & EPI_GATE) && g.gate != nullptr;
+        const int nw = g.n >> 5;
         int it = 0;
         for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             const int64_t gi = (int64_t)tile * BM + lr;
             const int32_t r = gi < g.m ? (g.rows ? __ldg(g.rows + gi) : (int32_t)gi) : -1;
-            const float sc = (r >= 0 && g.out_scale) ? __ldg(g.out_scale + r) : 1.0f;
-            uint32_t gate_word[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-            if (g.gate_bits && r >= 0) {
+            const float sc = (has_scale && r >= 0) ? __ldg(g.out_scale + r) : 1.0f;
+            int32_t rr[4];                                         // rows of the coalesced phase (constant per tile)
 #pragma unroll
-                for (int w = 0; w < 4; ++w) if (w < (g.n >> 5)) gate_word[w] = __ldg(g.gate_bits + (int64_t)r * (g.n >> 5) + w);
-            }
+            for (int i = 0; i < 4; ++i) rr[i] = __shfl_sync(0xffffffffu, r, i * 8 + rl);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            for (int c0 = 0; c0 < g.n; c0 += 32) {
-                uint32_t v[32], vc[32];
-                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * g.n + c0;
-                tmem_ld32(t0, v);
-                tmem_ld32(t0 + g.n, vc);
-                const uint32_t gbits = (g.gate_bits && r >= 0) ? gate_word[c0 >> 5] : 0xffffffffu;
-                uint32_t pos_bits = 0;
+            if (!(g.debug & 1)) {
+                for (int c32 = half * 32; c32 < g.n; c32 += 64) {
+                    uint32_t gword = 0xffffffffu, pos_bits = 0;
+                    if (has_gbits && r >= 0) gword = __ldg(g.gate_bits + (int64_t)r * nw + (c32 >> 5));
 #pragma unroll
-                for (int e = 0; e < 32; e += 4) {
-                    float o[4];
+                    for (int h = 0; h < 2; ++h) {
+                        const int c0 = c32 + h * RE_COLS;
+                        uint32_t v[16], vc[16];
+                        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * g.n + c0;
+                        if (!(g.debug & 16)) {
+                            tmem_ld16_nowait(t0, v);
+                            tmem_ld16_nowait(t0 + g.n, vc);
+                            tmem_wait_ld();
+                        } else {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float x = __uint_as_float(v[e + u]) + __uint_as_float(vc[e + u]);
-                        if (g.bias) x += __ldg(g.bias + c0 + e + u);
-                        x *= sc;
-                        if (g.relu_out) x = fmaxf(x, 0.f);
-                        if (!((gbits >> (e + u)) & 1u)) x = 0.f;
-                        if (x > 0.f) pos_bits |= 1u << (e + u);
-                        o[u] = x;
+                            for (int e = 0; e < 16; ++e) { v[e] = 0; vc[e] = 0; }
+                        }
+#pragma unroll
+                        for (int e = 0; e < RE_COLS; e += 4) {
+                            float o[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                float x = __uint_as_float(v[e + u]) + __uint_as_float(vc[e + u]);
+                                if (has_bias) x += __ldg(g.bias + c0 + e + u);
+                                if (has_scale) x *= sc;
+                                if (relu_out) x = fmaxf(x, 0.f);
+                                if (EPI & EPI_BITS) {
+                                    const int bit = h * RE_COLS + e + u;
+                                    if (!((gword >> bit) & 1u)) x = 0.f;
+                                    if (x > 0.f) pos_bits |= 1u << bit;
+                                }
+                                o[u] = x;
+                            }
+                            *reinterpret_cast<float4*>(tbuf + lane * RE_LD + e) = make_float4(o[0], o[1], o[2], o[3]);
+                        }
+                        __syncwarp();
+                        float4 gt[4];
+                        if (has_gate) {                            // fp32 gate rows first (all loads in flight)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                gt[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+                                if (rr[i] >= 0)
+                                    gt[i] = __ldg(reinterpret_cast<const float4*>(g.gate + (int64_t)rr[i] * g.ldgate + c0 + cl * 4));
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float4 o = *reinterpret_cast<const float4*>(tbuf + (i * 8 + rl) * RE_LD + cl * 4);
+                            if (has_gate) {
+                                if (!(gt[i].x > 0.f)) o.x = 0.f;
+                                if (!(gt[i].y > 0.f)) o.y = 0.f;
+                                if (!(gt[i].z > 0.f)) o.z = 0.f;
+                                if (!(gt[i].w > 0.f)) o.w = 0.f;
+                            }
+                            if (rr[i] >= 0 && !((g.debug & 8) && o.x != 123.456f))
+                                *reinterpret_cast<float4*>(g.out + (int64_t)rr[i] * g.ldo + c0 + cl * 4) = o;
+                        }
+                        __syncwarp();
                     }
-                    *reinterpret_cast<float4*>(tbuf + lane * EPI_LD + e) = make_float4(o[0], o[1], o[2], o[3]);
+                    if (has_mask && r >= 0) g.relu_mask_out[(int64_t)r * nw + (c32 >> 5)] = pos_bits;
                 }
-                if (g.relu_mask_out && r >= 0) g.relu_mask_out[(int64_t)r * (g.n >> 5) + (c0 >> 5)] = pos_bits;
-                __syncwarp();
-                // gate rows first (all 8 loads in flight; they may alias `out` as far as the compiler knows)
-                int32_t rr[8];
-                float4 gt[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    rr[i] = __shfl_sync(0xffffffffu, r, i * 4 + rl);
-                    gt[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-                    if (g.gate && rr[i] >= 0)
-                        gt[i] = __ldg(reinterpret_cast<const float4*>(g.gate + (int64_t)rr[i] * g.ldgate + c0 + cl * 4));
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float4 o = *reinterpret_cast<const float4*>(tbuf + (i * 4 + rl) * EPI_LD + cl * 4);
-                    if (!(gt[i].x > 0.f)) o.x = 0.f;
-                    if (!(gt[i].y > 0.f)) o.y = 0.f;
-                    if (!(gt[i].z > 0.f)) o.z = 0.f;
-                    if (!(gt[i].w > 0.f)) o.w = 0.f;
-                    if (rr[i] >= 0) *reinterpret_cast<float4*>(g.out + (int64_t)rr[i] * g.ldo + c0 + cl * 4) = o;
-                }
-                __syncwarp();
             }
             tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
     }
     // ---- teardown
     tc_fence_before();
     __syncthreads();
-    if (warp == MMA_WARP) {
+    if (warp == ROWS_MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
     }
@@ -381,7 +476,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_rows_tc_kernel(const Args
 constexpr size_t SMEM_LIMIT = 227 * 1024 - 4096;   // leave room for the static barriers / row ids
 static size_t fixed_bytes(int k, int n) {
     const int kchunks = (k + KC - 1) / KC;
-    return 1024 + (size_t)2 * kchunks * n * 128 + 1024 + EPI_BYTES;
+    return 1024 + (size_t)2 * kchunks * n * 128 + 1024 + ROWS_EPI_BYTES;
 }
 static int num_stages(int k, int n) {
     const size_t fixed = fixed_bytes(k, n);
@@ -414,7 +509,9 @@ constexpr int TN_FLUSH = 8;         // stages (x32 rows) per accumulator flush
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tn_tc_kernel(const TnArgs t) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // align by OFFSET (not through an integer cast) so the compiler keeps the shared address space: the cast version
+    // compiled every tile store to a generic ST.E and the proxy fence to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int g_tile = t.n2 * 128;                                  // bytes of one [n2 x 128 B] tile
     const int stage_bytes = 2 * TILE_BYTES + 2 * g_tile;            // A^T hi | A^T lo | G^T hi | G^T lo
     const int STAGES = t.stages;
@@ -633,13 +730,26 @@ extern "C" int gd_gemm_rows_tc(const float* a, int64_t lda, const int32_t* rows,
     GD_CHECK_ARG(gd_gemm_rows_tc_supported(k, n, lda, ldo), "shape not supported by the tcgen05 path");
     GD_CHECK_ARG(((uintptr_t)a | (uintptr_t)out | (uintptr_t)gate) % 16 == 0 && (!gate || ldgate % 4 == 0), "operands must be 16-byte aligned");
     tc::Args g{a, lda, rows, m, k, b, b_is_nk, n, bias, out_scale, gate, ldgate, relu_in, relu_out, out, ldo,
-               relu_mask_out, gate_bits, (int)ceil_div<int64_t>(m, tc::BM), tc::num_stages(k, n)};
+               relu_mask_out, gate_bits, (int)ceil_div<int64_t>(m, tc::BM), tc::num_stages(k, n), 0};
+    static const int dbg = [] { const char* e = getenv("GD_TC_DEBUG"); return e ? atoi(e) : 0; }();
+    g.debug = dbg;
     const size_t smem = tc::smem_bytes(k, n);
-    GD_CUDA(cudaFuncSetAttribute(tc::gemm_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = std::min(g.num_tiles, kNumSMs);
-    tc::gemm_rows_tc_kernel<<<grid, tc::NUM_THREADS, smem, stream>>>(g);
-    GD_LAUNCH_CHECK();
-    return GD_OK;
+    const int need = (bias ? tc::EPI_BIAS : 0) | (out_scale ? tc::EPI_SCALE : 0) | (relu_out ? tc::EPI_RELU : 0) |
+                     ((relu_mask_out || gate_bits) ? tc::EPI_BITS : 0) | (gate ? tc::EPI_GATE : 0);
+    auto launch = [&](auto kern) -> int {
+        GD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, tc::ROWS_THREADS, smem, stream>>>(g);
+        GD_LAUNCH_CHECK();
+        return GD_OK;
+    };
+    switch (need) {                        // the epilogues of the Del-training epoch are compiled without the unused branches
+        case 0: return launch(tc::gemm_rows_tc_kernel<0>);
+        case tc::EPI_SCALE: return launch(tc::gemm_rows_tc_kernel<tc::EPI_SCALE>);
+        case tc::EPI_BITS: return launch(tc::gemm_rows_tc_kernel<tc::EPI_BITS>);
+        case tc::EPI_SCALE | tc::EPI_BITS: return launch(tc::gemm_rows_tc_kernel<tc::EPI_SCALE | tc::EPI_BITS>);
+        default: return launch(tc::gemm_rows_tc_kernel<tc::EPI_ALL>);
+    }
 }
 
 __global__ void tn_reduce_kernel(const float* __restrict__ partial, int nparts, int64_t count, float* __restrict__ out) {
