@@ -30,7 +30,7 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 METRIC = 'Del-training epochs/s on OGB-Collab shape'
-NCU_DRAM_BYTES_SPMM_L2 = 98_713_856 + 43_857_408      # profiles/r1_spmm_pipe_ncu_full.md
+NCU_DRAM_BYTES_SPMM_L2 = 108_790_272 + 45_636_864     # profiles/r1_spmm_batched_ncu_full.md (dram read + write, F=64 launch)
 UNIT = 'epochs/s'
 
 
@@ -358,7 +358,8 @@ def main():
     nnz = data.train_pos_edge_index[:, data.sdf_mask].shape[1] + n
 
     # ---- value: device-resident epochs, CUDA-graph replay, both conv layers recomputed
-    eng = GCNDeleteEngine(model, data, neg, z_ori=z_ori, hoist_layer1=False)
+    # (the supplied negatives are fixed for the run, SURVEY.md §8(d): one loss-gradient gather over one incidence)
+    eng = GCNDeleteEngine(model, data, neg, z_ori=z_ori, hoist_layer1=False, static_negatives=True)
     c0 = lib.gd_launch_count()
     eng.epoch()
     launches_per_epoch = lib.gd_launch_count() - c0
@@ -375,7 +376,7 @@ def main():
     losses = eng.loss.losses.tolist()
 
     # ---- value_hoisted: layer-1 conv (frozen, input-constant) computed once outside the loop
-    eng_h = GCNDeleteEngine(model, data, neg, z_ori=z_ori, hoist_layer1=True)
+    eng_h = GCNDeleteEngine(model, data, neg, z_ori=z_ori, hoist_layer1=True, static_negatives=True)
     eng_h.capture(warmup=2)
     for _ in range(args.warmup):
         eng_h.epoch()
@@ -383,17 +384,17 @@ def main():
 
     # ---- per-kernel durations (eager launches, events on the launch stream) -> roofline
     peak, peak_src = load_peaks()
-    eng_k = GCNDeleteEngine(model, data, neg, z_ori=z_ori, hoist_layer1=False)
+    eng_k = GCNDeleteEngine(model, data, neg, z_ori=z_ori, hoist_layer1=False, static_negatives=True)
     time_kernels(eng_k, 3)
     kt = time_kernels(eng_k, min(args.steps, 50))
     b64 = spmm_algo_bytes(n, nnz, shape.out_dim)
     b128 = spmm_algo_bytes(n, nnz, shape.hidden_dim)
     achieved = b64 / (kt['spmm_l2_f64'] * 1e-3) / 1e9
     roofline = {
-        'kernel': 'gd::spmm_pipe_kernel<16,false> (GCN layer-2 aggregation, F=64)', 'bound': 'hbm',
+        'kernel': 'gd::spmm_batched_kernel<16,false> (GCN layer-2 aggregation, F=64)', 'bound': 'hbm',
         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one
-        # `ncu --set full` capture (profiles/r1_spmm_pipe_ncu_full.md); only meaningful for the Collab shape
+        # `ncu --set full` capture (profiles/r1_spmm_batched_ncu_full.md); only meaningful for the Collab shape
         'traffic': NCU_DRAM_BYTES_SPMM_L2 if shape.name == 'collab' else None,
         'gather_ceiling_tbs': 18.0, 'gathered_tbs': (4 * nnz * shape.out_dim) / (kt['spmm_l2_f64'] * 1e-3) / 1e12,
         'peak_source': peak_src, 'algorithmic_bytes_per_launch': b64, 'kernel_ms': kt['spmm_l2_f64'],

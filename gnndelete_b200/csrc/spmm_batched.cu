@@ -46,6 +46,44 @@ struct BArgs {
     float self_coef;
 };
 
+// packed fp32 pairs (sm_100 FADD2 / FFMA2): a feature fragment of 4 floats is two 64-bit registers
+struct f4p { unsigned long long lo, hi; };
+__device__ __forceinline__ f4p f4p_zero() { return f4p{0ull, 0ull}; }
+__device__ __forceinline__ void add_p(f4p& acc, const f4p& v) {
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc.lo) : "l"(v.lo));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc.hi) : "l"(v.hi));
+}
+__device__ __forceinline__ void fma_p(f4p& acc, float w, const f4p& v) {
+    unsigned long long ww;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.lo) : "l"(ww), "l"(v.lo));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.hi) : "l"(ww), "l"(v.hi));
+}
+__device__ __forceinline__ f4p ldg_p(const char* p) {
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p));
+    return f4p{v.x, v.y};
+}
+// zero when the slot is padding (c < 0); the address is computed unconditionally (one IMAD.WIDE) and only the
+// load is predicated - written in PTX because the compiler otherwise predicates (and re-derives) the whole
+// 64-bit address computation per slot
+__device__ __forceinline__ f4p ldg_p_if(const char* p, int c) {
+    f4p r;
+    asm("{\n.reg .pred q;\nsetp.ge.s32 q, %3, 0;\nmov.b64 %0, 0;\nmov.b64 %1, 0;\n@q ld.global.nc.v2.b64 {%0, %1}, [%2];\n}"
+        : "=&l"(r.lo), "=&l"(r.hi) : "l"(p), "r"(c));
+    return r;
+}
+__device__ __forceinline__ float4 to_f4(const f4p& v) {
+    float4 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v.lo));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.z), "=f"(r.w) : "l"(v.hi));
+    return r;
+}
+
+// Instruction budget matters: ncu on the first version of this kernel showed 16 warp instructions per
+// non-zero with the issue slots 55-63 % busy.  Hence: one IMAD.WIDE per gather address (byte offset =
+// column x row pitch added to a 64-bit lane base), packed FADD2 / FFMA2 accumulation, and - when a warp
+// holds more than one sub-warp - a single predicated gather path, because a full / partial branch that
+// the sub-warps of a warp take differently executes both sides.
 template <int LANES, bool WEIGHTED>
 __global__ void __launch_bounds__(256) spmm_batched_kernel(const BArgs a) {
     constexpr int PER_WARP = 32 / LANES;
@@ -57,8 +95,10 @@ __global__ void __launch_bounds__(256) spmm_batched_kernel(const BArgs a) {
     if (b0 >= a.num_batches) return;
     int b = (int)b0;
     const int bend = (int)min(b0 + (int64_t)a.per_worker, (int64_t)a.num_batches);
-    const float4* xb = reinterpret_cast<const float4*>(a.x) + sl;
-    const unsigned ld4 = (unsigned)(a.ldx >> 2);
+    unsigned long long xl = reinterpret_cast<unsigned long long>(a.x) + sl * 16;   // this lane's 16 bytes of every source row
+    asm volatile("" : "+l"(xl));                 // opaque: keeps base + lane offset in ONE register pair (the IMAD.WIDE addend)
+    const unsigned pitch = (unsigned)(a.ldx * 4);
+    auto row_ptr = [&](int c) -> const char* { return reinterpret_cast<const char*>(xl + (unsigned long long)(unsigned)c * pitch); };
 
     auto scale_of = [&](int d) -> float {      // row scale of a batch that flushes a whole row
         return (a.row_scale && d < 0 && !(d & kDescPiece)) ? __ldg(a.row_scale + (d & kDescId)) : 1.0f;
@@ -70,22 +110,19 @@ __global__ void __launch_bounds__(256) spmm_batched_kernel(const BArgs a) {
     int d_cur = __ldg(a.desc + b);
     int d_nxt = (b + 1 < bend) ? __ldg(a.desc + b + 1) : 0;
     float rs_cur = scale_of(d_cur);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    f4p acc = f4p_zero();
 
     for (; b < bend; ++b) {
-        // ---- 8 independent row gathers
-        float4 v[8];
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c1.w >= 0) {                        // padding is at the end of a batch: last slot valid = all valid
-            v[0] = __ldg(xb + (unsigned)c0.x * ld4); v[1] = __ldg(xb + (unsigned)c0.y * ld4);
-            v[2] = __ldg(xb + (unsigned)c0.z * ld4); v[3] = __ldg(xb + (unsigned)c0.w * ld4);
-            v[4] = __ldg(xb + (unsigned)c1.x * ld4); v[5] = __ldg(xb + (unsigned)c1.y * ld4);
-            v[6] = __ldg(xb + (unsigned)c1.z * ld4); v[7] = __ldg(xb + (unsigned)c1.w * ld4);
+        // ---- 8 independent row gathers (padding, -1, is at the end of a row's last batch)
+        f4p v[8];
+        if (LANES == 32 && c1.w >= 0) {         // whole warp on one batch: the full-batch test is uniform
+            v[0] = ldg_p(row_ptr(c0.x)); v[1] = ldg_p(row_ptr(c0.y)); v[2] = ldg_p(row_ptr(c0.z)); v[3] = ldg_p(row_ptr(c0.w));
+            v[4] = ldg_p(row_ptr(c1.x)); v[5] = ldg_p(row_ptr(c1.y)); v[6] = ldg_p(row_ptr(c1.z)); v[7] = ldg_p(row_ptr(c1.w));
         } else {
-            v[0] = c0.x >= 0 ? __ldg(xb + (unsigned)c0.x * ld4) : z4; v[1] = c0.y >= 0 ? __ldg(xb + (unsigned)c0.y * ld4) : z4;
-            v[2] = c0.z >= 0 ? __ldg(xb + (unsigned)c0.z * ld4) : z4; v[3] = c0.w >= 0 ? __ldg(xb + (unsigned)c0.w * ld4) : z4;
-            v[4] = c1.x >= 0 ? __ldg(xb + (unsigned)c1.x * ld4) : z4; v[5] = c1.y >= 0 ? __ldg(xb + (unsigned)c1.y * ld4) : z4;
-            v[6] = c1.z >= 0 ? __ldg(xb + (unsigned)c1.z * ld4) : z4; v[7] = z4;
+            v[0] = ldg_p_if(row_ptr(c0.x), c0.x); v[1] = ldg_p_if(row_ptr(c0.y), c0.y);
+            v[2] = ldg_p_if(row_ptr(c0.z), c0.z); v[3] = ldg_p_if(row_ptr(c0.w), c0.w);
+            v[4] = ldg_p_if(row_ptr(c1.x), c1.x); v[5] = ldg_p_if(row_ptr(c1.y), c1.y);
+            v[6] = ldg_p_if(row_ptr(c1.z), c1.z); v[7] = ldg_p_if(row_ptr(c1.w), c1.w);
         }
         const float4 wc0 = w0, wc1 = w1;
         // ---- next batch: column ids (+ weights), the descriptor after it, its row scale
@@ -100,20 +137,21 @@ __global__ void __launch_bounds__(256) spmm_batched_kernel(const BArgs a) {
         }
         // ---- accumulate
         if (WEIGHTED) {
-            fma4(acc, wc0.x, v[0]); fma4(acc, wc0.y, v[1]); fma4(acc, wc0.z, v[2]); fma4(acc, wc0.w, v[3]);
-            fma4(acc, wc1.x, v[4]); fma4(acc, wc1.y, v[5]); fma4(acc, wc1.z, v[6]); fma4(acc, wc1.w, v[7]);
+            fma_p(acc, wc0.x, v[0]); fma_p(acc, wc0.y, v[1]); fma_p(acc, wc0.z, v[2]); fma_p(acc, wc0.w, v[3]);
+            fma_p(acc, wc1.x, v[4]); fma_p(acc, wc1.y, v[5]); fma_p(acc, wc1.z, v[6]); fma_p(acc, wc1.w, v[7]);
         } else {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) add4(acc, v[u]);
+            for (int u = 0; u < 8; ++u) add_p(acc, v[u]);
         }
         // ---- end of a row (or of this worker's piece of it)
         if (d_cur < 0) {
             int row = d_cur & kDescId;
             float rs = rs_cur;
             bool write = true;
+            float4 o = to_f4(acc);
             if (d_cur & kDescPiece) {
                 const int piece = row;
-                stg4(a.scratch + (int64_t)piece * a.feat + sl * 4, acc);
+                stg4(a.scratch + (int64_t)piece * a.feat + sl * 4, o);
                 const int h = __ldg(a.piece_split + piece);
                 const int np = __ldg(a.split_npiece + h);
                 __threadfence();
@@ -125,22 +163,23 @@ __global__ void __launch_bounds__(256) spmm_batched_kernel(const BArgs a) {
                     __threadfence();
                     if (sl == 0) a.split_ticket[h] = 0;
                     const int p0 = __ldg(a.split_piece_beg + h);
-                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
                     for (int p = 0; p < np; ++p)
-                        add4(acc, __ldcg(reinterpret_cast<const float4*>(a.scratch + (int64_t)(p0 + p) * a.feat) + sl));
+                        add4(o, __ldcg(reinterpret_cast<const float4*>(a.scratch + (int64_t)(p0 + p) * a.feat) + sl));
                     row = __ldg(a.split_row + h);
                     rs = a.row_scale ? __ldg(a.row_scale + row) : 1.0f;
                 }
             }
             if (write) {
-                if (a.row_scale) { acc.x *= rs; acc.y *= rs; acc.z *= rs; acc.w *= rs; }
-                if (a.self_coef != 0.f) fma4(acc, a.self_coef, __ldg(xb + (unsigned)row * ld4));
-                if (a.bias) add4(acc, __ldg(reinterpret_cast<const float4*>(a.bias) + sl));
+                if (a.row_scale) { o.x *= rs; o.y *= rs; o.z *= rs; o.w *= rs; }
+                if (a.self_coef != 0.f) fma4(o, a.self_coef, __ldg(reinterpret_cast<const float4*>(row_ptr(row))));
+                if (a.bias) add4(o, __ldg(reinterpret_cast<const float4*>(a.bias) + sl));
                 float* op = a.out + (int64_t)row * a.ldo + sl * 4;
-                if (a.accumulate) add4(acc, *reinterpret_cast<const float4*>(op));
-                stg4(op, acc);
+                if (a.accumulate) add4(o, *reinterpret_cast<const float4*>(op));
+                stg4(op, o);
             }
-            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            acc = f4p_zero();
         }
         d_cur = d_nxt; d_nxt = d_n2; rs_cur = rs_nxt;
     }
@@ -196,7 +235,7 @@ extern "C" int gd_spmm_batched(const gd_spmm_bplan_t* plan, const float* valp, c
     GD_CHECK_ARG(ldx >= feat && ldo >= feat && ldx % 4 == 0 && ldo % 4 == 0, "leading dimensions must be multiples of 4 and >= feat");
     GD_CHECK_ARG((((uintptr_t)x | (uintptr_t)out | (uintptr_t)scratch | (uintptr_t)bias | (uintptr_t)valp | (uintptr_t)plan->colp) % 16) == 0,
                  "operands must be 16-byte aligned");
-    GD_CHECK_ARG((double)plan->num_rows * (double)(ldx / 4) < 4.0e9 && plan->num_rows < kDescId, "too many rows for 32-bit row offsets");
+    GD_CHECK_ARG(ldx * 4 < (int64_t)1 << 32 && plan->num_rows < kDescId, "row pitch / row count out of range");
     BArgs a;
     a.desc = plan->desc; a.colp = reinterpret_cast<const int4*>(plan->colp); a.valp = reinterpret_cast<const float4*>(valp);
     a.row_scale = row_scale; a.x = x; a.bias = bias; a.out = out; a.scratch = scratch;

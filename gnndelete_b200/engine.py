@@ -27,9 +27,12 @@ from .losses import DenseNIPlan, EdgeLossPlan
 
 class GCNDeleteEngine:
     def __init__(self, model, data, neg_edge_index, z_ori=None, ni_target=None, hoist_layer1=True,
-                 lr=1e-3, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, logits_ori=None):
+                 lr=1e-3, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, logits_ori=None, static_negatives=False):
         """``logits_ori`` (dense ``[N, N]``, the original model's ``z z^T`` as saved in
-        ``pred_proba.pt``) selects ``train_fullbatch``'s dense-block NI loss instead of the edge form."""
+        ``pred_proba.pt``) selects ``train_fullbatch``'s dense-block NI loss instead of the edge form.
+        ``static_negatives``: the supplied negatives are fixed for the run, so the loss
+        gradient is one gather over one incidence; leave False when negatives are replaced every epoch
+        (``set_negatives`` / ``capture(dynamic_negatives=True)``)."""
         self.model = model
         dev = data.x.device
         self.x = data.x.contiguous()
@@ -47,7 +50,7 @@ class GCNDeleteEngine:
             self.dense = DenseNIPlan(data.sdf_node_2hop_mask, ei[:, data.df_mask], logits_ori, n, out, weight=1.0 - alpha)
             ni = ni[:, :0]
         self.loss = EdgeLossPlan(ei[:, data.df_mask], neg_edge_index, ni, n, z_ori=z_ori,
-                                 target=ni_target, alpha=alpha)
+                                 target=ni_target, alpha=alpha, static_negatives=static_negatives)
         self.losses_total = torch.zeros(3, dtype=torch.float32, device=dev)
         self.alpha = float(alpha)
         f32 = dict(dtype=torch.float32, device=dev)
@@ -142,6 +145,8 @@ class GCNDeleteEngine:
         """Capture one epoch into a CUDA graph.  Warm-up epochs run first (module loading
         and workspace allocation are not capturable) and are undone, so the captured
         graph starts from the current parameters and optimizer state."""
+        if dynamic_negatives and self.loss.static:
+            raise ValueError('capture(dynamic_negatives=True) needs an engine built with static_negatives=False')
         snap_p = [p.detach().clone() for p in self.params]
         snap_s = [{k: v.clone() for k, v in st.items()} for st in self.state]
         s = torch.cuda.Stream()
@@ -179,4 +184,6 @@ class GCNDeleteEngine:
         if self.graph is not None and self._graph_dynamic_neg:
             self.loss.neg_buf.copy_(neg_edge_index, non_blocking=True)
         else:
+            if self.loss.static:
+                self.graph = None                     # the incidence buffers are rebuilt: a captured graph is stale
             self.loss.update_negatives(neg_edge_index)

@@ -57,11 +57,16 @@ class EdgeLossPlan:
     can live inside the epoch's CUDA graph; ``dz`` is the fixed gather plus the accumulated
     negative gather."""
 
-    def __init__(self, df_edges, neg_edges, ni_edges, num_nodes, z_ori=None, target=None, alpha=0.5):
+    def __init__(self, df_edges, neg_edges, ni_edges, num_nodes, z_ori=None, target=None, alpha=0.5,
+                 static_negatives=False):
+        """``static_negatives``: the supplied negatives never change (SURVEY.md §8(d)'s epoch definition), so
+        they join the fixed incidence and ``dz`` is ONE gather; :meth:`update_negatives` then rebuilds the
+        whole incidence (slow path).  Default: negatives are replaceable every step without a rebuild."""
         dev = df_edges.device
         n_df, n_ni, n = df_edges.shape[1], ni_edges.shape[1], int(num_nodes)
         assert neg_edges.shape[1] == n_df, 'one negative per Df entry (gnndelete.py:221-228)'
         self.n_df, self.n_ni, self.num_nodes = n_df, n_ni, n
+        self.static = bool(static_negatives)
         P = 2 * n_df + n_ni
         self.num_pairs = P
         self.pu = torch.cat([df_edges[0], neg_edges[0], ni_edges[0]]).to(torch.int32).contiguous()
@@ -69,18 +74,11 @@ class EdgeLossPlan:
         if self.pu.numel() == 0:
             self.pu = torch.zeros(1, dtype=torch.int32, device=dev)
             self.pv = torch.zeros(1, dtype=torch.int32, device=dev)
-        # ---- fixed incidence: entry e < Pf is the u side of fixed pair e, entry Pf + e its v side
-        fu = torch.cat([df_edges[0], ni_edges[0]]).long()
-        fv = torch.cat([df_edges[1], ni_edges[1]]).long()
-        Pf = n_df + n_ni
-        self.inc_fixed = build_csr(torch.cat([fv, fu]), torch.cat([fu, fv]), n, self_loops=False)
-        posf = invert_perm(self.inc_fixed.eid, max(2 * Pf, 1))
-        self.nnz_fixed = 2 * Pf
-        self._posf = posf
         self.pos_u = torch.zeros(max(P, 1), dtype=torch.int32, device=dev)
         self.pos_v = torch.zeros(max(P, 1), dtype=torch.int32, device=dev)
-        # ---- negative incidence: persistent buffers, rebuilt by update_negatives
-        m = 2 * n_df
+        # ---- negative incidence: persistent buffers, rebuilt by update_negatives (dynamic mode only)
+        m = 0 if self.static else 2 * n_df
+        self.neg_m = m
         self.neg_src = torch.zeros(max(m, 1), dtype=torch.int64, device=dev)
         self.neg_dst = torch.zeros(max(m, 1), dtype=torch.int64, device=dev)
         self.neg_rowptr = torch.zeros(n + 1, dtype=torch.int32, device=dev)
@@ -88,13 +86,14 @@ class EdgeLossPlan:
         self.neg_eid = torch.zeros(max(m, 1), dtype=torch.int32, device=dev)
         self.neg_pos = torch.zeros(max(m, 1), dtype=torch.int32, device=dev)
         self.neg_status = torch.zeros(2, dtype=torch.int32, device=dev)
-        self.neg_ws_bytes = L.load().gd_csr_workspace_bytes(m, n)
+        self.neg_ws_bytes = L.load().gd_csr_workspace_bytes(max(m, 1), n)
         self.neg_ws = torch.empty(self.neg_ws_bytes, dtype=torch.uint8, device=dev)
         from .graph import CSR
         self.inc_neg = CSR(self.neg_rowptr, self.neg_col, self.neg_eid, None, n, m)
         self.inc_neg.dynamic = True                  # rebuilt in place every step: no cached batch plan
         self.neg_buf = neg_edges.clone()             # staging buffer a caller may overwrite (H2D) before a graph replay
         self._feat = None
+        self._build_fixed()
         self._layout(z_ori.shape[1] if z_ori is not None else 0)
         self.update_negatives()
         if target is None:
@@ -109,6 +108,21 @@ class EdgeLossPlan:
         self.ws_bytes = L.load().gd_edge_loss_workspace_bytes(P)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
 
+    def _build_fixed(self):
+        """Fixed incidence CSR (node -> (partner, pair side)) over the pairs that never change:
+        Df + NI, plus the negatives in static mode.  Entry e < Pf is the u side of fixed pair e,
+        entry Pf + e its v side."""
+        dev, n_df, P = self.pu.device, self.n_df, self.num_pairs
+        if self.static:
+            self.fixed_idx = torch.arange(P, device=dev)
+        else:
+            self.fixed_idx = torch.cat([torch.arange(n_df, device=dev), torch.arange(2 * n_df, P, device=dev)])
+        fu, fv = self.pu[:P][self.fixed_idx].long(), self.pv[:P][self.fixed_idx].long()
+        Pf = int(self.fixed_idx.numel())
+        self.inc_fixed = build_csr(torch.cat([fv, fu]), torch.cat([fu, fv]), self.num_nodes, self_loops=False)
+        self._posf = invert_perm(self.inc_fixed.eid, max(2 * Pf, 1))
+        self.nnz_fixed = 2 * Pf
+
     def _layout(self, feat):
         """Lay out the per-entry gradient buffer ``inc_val`` = [fixed incidence | negative incidence].
         When the batched aggregation covers ``feat`` the fixed part is in the padded slot layout of its
@@ -117,7 +131,7 @@ class EdgeLossPlan:
         if self._feat == feat:
             return
         self._feat = feat
-        n_df, P, Pf = self.n_df, self.num_pairs, self.n_df + self.n_ni
+        n_df, P, Pf = self.n_df, self.num_pairs, int(self.fixed_idx.numel())
         bp = self.inc_fixed.bplan(feat, True) if (feat and self.nnz_fixed) else None
         self.bplan_fixed = bp
         posf = self._posf
@@ -126,17 +140,16 @@ class EdgeLossPlan:
             self.val_off = bp.num_batches * bp.SLOTS
         else:
             self.val_off = max(self.nnz_fixed, 1)
-        self.pos_u[:n_df] = posf[:n_df]
-        self.pos_v[:n_df] = posf[Pf:Pf + n_df]
-        self.pos_u[2 * n_df:P] = posf[n_df:Pf]
-        self.pos_v[2 * n_df:P] = posf[Pf + n_df:2 * Pf]
-        self.inc_val = torch.zeros(self.val_off + max(2 * n_df, 1), dtype=torch.float32, device=self.pos_u.device)
-        if n_df:
+        self.pos_u[self.fixed_idx] = posf[:Pf]
+        self.pos_v[self.fixed_idx] = posf[Pf:2 * Pf]
+        self.inc_val = torch.zeros(self.val_off + max(self.neg_m, 1), dtype=torch.float32, device=self.pos_u.device)
+        if self.neg_m:
             torch.add(self.neg_pos[:n_df], self.val_off, out=self.pos_u[n_df:2 * n_df])
             torch.add(self.neg_pos[n_df:2 * n_df], self.val_off, out=self.pos_v[n_df:2 * n_df])
 
     def update_negatives(self, neg_edges=None):
-        """Install new negatives (default: whatever is in ``self.neg_buf``).  No allocation, no host sync."""
+        """Install new negatives (default: whatever is in ``self.neg_buf``).  Dynamic mode: no allocation,
+        no host sync (capturable).  Static mode: rebuilds the whole incidence (not capturable)."""
         n_df = self.n_df
         if n_df == 0:
             return
@@ -145,6 +158,17 @@ class EdgeLossPlan:
         nu, nv = self.neg_buf[0], self.neg_buf[1]
         self.pu[n_df:2 * n_df].copy_(nu)
         self.pv[n_df:2 * n_df].copy_(nv)
+        if self.static:
+            if neg_edges is not None:
+                bad = int(((self.neg_buf < 0) | (self.neg_buf >= self.num_nodes)).sum().item())
+                self.neg_status[1] = bad
+                if bad:
+                    return
+                feat = self._feat
+                self._build_fixed()
+                self._feat = None
+                self._layout(feat)
+            return
         self.neg_dst[:n_df].copy_(nu); self.neg_dst[n_df:].copy_(nv)
         self.neg_src[:n_df].copy_(nv); self.neg_src[n_df:].copy_(nu)
         m = 2 * n_df
@@ -177,7 +201,7 @@ class EdgeLossPlan:
             out = ops.spmm(self.inc_fixed, z, out=out, valp=self.inc_val[:self.val_off])
         else:
             out = ops.spmm(self.inc_fixed, z, out=out, val=self.inc_val[:self.val_off])
-        if self.n_df > 0:
+        if self.neg_m > 0:
             ops.spmm(self.inc_neg, z, out=out, val=self.inc_val[self.val_off:], accumulate=True)
         return out
 

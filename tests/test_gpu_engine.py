@@ -25,8 +25,9 @@ def _oracle_run(shape, data, neg, epochs, dtype):
     return om, zo, torch.tensor(hist, dtype=torch.float64)
 
 
-@pytest.mark.parametrize('graph,hoist', [(False, False), (True, False), (True, True)])
-def test_engine_loss_curve(lib, graph, hoist):
+@pytest.mark.parametrize('graph,hoist,static', [(False, False, False), (True, False, False), (True, True, False),
+                                                (True, False, True)])
+def test_engine_loss_curve(lib, graph, hoist, static):
     from gnndelete_b200 import models as M
     from gnndelete_b200.engine import GCNDeleteEngine
     shape, raw, df, data, neg = U.make_case('cora', 0.05)
@@ -36,7 +37,8 @@ def test_engine_loss_curve(lib, graph, hoist):
     m = M.GCNDelete(U.args_for(shape), data.sdf_node_1hop_mask, data.sdf_node_2hop_mask)
     m.load_state_dict(init.state_dict())
     m = m.to(DEV)
-    eng = GCNDeleteEngine(m, data.clone().to(DEV), neg.to(DEV), z_ori=zo.float().to(DEV), hoist_layer1=hoist)
+    eng = GCNDeleteEngine(m, data.clone().to(DEV), neg.to(DEV), z_ori=zo.float().to(DEV), hoist_layer1=hoist,
+                          static_negatives=static)
     if graph:
         eng.capture()
     got = []
@@ -48,6 +50,40 @@ def test_engine_loss_curve(lib, graph, hoist):
     U.assert_close(got, hist, tol=1e-4, what='loss curve')
     U.assert_close(m.deletion1.deletion_weight, om.deletion1.deletion_weight, tol=1e-4, what='W_del1 after training')
     U.assert_close(m.deletion2.deletion_weight, om.deletion2.deletion_weight, tol=1e-4, what='W_del2 after training')
+
+
+@pytest.mark.parametrize('static', [False, True])
+def test_engine_new_negatives_every_epoch(lib, static):
+    """The reference draws new negatives every epoch (gnndelete.py:221-225): after set_negatives the losses
+    equal those of an engine built on the new negatives, in both incidence layouts and through the
+    in-graph rebuild."""
+    from gnndelete_b200 import models as M
+    from gnndelete_b200 import synthetic as S
+    from gnndelete_b200.engine import GCNDeleteEngine
+    shape, raw, df, data, neg = U.make_case('cora', 0.05)
+    om = U.oracle_model('gcn', shape, data, dtype=torch.float32)
+    with torch.no_grad():
+        zo = om.get_original_embeddings(data.x, data.train_pos_edge_index[:, data.dr_mask])
+    neg2 = S.supplied_negatives(shape.num_nodes, neg.shape[1], seed=777)
+
+    def fresh(ng, **kw):
+        m = M.GCNDelete(U.args_for(shape), data.sdf_node_1hop_mask, data.sdf_node_2hop_mask)
+        m.load_state_dict(om.state_dict())
+        return GCNDeleteEngine(m.to(DEV), data.clone().to(DEV), ng.to(DEV), z_ori=zo.to(DEV), hoist_layer1=False, **kw)
+
+    want = fresh(neg2).forward_backward().clone()
+    eng = fresh(neg, static_negatives=static)
+    eng.forward_backward()
+    eng.set_negatives(neg2.to(DEV))
+    U.assert_close(eng.forward_backward(), want, what='losses after set_negatives')
+    g_want = fresh(neg2)
+    g_want.forward_backward()
+    U.assert_close(eng.params[0].grad, g_want.params[0].grad, what='dW_del1 after set_negatives')
+    if not static:
+        eng2 = fresh(neg)
+        eng2.capture(dynamic_negatives=True)
+        eng2.set_negatives(neg2.to(DEV))
+        U.assert_close(eng2.epoch(), want, what='losses through the in-graph negative rebuild')
 
 
 def test_engine_first_step_tight(lib):
