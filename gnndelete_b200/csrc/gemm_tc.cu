@@ -77,10 +77,26 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                             // layout: SWIZZLE_128B
     return d;
 }
+// MN-major descriptor for 32-bit operands.  tf32 MN-major has exactly one legal shared-memory layout,
+// SWIZZLE_128B_BASE32B (layout type 1): atoms of 4 k-rows x 128 B (32 tf32 contiguous along M / N), the 32-byte
+// chunk c of k-row i stored at chunk c ^ (i & 3) (Swizzle<2,5,2> on the byte address).  lbo = byte stride between
+// atoms along M / N, sbo = between atoms along K; one K = 8 instruction reads two k-atoms.  (The 16-byte-granular
+// SWIZZLE_128B layout is accepted by the assembler for MN-major tf32 but the MMA then produces zeros.)
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
+    return d;
+}
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128
 __device__ __forceinline__ uint32_t make_idesc(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
+// same with A and B MN-major (instruction descriptor bits 15 / 16)
+__device__ __forceinline__ uint32_t make_idesc_mn(int n) { return make_idesc(n) | (1u << 15) | (1u << 16); }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
         "{\n"
@@ -506,6 +522,8 @@ struct TnArgs {
     int stages;
 };
 constexpr int TN_FLUSH = 8;         // stages (x32 rows) per accumulator flush
+constexpr int TN_PREFETCH = 3;      // producer register ring depth (stages of row loads in flight)
+constexpr int TN_ATOM_COL = 4096;   // bytes of one 32-feature atom column of a stage: 8 k-atoms (4 rows x 128 B) = 32 rows
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tn_tc_kernel(const TnArgs t) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -522,8 +540,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tn_tc_kernel(const TnArgs
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t tmem_cols = t.n2 <= 32 ? 128 : (t.n2 <= 64 ? 256 : 512);
     if (tid == 0) {
-        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full_bar[s], NUM_PRODUCER_WARPS * 32); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
+        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full_bar[s], NUM_PRODUCER_WARPS); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {
@@ -548,80 +566,83 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tn_tc_kernel(const TnArgs
     const int ngroups = (nstages + TN_FLUSH - 1) / TN_FLUSH;
 
     if (warp < NUM_PRODUCER_WARPS) {
-        // ------------------------------ producers: transposing stage fill ------------------------------
-        // thread -> (row rr of the stage, 16-byte column lane cl); a warp covers 8 rows x 4 column lanes,
-        // which spreads the 4-byte transposed stores over 16 banks
-        const int rr = (tid >> 2) & 31, cl = (tid & 3) + 4 * (tid >> 7);
+        // ------------------------------ producers: MN-major stage fill ------------------------------
+        // The contraction index is the ROW, so row-major A[rows, k1] / G[rows, n2] ARE the MN-major operand
+        // layouts of tcgen05 (features contiguous, one k-row per matrix row): no transposition, every lane
+        // copies 16-byte chunks (SWIZZLE_128B_BASE32B placement).  8 lanes cover the 128 B of one k-row of one 32-feature atom (a conflict-free
+        // quarter-warp store), a warp covers 4 rows, the 8 warps the 32 rows of a stage.
+        const int rr = warp * 4 + (lane >> 3), cj = lane & 7;      // row of the stage, 16-byte chunk inside an atom row
         const int a4 = t.k1 >> 2, g4 = t.n2 >> 2;                   // float4 per row
+        const uint32_t row_off = (uint32_t)((rr >> 2) * 512 + (rr & 3) * 128 + ((((cj >> 1) ^ (rr & 3)) << 5) | ((cj & 1) << 4)));
         uint32_t stage = 0, phase = 0;
         auto fetch_rid = [&](int s) -> int32_t {
             const int64_t i = r_beg + (int64_t)s * KC + rr;
             return (s < nstages && i < r_end) ? (t.rows ? __ldg(t.rows + i) : (int32_t)i) : -1;
         };
-        int32_t rid = fetch_rid(0), rid_nxt = fetch_rid(1);
-        float4 va[4], vg[4];
-        float sc = 1.f;
-        auto issue = [&](int32_t r) {
+        // Register ring: the loads of TN_PREFETCH stages are in flight while earlier stages are split and stored
+        // (the row id of the stage after those is already loaded, so an issue is never two dependent latencies).
+        float4 va[TN_PREFETCH][4], vg[TN_PREFETCH][4];
+        float sc[TN_PREFETCH];
+        int s_issue = 0;
+        int32_t rid_nxt = fetch_rid(0);
+        auto issue = [&](float4 (&xa)[4], float4 (&xg)[4], float& xs) {
+            const int32_t r = rid_nxt;
+            ++s_issue;
+            rid_nxt = fetch_rid(s_issue);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                vg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                xa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                xg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (r >= 0) {
-                    if (cl + 8 * i < a4) va[i] = __ldg(reinterpret_cast<const float4*>(t.a + (int64_t)r * t.lda) + cl + 8 * i);
-                    if (cl + 8 * i < g4) vg[i] = __ldg(reinterpret_cast<const float4*>(t.g + (int64_t)r * t.ldg) + cl + 8 * i);
+                    if (cj + 8 * i < a4) xa[i] = __ldg(reinterpret_cast<const float4*>(t.a + (int64_t)r * t.lda) + cj + 8 * i);
+                    if (cj + 8 * i < g4) xg[i] = __ldg(reinterpret_cast<const float4*>(t.g + (int64_t)r * t.ldg) + cj + 8 * i);
                 }
             }
-            sc = (r >= 0 && t.a_scale) ? __ldg(t.a_scale + r) : 1.f;
+            xs = (r >= 0 && t.a_scale) ? __ldg(t.a_scale + r) : 1.f;
         };
-        issue(rid);
-        for (int s = 0; s < nstages; ++s) {
+        auto consume = [&](const float4 (&xa)[4], const float4 (&xg)[4], float xs) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* at_hi = smem + stage * stage_bytes;
+            uint8_t* at_hi = smem + stage * stage_bytes + row_off;
             uint8_t* at_lo = at_hi + TILE_BYTES;
             uint8_t* gt_hi = at_lo + TILE_BYTES;
             uint8_t* gt_lo = gt_hi + g_tile;
-            const uint32_t kq = rr >> 2, kr = (rr & 3) * 4;        // 16-byte chunk / byte offset of row rr along K
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int cc = cl + 8 * i;
-                if (cc < a4) {
-                    float x[4] = {va[i].x, va[i].y, va[i].z, va[i].w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float v = t.relu_a ? fmaxf(x[e], 0.f) : x[e];
-                        v *= sc;
-                        float hi, lo;
-                        split_tf32(v, hi, lo);
-                        const int f = cc * 4 + e;
-                        const uint32_t o = (uint32_t)(f * 128 + ((kq ^ (f & 7)) << 4) + kr);
-                        *reinterpret_cast<float*>(at_hi + o) = hi;
-                        *reinterpret_cast<float*>(at_lo + o) = lo;
-                    }
+            for (int i = 0; i < 4; ++i) {                          // atom i = features 32 i .. 32 i + 31, 4 KB apart
+                if (cj + 8 * i < a4) {
+                    float4 x = xa[i];
+                    if (t.relu_a) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                    x.x *= xs; x.y *= xs; x.z *= xs; x.w *= xs;
+                    float4 hi, lo;
+                    split4(x, hi, lo);
+                    *reinterpret_cast<float4*>(at_hi + i * TN_ATOM_COL) = hi;
+                    *reinterpret_cast<float4*>(at_lo + i * TN_ATOM_COL) = lo;
                 }
-                if (cc < g4) {
-                    float x[4] = {vg[i].x, vg[i].y, vg[i].z, vg[i].w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float hi, lo;
-                        split_tf32(x[e], hi, lo);
-                        const int f = cc * 4 + e;
-                        const uint32_t o = (uint32_t)(f * 128 + ((kq ^ (f & 7)) << 4) + kr);
-                        *reinterpret_cast<float*>(gt_hi + o) = hi;
-                        *reinterpret_cast<float*>(gt_lo + o) = lo;
-                    }
+                if (cj + 8 * i < g4) {
+                    float4 hi, lo;
+                    split4(xg[i], hi, lo);
+                    *reinterpret_cast<float4*>(gt_hi + i * TN_ATOM_COL) = hi;
+                    *reinterpret_cast<float4*>(gt_lo + i * TN_ATOM_COL) = lo;
                 }
             }
-            // next stage's loads go out before this stage is published, so they overlap the MMAs
-            rid = rid_nxt;
-            rid_nxt = fetch_rid(s + 2);
-            if (s + 1 < nstages) issue(rid);
             fence_proxy_async();
-            mbar_arrive(&full_bar[stage]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[stage]);               // one arrival per warp
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        };
+#pragma unroll
+        for (int d = 0; d < TN_PREFETCH; ++d) issue(va[d], vg[d], sc[d]);
+        for (int s = 0; s < nstages; s += TN_PREFETCH) {
+#pragma unroll
+            for (int d = 0; d < TN_PREFETCH; ++d) {
+                if (s + d < nstages) {
+                    consume(va[d], vg[d], sc[d]);
+                    issue(va[d], vg[d], sc[d]);
+                }
+            }
         }
     } else if (warp == MMA_WARP) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(t.n2);
+            const uint32_t idesc = make_idesc_mn(t.n2);
             uint32_t stage = 0, phase = 0;
             for (int grp = 0; grp < ngroups; ++grp) {
                 const uint32_t acc = grp & 1, acc_phase = (grp >> 1) & 1;
@@ -637,8 +658,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tn_tc_kernel(const TnArgs
                     const bool first = (s == grp * TN_FLUSH);
 #pragma unroll
                     for (int ks = 0; ks < KC / 8; ++ks) {
-                        const uint64_t da_hi = make_desc(ahi + ks * 32), da_lo = make_desc(alo + ks * 32);
-                        const uint64_t db_hi = make_desc(ghi + ks * 32), db_lo = make_desc(glo + ks * 32);
+                        // rows 8 ks .. 8 ks + 7 of the stage = two 4-row k-atoms (512 B each) inside every 4 KB feature-atom column
+                        const uint64_t da_hi = make_desc_mn(ahi + ks * 1024, TN_ATOM_COL, 512), da_lo = make_desc_mn(alo + ks * 1024, TN_ATOM_COL, 512);
+                        const uint64_t db_hi = make_desc_mn(ghi + ks * 1024, TN_ATOM_COL, 512), db_lo = make_desc_mn(glo + ks * 1024, TN_ATOM_COL, 512);
                         const uint32_t accum = !(first && ks == 0);
                         umma_tf32(dc, da_lo, db_hi, idesc, accum);
                         umma_tf32(dc, da_hi, db_lo, idesc, 1);
@@ -686,7 +708,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tn_tc_kernel(const TnArgs
                 __syncwarp();
             }
             tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
         if (ngroups == 0) {                                         // CTA without rows: its partial is zero
             if (f < t.k1) for (int c = 0; c < t.n2; ++c) part[(int64_t)f * t.n2 + c] = 0.f;
@@ -752,11 +775,25 @@ extern "C" int gd_gemm_rows_tc(const float* a, int64_t lda, const int32_t* rows,
     }
 }
 
-__global__ void tn_reduce_kernel(const float* __restrict__ partial, int nparts, int64_t count, float* __restrict__ out) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int p = 0; p < nparts; ++p) s += partial[(int64_t)p * count + i];
-        out[i] = s;
+// out[i] = sum_p partial[p][i] in a fixed order: warp w of a block adds the partials p = w, w + 8, ... for 32
+// consecutive elements (coalesced, all loads independent), then the 8 warp sums are added in warp order.
+__global__ void __launch_bounds__(256) tn_reduce_kernel(const float* __restrict__ partial, int nparts, int64_t count,
+                                                        float* __restrict__ out) {
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 32 + lane;
+    float s = 0.f;
+    if (i < count) {
+#pragma unroll 4
+        for (int p = w; p < nparts; p += 8) s += __ldg(partial + (int64_t)p * count + i);
+    }
+    red[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && i < count) {
+        float r = red[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) r += red[k][lane];
+        out[i] = r;
     }
 }
 
@@ -789,7 +826,7 @@ extern "C" int gd_gemm_tn_rows_tc(const float* a, int64_t lda, const float* g, i
     tc::gemm_tn_tc_kernel<<<grid, tc::NUM_THREADS, smem, stream>>>(t);
     GD_LAUNCH_CHECK();
     const int64_t count = (int64_t)k1 * n2;
-    tn_reduce_kernel<<<(unsigned)ceil_div<int64_t>(count, 256), 256, 0, stream>>>(t.partial, grid, count, c);
+    tn_reduce_kernel<<<(unsigned)ceil_div<int64_t>(count, 32), 256, 0, stream>>>(t.partial, grid, count, c);
     GD_LAUNCH_CHECK();
     return GD_OK;
 }
