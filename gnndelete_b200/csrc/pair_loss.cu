@@ -44,11 +44,14 @@ __global__ void __launch_bounds__(256) edge_loss_fwd_kernel(const EdgeLossArgs a
     const int64_t G = (int64_t)gridDim.x * 8 * PER_WARP;
     int64_t st = ((int64_t)blockIdx.x * 8 + warp_in_block) * PER_WARP + sub;
     float sum_r = 0.f, sum_l = 0.f;
-    const float4* zb = reinterpret_cast<const float4*>(a.z) + sl;
-    const int64_t ld4 = a.ldz >> 2;
 
-    // lane q < 4 owns pair slot q of a step: slots (0,1) = Df items (2s, 2s+1), slots (2,3) = their negatives;
-    // for NI steps the four slots are four consecutive NI pairs
+    // Pair slot q of a step is OWNED by one lane of the sub-warp (it loads the slot's indices and writes its
+    // outputs): lane q, or lane 4q when LANES = 16 - where the four dot products are reduced by a transposing
+    // butterfly (5 shuffles for all four instead of 4 x 4) that leaves the total of slot q on lanes 4q .. 4q+3.
+    // Slots (0,1) = Df items (2s, 2s+1), slots (2,3) = their negatives; for NI steps four consecutive NI pairs.
+    constexpr bool T16 = LANES == 16;
+    const bool owner = T16 ? (sl & 3) == 0 : sl < 4;
+    const int my_q = T16 ? sl >> 2 : sl;
     auto pair_of = [&](int64_t s, int q) -> int64_t {
         if (s >= S) return -1;
         if (s < S_dec) { const int64_t i = 2 * s + (q & 1); return i < a.n_df ? ((q & 2) ? a.n_df + i : i) : -1; }
@@ -56,13 +59,21 @@ __global__ void __launch_bounds__(256) edge_loss_fwd_kernel(const EdgeLossArgs a
         return j < a.n_ni ? 2 * a.n_df + j : -1;
     };
     auto fetch = [&](int64_t s, int& u, int& v, int& pu_, int& pv_, float& tgt) {
-        u = 0; v = 0; pu_ = 0; pv_ = 0; tgt = 0.f;
-        const int64_t p = sl < 4 ? pair_of(s, sl) : -1;
+        u = -1; v = 0; pu_ = 0; pv_ = 0; tgt = 0.f;
+        const int64_t p = owner ? pair_of(s, my_q) : -1;
         if (p >= 0) {
             u = __ldg(a.pu + p); v = __ldg(a.pv + p);
             pu_ = __ldg(a.pos_u + p); pv_ = __ldg(a.pos_v + p);
             if (s >= S_dec) tgt = __ldg(a.target + (p - 2 * a.n_df));
         }
+    };
+    unsigned long long zl = reinterpret_cast<unsigned long long>(a.z) + sl * 16;       // this lane's 16 bytes of every row
+    asm volatile("" : "+l"(zl));
+    const unsigned pitch = (unsigned)(a.ldz * 4);
+    auto row = [&](int r) -> float4 {          // u = -1 marks an empty slot: zero row (the load is predicated off)
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r >= 0) x = __ldg(reinterpret_cast<const float4*>(zl + (unsigned long long)(unsigned)r * pitch));
+        return x;
     };
     int u0, v0, pu0, pv0; float t0;
     fetch(st, u0, v0, pu0, pv0, t0);
@@ -70,42 +81,50 @@ __global__ void __launch_bounds__(256) edge_loss_fwd_kernel(const EdgeLossArgs a
         int u1, v1, pu1, pv1; float t1;
         fetch(st + G, u1, v1, pu1, pv1, t1);                       // prefetch the next step's indices
         float4 ra[4], rb[4];
-        bool valid[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            valid[q] = pair_of(st, q) >= 0;
-            const int uu = __shfl_sync(mask, u0, q, LANES), vv = __shfl_sync(mask, v0, q, LANES);
-            ra[q] = valid[q] ? __ldg(zb + (int64_t)uu * ld4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            rb[q] = valid[q] ? __ldg(zb + (int64_t)vv * ld4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int src = T16 ? 4 * q : q;
+            const int uu = __shfl_sync(mask, u0, src, LANES), vv = __shfl_sync(mask, v0, src, LANES);
+            ra[q] = row(uu);
+            rb[q] = row(uu >= 0 ? vv : -1);
         }
         float d[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float s = ra[q].x * rb[q].x + ra[q].y * rb[q].y + ra[q].z * rb[q].z + ra[q].w * rb[q].w;
+        for (int q = 0; q < 4; ++q) d[q] = ra[q].x * rb[q].x + ra[q].y * rb[q].y + ra[q].z * rb[q].z + ra[q].w * rb[q].w;
+        float mine, other;
+        if (T16) {
+            const bool b3 = sl & 8, b2 = sl & 4;
+            const float r0 = (b3 ? d[2] : d[0]) + __shfl_xor_sync(mask, b3 ? d[0] : d[2], 8, LANES);
+            const float r1 = (b3 ? d[3] : d[1]) + __shfl_xor_sync(mask, b3 ? d[1] : d[3], 8, LANES);
+            float t = (b2 ? r1 : r0) + __shfl_xor_sync(mask, b2 ? r0 : r1, 4, LANES);
+            t += __shfl_xor_sync(mask, t, 2, LANES);
+            t += __shfl_xor_sync(mask, t, 1, LANES);
+            mine = t;                                              // total of slot sl >> 2
+            other = __shfl_xor_sync(mask, t, 8, LANES);            // slot q ^ 2: the negative of a Df item / vice versa
+        } else {
 #pragma unroll
-            for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(mask, s, o, LANES);
-            d[q] = s;
-        }
-        // lane q writes the outputs of pair slot q
-        if (sl < 4) {
-            const int64_t p = pair_of(st, sl);
-            if (p >= 0) {
-                const float mine = sl == 0 ? d[0] : (sl == 1 ? d[1] : (sl == 2 ? d[2] : d[3]));
-                float c;
-                if (st < S_dec) {
-                    const float other = sl == 0 ? d[2] : (sl == 1 ? d[3] : (sl == 2 ? d[0] : d[1]));
-                    const float r = (sl < 2) ? mine - other : other - mine;      // pos - neg
-                    c = (sl < 2) ? a.c_r * r : -a.c_r * r;
-                    if (sl < 2 && 2 * st + (sl & 1) < a.own_df) sum_r += r * r;
-                } else {
-                    const float r = mine - t0;
-                    c = a.c_l * r;
-                    if (4 * (st - S_dec) + sl < a.own_ni) sum_l += r * r;
-                }
-                a.logits[p] = mine;
-                a.inc_val[pu0] = c;
-                a.inc_val[pv0] = c;
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                for (int o = LANES / 2; o > 0; o >>= 1) d[q] += __shfl_xor_sync(mask, d[q], o, LANES);
             }
+            mine = sl == 0 ? d[0] : (sl == 1 ? d[1] : (sl == 2 ? d[2] : d[3]));
+            other = sl == 0 ? d[2] : (sl == 1 ? d[3] : (sl == 2 ? d[0] : d[1]));
+        }
+        if (owner && u0 >= 0) {
+            const int64_t p = pair_of(st, my_q);
+            float c;
+            if (st < S_dec) {
+                const float r = (my_q < 2) ? mine - other : other - mine;      // pos - neg
+                c = (my_q < 2) ? a.c_r * r : -a.c_r * r;
+                if (my_q < 2 && 2 * st + (my_q & 1) < a.own_df) sum_r += r * r;
+            } else {
+                const float r = mine - t0;
+                c = a.c_l * r;
+                if (4 * (st - S_dec) + my_q < a.own_ni) sum_l += r * r;
+            }
+            a.logits[p] = mine;
+            a.inc_val[pu0] = c;
+            a.inc_val[pv0] = c;
         }
         st += G; u0 = u1; v0 = v1; pu0 = pu1; pv0 = pv1; t0 = t1;
     }
