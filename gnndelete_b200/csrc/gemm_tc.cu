@@ -164,7 +164,8 @@ constexpr int ROWS_EPI_WARPS = 8;
 constexpr int ROWS_MMA_WARP = NUM_PRODUCER_WARPS + ROWS_EPI_WARPS;
 constexpr int ROWS_THREADS = (ROWS_MMA_WARP + 1) * 32;
 constexpr int RE_COLS = 16;                                   // columns per epilogue step
-constexpr int RE_LD = RE_COLS + 4;                            // padded row (floats) of the per-warp transpose tile
+constexpr int RE_LD = RE_COLS;                                // row (floats) of the per-warp transpose tile; 16-byte chunk c of row r sits at c ^ ((r >> 1) & 3):
+                                                              // conflict-free for the row-per-lane writes and the 4-lanes-per-row reads
 constexpr int ROWS_EPI_BYTES = ROWS_EPI_WARPS * 32 * RE_LD * 4;
 enum : int { EPI_BIAS = 1, EPI_SCALE = 2, EPI_RELU = 4, EPI_BITS = 8, EPI_GATE = 16, EPI_ALL = 31 };
 
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) gemm_rows_tc_kernel(const Arg
                                 }
                                 o[u] = x;
                             }
-                            *reinterpret_cast<float4*>(tbuf + lane * RE_LD + e) = make_float4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<float4*>(tbuf + lane * RE_LD + (((e >> 2) ^ ((lane >> 1) & 3)) << 2)) = make_float4(o[0], o[1], o[2], o[3]);
                         }
                         __syncwarp();
                         float4 gt[4];
@@ -460,7 +461,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) gemm_rows_tc_kernel(const Arg
                         }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            float4 o = *reinterpret_cast<const float4*>(tbuf + (i * 8 + rl) * RE_LD + cl * 4);
+                            float4 o = *reinterpret_cast<const float4*>(tbuf + (i * 8 + rl) * RE_LD + ((cl ^ (((i * 8 + rl) >> 1) & 3)) << 2));
                             if (has_gate) {
                                 if (!(gt[i].x > 0.f)) o.x = 0.f;
                                 if (!(gt[i].y > 0.f)) o.y = 0.f;

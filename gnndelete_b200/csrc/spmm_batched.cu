@@ -85,7 +85,7 @@ __device__ __forceinline__ float4 to_f4(const f4p& v) {
 // holds more than one sub-warp - a single predicated gather path, because a full / partial branch that
 // the sub-warps of a warp take differently executes both sides.
 template <int LANES, bool WEIGHTED>
-__global__ void __launch_bounds__(256) spmm_batched_kernel(const BArgs a) {
+__global__ void __launch_bounds__(256, 4) spmm_batched_kernel(const BArgs a) {
     constexpr int PER_WARP = 32 / LANES;
     const int lane = threadIdx.x & 31;
     const int sub = lane / LANES, sl = lane % LANES;
@@ -105,8 +105,6 @@ __global__ void __launch_bounds__(256) spmm_batched_kernel(const BArgs a) {
     };
 
     int4 c0 = __ldg(a.colp + 2 * (int64_t)b), c1 = __ldg(a.colp + 2 * (int64_t)b + 1);
-    float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
-    if (WEIGHTED) { w0 = __ldg(a.valp + 2 * (int64_t)b); w1 = __ldg(a.valp + 2 * (int64_t)b + 1); }
     int d_cur = __ldg(a.desc + b);
     int d_nxt = (b + 1 < bend) ? __ldg(a.desc + b + 1) : 0;
     float rs_cur = scale_of(d_cur);
@@ -124,14 +122,16 @@ __global__ void __launch_bounds__(256) spmm_batched_kernel(const BArgs a) {
             v[4] = ldg_p_if(row_ptr(c1.x), c1.x); v[5] = ldg_p_if(row_ptr(c1.y), c1.y);
             v[6] = ldg_p_if(row_ptr(c1.z), c1.z); v[7] = ldg_p_if(row_ptr(c1.w), c1.w);
         }
-        const float4 wc0 = w0, wc1 = w1;
+        // the slot weights are a coalesced load whose address depends on b only: issued with the gathers they
+        // arrive with them, and not double-buffering them keeps the weighted kernel at 64 registers (4 CTAs / SM)
+        float4 wc0 = make_float4(0.f, 0.f, 0.f, 0.f), wc1 = wc0;
+        if (WEIGHTED) { wc0 = __ldg(a.valp + 2 * (int64_t)b); wc1 = __ldg(a.valp + 2 * (int64_t)b + 1); }
         // ---- next batch: column ids (+ weights), the descriptor after it, its row scale
         const int bn = b + 1;
         int d_n2 = 0;
         float rs_nxt = 1.0f;
         if (bn < bend) {
             c0 = __ldg(a.colp + 2 * (int64_t)bn); c1 = __ldg(a.colp + 2 * (int64_t)bn + 1);
-            if (WEIGHTED) { w0 = __ldg(a.valp + 2 * (int64_t)bn); w1 = __ldg(a.valp + 2 * (int64_t)bn + 1); }
             if (bn + 1 < bend) d_n2 = __ldg(a.desc + bn + 1);
             rs_nxt = scale_of(d_nxt);
         }
