@@ -63,6 +63,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+// explicit 128-bit shared load (the compiler split the float4 dereference of the transpose tile into two LDS.64,
+// which breaks the quarter-warp conflict-free pattern the tile is laid out for)
+__device__ __forceinline__ float4 lds128(const float* p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -461,7 +468,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) gemm_rows_tc_kernel(const Arg
                         }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            float4 o = *reinterpret_cast<const float4*>(tbuf + (i * 8 + rl) * RE_LD + ((cl ^ (((i * 8 + rl) >> 1) & 3)) << 2));
+                            float4 o = lds128(tbuf + (i * 8 + rl) * RE_LD + ((cl ^ (((i * 8 + rl) >> 1) & 3)) << 2));
                             if (has_gate) {
                                 if (!(gt[i].x > 0.f)) o.x = 0.f;
                                 if (!(gt[i].y > 0.f)) o.y = 0.f;

@@ -84,7 +84,10 @@ __device__ __forceinline__ float4 to_f4(const f4p& v) {
 // column x row pitch added to a 64-bit lane base), packed FADD2 / FFMA2 accumulation, and - when a warp
 // holds more than one sub-warp - a single predicated gather path, because a full / partial branch that
 // the sub-warps of a warp take differently executes both sides.
-template <int LANES, bool WEIGHTED>
+// FLUSH_* select, at compile time, what the end-of-row code does; FLUSH_ANY keeps every runtime test.
+enum : int { FLUSH_SCALE = 1, FLUSH_BIAS = 2, FLUSH_SELF = 4, FLUSH_ACC = 8, FLUSH_ANY = 16 };
+
+template <int LANES, bool WEIGHTED, int FL>
 __global__ void __launch_bounds__(256, 4) spmm_batched_kernel(const BArgs a) {
     constexpr int PER_WARP = 32 / LANES;
     const int lane = threadIdx.x & 31;
@@ -93,24 +96,32 @@ __global__ void __launch_bounds__(256, 4) spmm_batched_kernel(const BArgs a) {
     const int64_t worker = ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5) * PER_WARP + sub;
     const int64_t b0 = worker * a.per_worker;
     if (b0 >= a.num_batches) return;
-    int b = (int)b0;
-    const int bend = (int)min(b0 + (int64_t)a.per_worker, (int64_t)a.num_batches);
+    const int nb = (int)min((int64_t)a.per_worker, (int64_t)a.num_batches - b0);
     unsigned long long xl = reinterpret_cast<unsigned long long>(a.x) + sl * 16;   // this lane's 16 bytes of every source row
-    asm volatile("" : "+l"(xl));                 // opaque: keeps base + lane offset in ONE register pair (the IMAD.WIDE addend)
-    const unsigned pitch = (unsigned)(a.ldx * 4);
+    unsigned long long ol = reinterpret_cast<unsigned long long>(a.out) + sl * 16; // ... and of every output row
+    asm volatile("" : "+l"(xl), "+l"(ol));       // opaque: keeps base + lane offset in ONE register pair (the IMAD.WIDE addend)
+    const unsigned pitch = (unsigned)(a.ldx * 4), opitch = (unsigned)(a.ldo * 4);
     auto row_ptr = [&](int c) -> const char* { return reinterpret_cast<const char*>(xl + (unsigned long long)(unsigned)c * pitch); };
+    const bool has_scale = (FL & FLUSH_ANY) ? a.row_scale != nullptr : (FL & FLUSH_SCALE) != 0;
+    const bool has_bias = (FL & FLUSH_ANY) ? a.bias != nullptr : (FL & FLUSH_BIAS) != 0;
+    const bool has_self = (FL & FLUSH_ANY) ? a.self_coef != 0.f : (FL & FLUSH_SELF) != 0;
+    const bool has_acc = (FL & FLUSH_ANY) ? a.accumulate != 0 : (FL & FLUSH_ACC) != 0;
 
     auto scale_of = [&](int d) -> float {      // row scale of a batch that flushes a whole row
-        return (a.row_scale && d < 0 && !(d & kDescPiece)) ? __ldg(a.row_scale + (d & kDescId)) : 1.0f;
+        return (has_scale && d < 0 && !(d & kDescPiece)) ? __ldg(a.row_scale + (d & kDescId)) : 1.0f;
     };
 
-    int4 c0 = __ldg(a.colp + 2 * (int64_t)b), c1 = __ldg(a.colp + 2 * (int64_t)b + 1);
-    int d_cur = __ldg(a.desc + b);
-    int d_nxt = (b + 1 < bend) ? __ldg(a.desc + b + 1) : 0;
+    // running pointers; the plan arrays carry two batches of slack, so "the next batch" can be loaded unconditionally
+    const int4* cp = a.colp + 2 * b0;
+    const float4* wp = WEIGHTED ? a.valp + 2 * b0 : nullptr;
+    const int32_t* dp = a.desc + b0;
+    int4 c0 = __ldg(cp), c1 = __ldg(cp + 1);
+    int d_cur = __ldg(dp);
+    int d_nxt = __ldg(dp + 1);
     float rs_cur = scale_of(d_cur);
     f4p acc = f4p_zero();
 
-    for (; b < bend; ++b) {
+    for (int it = 0; it < nb; ++it) {
         // ---- 8 independent row gathers (padding, -1, is at the end of a row's last batch)
         f4p v[8];
         if (LANES == 32 && c1.w >= 0) {         // whole warp on one batch: the full-batch test is uniform
@@ -122,19 +133,15 @@ __global__ void __launch_bounds__(256, 4) spmm_batched_kernel(const BArgs a) {
             v[4] = ldg_p_if(row_ptr(c1.x), c1.x); v[5] = ldg_p_if(row_ptr(c1.y), c1.y);
             v[6] = ldg_p_if(row_ptr(c1.z), c1.z); v[7] = ldg_p_if(row_ptr(c1.w), c1.w);
         }
-        // the slot weights are a coalesced load whose address depends on b only: issued with the gathers they
+        // the slot weights are a coalesced load whose address depends on the batch only: issued with the gathers they
         // arrive with them, and not double-buffering them keeps the weighted kernel at 64 registers (4 CTAs / SM)
         float4 wc0 = make_float4(0.f, 0.f, 0.f, 0.f), wc1 = wc0;
-        if (WEIGHTED) { wc0 = __ldg(a.valp + 2 * (int64_t)b); wc1 = __ldg(a.valp + 2 * (int64_t)b + 1); }
-        // ---- next batch: column ids (+ weights), the descriptor after it, its row scale
-        const int bn = b + 1;
-        int d_n2 = 0;
-        float rs_nxt = 1.0f;
-        if (bn < bend) {
-            c0 = __ldg(a.colp + 2 * (int64_t)bn); c1 = __ldg(a.colp + 2 * (int64_t)bn + 1);
-            if (bn + 1 < bend) d_n2 = __ldg(a.desc + bn + 1);
-            rs_nxt = scale_of(d_nxt);
-        }
+        if (WEIGHTED) { wc0 = __ldg(wp); wc1 = __ldg(wp + 1); wp += 2; }
+        // ---- next batch: column ids, the descriptor after it, its row scale
+        cp += 2; dp += 1;
+        c0 = __ldg(cp); c1 = __ldg(cp + 1);
+        const int d_n2 = __ldg(dp + 1);
+        const float rs_nxt = scale_of(d_nxt);
         // ---- accumulate
         if (WEIGHTED) {
             fma_p(acc, wc0.x, v[0]); fma_p(acc, wc0.y, v[1]); fma_p(acc, wc0.z, v[2]); fma_p(acc, wc0.w, v[3]);
@@ -168,16 +175,16 @@ __global__ void __launch_bounds__(256, 4) spmm_batched_kernel(const BArgs a) {
                     for (int p = 0; p < np; ++p)
                         add4(o, __ldcg(reinterpret_cast<const float4*>(a.scratch + (int64_t)(p0 + p) * a.feat) + sl));
                     row = __ldg(a.split_row + h);
-                    rs = a.row_scale ? __ldg(a.row_scale + row) : 1.0f;
+                    rs = has_scale ? __ldg(a.row_scale + row) : 1.0f;
                 }
             }
             if (write) {
-                if (a.row_scale) { o.x *= rs; o.y *= rs; o.z *= rs; o.w *= rs; }
-                if (a.self_coef != 0.f) fma4(o, a.self_coef, __ldg(reinterpret_cast<const float4*>(row_ptr(row))));
-                if (a.bias) add4(o, __ldg(reinterpret_cast<const float4*>(a.bias) + sl));
-                float* op = a.out + (int64_t)row * a.ldo + sl * 4;
-                if (a.accumulate) add4(o, *reinterpret_cast<const float4*>(op));
-                stg4(op, o);
+                if (has_scale) { o.x *= rs; o.y *= rs; o.z *= rs; o.w *= rs; }
+                if (has_self) fma4(o, a.self_coef, __ldg(reinterpret_cast<const float4*>(row_ptr(row))));
+                if (has_bias) add4(o, __ldg(reinterpret_cast<const float4*>(a.bias) + sl));
+                float4* op = reinterpret_cast<float4*>(ol + (unsigned long long)(unsigned)row * opitch);
+                if (has_acc) add4(o, *op);
+                *op = o;
             }
             acc = f4p_zero();
         }
@@ -188,12 +195,25 @@ __global__ void __launch_bounds__(256, 4) spmm_batched_kernel(const BArgs a) {
 template <int LANES, bool WEIGHTED>
 static int resident_workers() {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmm_batched_kernel<LANES, WEIGHTED>, 256, 0) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmm_batched_kernel<LANES, WEIGHTED, FLUSH_ANY>, 256, 0) != cudaSuccess) {
         cudaGetLastError();
         per_sm = 0;
     }
-    if (per_sm <= 0) per_sm = 3;                 // no device in this process (plan built for a later run): assume 64-80 registers
+    if (per_sm <= 0) per_sm = 4;                 // no device in this process (plan built for a later run): 64 registers
     return kNumSMs * per_sm * 8 * (32 / LANES);
+}
+
+template <int LANES, bool WEIGHTED>
+static int launch_flags(const BArgs& a, unsigned blocks, cudaStream_t stream) {
+    const int need = (a.row_scale ? FLUSH_SCALE : 0) | (a.bias ? FLUSH_BIAS : 0) | (a.self_coef != 0.f ? FLUSH_SELF : 0) |
+                     (a.accumulate ? FLUSH_ACC : 0);
+    // the flush variants of the Del-training epoch are compiled without the unused tests: GCN forward
+    // (scale + bias), transpose-backward / loss gather (nothing); everything else takes the generic variant
+    if (need == 0) spmm_batched_kernel<LANES, WEIGHTED, 0><<<blocks, 256, 0, stream>>>(a);
+    else if (need == (FLUSH_SCALE | FLUSH_BIAS)) spmm_batched_kernel<LANES, WEIGHTED, FLUSH_SCALE | FLUSH_BIAS><<<blocks, 256, 0, stream>>>(a);
+    else spmm_batched_kernel<LANES, WEIGHTED, FLUSH_ANY><<<blocks, 256, 0, stream>>>(a);
+    GD_LAUNCH_CHECK();
+    return GD_OK;
 }
 
 template <int LANES>
@@ -201,10 +221,7 @@ static int launch_batched(const BArgs& a, int64_t workers, bool weighted, cudaSt
     const int per_cta = 8 * (32 / LANES);
     const unsigned blocks = (unsigned)ceil_div<int64_t>(workers, per_cta);
     if (blocks == 0) return GD_OK;
-    if (weighted) spmm_batched_kernel<LANES, true><<<blocks, 256, 0, stream>>>(a);
-    else spmm_batched_kernel<LANES, false><<<blocks, 256, 0, stream>>>(a);
-    GD_LAUNCH_CHECK();
-    return GD_OK;
+    return weighted ? launch_flags<LANES, true>(a, blocks, stream) : launch_flags<LANES, false>(a, blocks, stream);
 }
 
 }  // namespace gd
@@ -232,7 +249,8 @@ extern "C" int gd_spmm_batched(const gd_spmm_bplan_t* plan, const float* valp, c
                      (int64_t)plan->num_workers * plan->batches_per_worker >= plan->num_batches, "inconsistent worker partition");
     GD_CHECK_ARG(plan->num_piece == 0 || (scratch && plan->piece_split && plan->split_row && plan->split_piece_beg &&
                                           plan->split_npiece && plan->split_ticket), "split rows without scratch / ticket arrays");
-    GD_CHECK_ARG(ldx >= feat && ldo >= feat && ldx % 4 == 0 && ldo % 4 == 0, "leading dimensions must be multiples of 4 and >= feat");
+    GD_CHECK_ARG(ldx >= feat && ldo >= feat && ldx % 4 == 0 && ldo % 4 == 0 && ldo * 4 < (int64_t)1 << 32,
+                 "leading dimensions must be multiples of 4 and >= feat");
     GD_CHECK_ARG((((uintptr_t)x | (uintptr_t)out | (uintptr_t)scratch | (uintptr_t)bias | (uintptr_t)valp | (uintptr_t)plan->colp) % 16) == 0,
                  "operands must be 16-byte aligned");
     GD_CHECK_ARG(ldx * 4 < (int64_t)1 << 32 && plan->num_rows < kDescId, "row pitch / row count out of range");

@@ -110,8 +110,11 @@ class BatchPlan:
         ebase = rp[row_of] + S * k_in
         slot_e = ebase[:, None] + torch.arange(S, device=dev)[None, :]
         valid = slot_e < rp[row_of + 1][:, None]
-        colp = torch.full((nb, S), -1, dtype=torch.int32, device=dev)
-        colp[valid] = col[:nnz][slot_e[valid]]
+        # two batches of slack at the end of desc / colp / every per-slot value buffer: the kernel loads
+        # "the next batch" unconditionally
+        self.num_slots = (nb + 2) * S
+        colp = torch.full((nb + 2, S), -1, dtype=torch.int32, device=dev)
+        colp[:nb][valid] = col[:nnz][slot_e[valid]]
         self.colp = colp.reshape(-1).contiguous()
         soe = torch.empty(max(int(nnz), 1), dtype=torch.int64, device=dev)
         soe[slot_e[valid]] = (ar[:, None] * S + torch.arange(S, device=dev)[None, :])[valid]
@@ -135,7 +138,7 @@ class BatchPlan:
         desc = torch.zeros(nb, dtype=torch.int64, device=dev)
         desc = torch.where(flush & ~in_split, row_of + self.FLUSH, desc)
         desc = torch.where(piece_flush, piece_id + self.PIECE + self.FLUSH, desc)
-        self.desc = desc.to(torch.int32).contiguous()
+        self.desc = torch.cat([desc, desc.new_zeros(2)]).to(torch.int32).contiguous()
         i32 = dict(dtype=torch.int32, device=dev)
         if self.num_split:
             hid = torch.cumsum(split.long(), 0) - 1                   # row -> split index
@@ -175,9 +178,9 @@ class BatchPlan:
         key = (col_scale.data_ptr(), col_scale._version)
         hit = self._cs.get(key)
         if hit is None:
-            w = torch.zeros(max(self.num_batches * self.SLOTS, 1), dtype=torch.float32, device=col_scale.device)
+            w = torch.zeros(self.num_slots, dtype=torch.float32, device=col_scale.device)
             ok = self.colp >= 0
-            w[:self.colp.numel()][ok] = col_scale[self.colp[ok].long()]
+            w[ok] = col_scale[self.colp[ok].long()]
             self._cs = {key: (w, col_scale)}          # the cached entry keeps the source tensor alive (pointer reuse)
             hit = self._cs[key]
         return hit[0]
@@ -185,7 +188,7 @@ class BatchPlan:
     def pad_values(self, val, out=None):
         """Per-entry values (CSR order) -> padded slot layout (padding slots 0)."""
         if out is None:
-            out = torch.zeros(max(self.num_batches * self.SLOTS, 1), dtype=torch.float32, device=val.device)
+            out = torch.zeros(self.num_slots, dtype=torch.float32, device=val.device)
         out[self.slot_of_entry] = val[:self.slot_of_entry.numel()]
         return out
 

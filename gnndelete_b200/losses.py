@@ -137,7 +137,7 @@ class EdgeLossPlan:
         posf = self._posf
         if bp is not None:
             posf = bp.slot_of_entry[posf[:2 * Pf].long()].to(torch.int32)
-            self.val_off = bp.num_batches * bp.SLOTS
+            self.val_off = bp.num_slots                        # incl. the plan's two batches of slack
         else:
             self.val_off = max(self.nnz_fixed, 1)
         self.pos_u[self.fixed_idx] = posf[:Pf]

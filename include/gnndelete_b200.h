@@ -132,14 +132,16 @@ int gd_spmm_acc(const gd_csr_t* csr, const float* val, const float* col_scale, c
  * the host (gnndelete_b200/graph.py::BatchPlan); all arrays are device pointers owned by the caller.
  *   desc[b]  : bit 31 = batch ends its row / piece (flush); bit 30 = the flush is a piece;
  *              low 30 bits = row id, or piece id when bit 30 is set;
- *   colp     : [num_batches][8] source ids, -1 = padding (only at the end of a row's last batch). */
+ *   colp     : [num_batches][8] source ids, -1 = padding (only at the end of a row's last batch).
+ * desc, colp (and the caller's valp) must be readable for TWO batches past num_batches (the kernel loads the
+ * next batch unconditionally); the values there are ignored. */
 typedef struct gd_spmm_bplan {
     int64_t num_rows;
     int64_t num_batches;
     int32_t num_workers;
     int32_t batches_per_worker;
-    const int32_t* desc;             /* [num_batches] */
-    const int32_t* colp;             /* [num_batches * 8], 16-byte aligned */
+    const int32_t* desc;             /* [num_batches + 2] */
+    const int32_t* colp;             /* [(num_batches + 2) * 8], 16-byte aligned */
     int32_t num_split;               /* rows cut into pieces */
     int32_t num_piece;
     const int32_t* piece_split;      /* [num_piece] index of the piece's row in split_* */

@@ -29,6 +29,8 @@ def _walk(plan, x, valp=None):
     arrived = torch.zeros(max(plan.num_split, 1), dtype=torch.long)
     colp = plan.colp.view(-1, 8).long()
     desc = plan.desc.long()
+    assert colp.shape[0] == plan.num_batches + 2 and desc.numel() == plan.num_batches + 2, 'two batches of slack'
+    assert bool((colp[plan.num_batches:] == -1).all()) and bool((desc[plan.num_batches:] == 0).all())
     written = torch.zeros(n, dtype=torch.long)
     for w in range(plan.num_workers):
         b0 = w * plan.batches_per_worker
@@ -95,4 +97,4 @@ def test_batch_plan_slots_and_scale_weights():
     cs = torch.rand(n) + 0.5
     w = plan.col_scale_weights(cs)
     assert torch.equal(w[soe], cs[col.long()])
-    assert float(w[plan.colp < 0].abs().sum()) == 0.0
+    assert w.numel() == plan.num_slots and float(w[plan.colp < 0].abs().sum()) == 0.0

@@ -4,6 +4,5 @@ python -m pytest tests/ -m gpu -x -q 2>&1 | tail -3
 python tools/spmm_bench.py
 python tools/gemm_sweep.py 2>&1 | grep -E "tiles/CTA +(8|16) "
 python bench.py --no-cpu-baseline
-python bench.py --workload powerlaw10m --scale 0.1 --steps 5 --warmup 3 --no-cpu-baseline
 } > gpurun_out/check.log 2>&1
 cat gpurun_out/check.log | cut -c1-1700
