@@ -428,11 +428,31 @@ def main():
     for _ in range(e2e_steps):
         e2e_step()
     barrier_sync(world)
+    e2e_sync_s = max_over_ranks(time.perf_counter() - t0, world, dev)
+
+    # the same steps with the transfers overlapped (EpochPipeline): H2D of step k and D2H of step k-1 ride a copy
+    # stream while the graph of the neighbouring step runs; the host reads every step's losses, one step late
+    from gnndelete_b200.engine import EpochPipeline
+    pipe = EpochPipeline(eng_e)
+    for i in range(3):
+        pipe.result(pipe.submit(neg_host))
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(e2e_steps):
+        k = pipe.submit(neg_host)
+        if last is not None:
+            pipe.result(last)
+        last = k
+    pipe.result(last)
+    barrier_sync(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world, dev)
     e2e = {'value': world * e2e_steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': neg_host.numel() * 8,
-           'd2h_bytes_per_step': 12, 'steps': e2e_steps,
-           'what': 'per step through GCNDeleteEngine: supplied negatives pinned-host -> device, in-graph rebuild of the '
-                   'negative-pair incidence (radix sort), epoch (one CUDA-graph launch), losses -> pinned host, sync'}
+           'd2h_bytes_per_step': 12, 'steps': e2e_steps, 'value_step_synchronous': world * e2e_steps / e2e_sync_s,
+           'what': 'per step through GCNDeleteEngine / EpochPipeline: new negatives pinned-host -> device, in-graph rebuild '
+                   'of the negative-pair incidence (radix sort), epoch (one CUDA-graph launch), losses -> pinned host and '
+                   'read by the host; transfers of neighbouring steps overlap compute (value_step_synchronous: same steps '
+                   'with a full host sync after every step)'}
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,

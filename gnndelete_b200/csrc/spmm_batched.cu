@@ -41,6 +41,9 @@ struct BArgs {
     const int32_t* split_piece_beg;
     const int32_t* split_npiece;
     int32_t* split_ticket;
+    const int32_t* tail_rowptr;      // optional second (plain CSR) operand added to every row at its flush
+    const int32_t* tail_col;
+    const float* tail_val;
     int64_t ldx, ldo;
     int32_t num_batches, per_worker, feat, accumulate;
     float self_coef;
@@ -85,7 +88,7 @@ __device__ __forceinline__ float4 to_f4(const f4p& v) {
 // holds more than one sub-warp - a single predicated gather path, because a full / partial branch that
 // the sub-warps of a warp take differently executes both sides.
 // FLUSH_* select, at compile time, what the end-of-row code does; FLUSH_ANY keeps every runtime test.
-enum : int { FLUSH_SCALE = 1, FLUSH_BIAS = 2, FLUSH_SELF = 4, FLUSH_ACC = 8, FLUSH_ANY = 16 };
+enum : int { FLUSH_SCALE = 1, FLUSH_BIAS = 2, FLUSH_SELF = 4, FLUSH_ACC = 8, FLUSH_ANY = 16, FLUSH_TAIL = 32 };
 
 template <int LANES, bool WEIGHTED, int FL>
 __global__ void __launch_bounds__(256, 4) spmm_batched_kernel(const BArgs a) {
@@ -106,6 +109,7 @@ __global__ void __launch_bounds__(256, 4) spmm_batched_kernel(const BArgs a) {
     const bool has_bias = (FL & FLUSH_ANY) ? a.bias != nullptr : (FL & FLUSH_BIAS) != 0;
     const bool has_self = (FL & FLUSH_ANY) ? a.self_coef != 0.f : (FL & FLUSH_SELF) != 0;
     const bool has_acc = (FL & FLUSH_ANY) ? a.accumulate != 0 : (FL & FLUSH_ACC) != 0;
+    const bool has_tail = (FL & FLUSH_ANY) ? a.tail_rowptr != nullptr : (FL & FLUSH_TAIL) != 0;
 
     auto scale_of = [&](int d) -> float {      // row scale of a batch that flushes a whole row
         return (has_scale && d < 0 && !(d & kDescPiece)) ? __ldg(a.row_scale + (d & kDescId)) : 1.0f;
@@ -179,6 +183,11 @@ __global__ void __launch_bounds__(256, 4) spmm_batched_kernel(const BArgs a) {
                 }
             }
             if (write) {
+                if (has_tail) {                  // the few entries of the second CSR (this step's negative pairs)
+                    const int k0 = __ldg(a.tail_rowptr + row), k1 = __ldg(a.tail_rowptr + row + 1);
+                    for (int k = k0; k < k1; ++k)
+                        fma4(o, __ldg(a.tail_val + k), __ldg(reinterpret_cast<const float4*>(row_ptr(__ldg(a.tail_col + k)))));
+                }
                 if (has_scale) { o.x *= rs; o.y *= rs; o.z *= rs; o.w *= rs; }
                 if (has_self) fma4(o, a.self_coef, __ldg(reinterpret_cast<const float4*>(row_ptr(row))));
                 if (has_bias) add4(o, __ldg(reinterpret_cast<const float4*>(a.bias) + sl));
@@ -206,11 +215,13 @@ static int resident_workers() {
 template <int LANES, bool WEIGHTED>
 static int launch_flags(const BArgs& a, unsigned blocks, cudaStream_t stream) {
     const int need = (a.row_scale ? FLUSH_SCALE : 0) | (a.bias ? FLUSH_BIAS : 0) | (a.self_coef != 0.f ? FLUSH_SELF : 0) |
-                     (a.accumulate ? FLUSH_ACC : 0);
+                     (a.accumulate ? FLUSH_ACC : 0) | (a.tail_rowptr ? FLUSH_TAIL : 0);
     // the flush variants of the Del-training epoch are compiled without the unused tests: GCN forward
-    // (scale + bias), transpose-backward / loss gather (nothing); everything else takes the generic variant
+    // (scale + bias), transpose-backward / loss gather (nothing), loss gather + this step's negatives (tail);
+    // everything else takes the generic variant
     if (need == 0) spmm_batched_kernel<LANES, WEIGHTED, 0><<<blocks, 256, 0, stream>>>(a);
     else if (need == (FLUSH_SCALE | FLUSH_BIAS)) spmm_batched_kernel<LANES, WEIGHTED, FLUSH_SCALE | FLUSH_BIAS><<<blocks, 256, 0, stream>>>(a);
+    else if (need == FLUSH_TAIL) spmm_batched_kernel<LANES, WEIGHTED, FLUSH_TAIL><<<blocks, 256, 0, stream>>>(a);
     else spmm_batched_kernel<LANES, WEIGHTED, FLUSH_ANY><<<blocks, 256, 0, stream>>>(a);
     GD_LAUNCH_CHECK();
     return GD_OK;
@@ -240,6 +251,14 @@ extern "C" int32_t gd_spmm_batched_workers(int32_t feat, int32_t weighted) {
 extern "C" int gd_spmm_batched(const gd_spmm_bplan_t* plan, const float* valp, const float* row_scale, const float* x,
                                int64_t ldx, int32_t feat, float self_coef, const float* bias, float* out, int64_t ldo,
                                float* scratch, int32_t accumulate, gd_stream_t stream_) {
+    return gd_spmm_batched_tail(plan, valp, nullptr, nullptr, nullptr, row_scale, x, ldx, feat, self_coef, bias, out, ldo, scratch,
+                                accumulate, stream_);
+}
+
+extern "C" int gd_spmm_batched_tail(const gd_spmm_bplan_t* plan, const float* valp, const int32_t* tail_rowptr,
+                                    const int32_t* tail_col, const float* tail_val, const float* row_scale, const float* x,
+                                    int64_t ldx, int32_t feat, float self_coef, const float* bias, float* out, int64_t ldo,
+                                    float* scratch, int32_t accumulate, gd_stream_t stream_) {
     cudaStream_t stream = as_stream(stream_);
     GD_CHECK_ARG(plan != nullptr, "null plan");
     GD_CHECK_ARG(feat == 32 || feat == 64 || feat == 128, "feat must be 32, 64 or 128");
@@ -254,11 +273,13 @@ extern "C" int gd_spmm_batched(const gd_spmm_bplan_t* plan, const float* valp, c
     GD_CHECK_ARG((((uintptr_t)x | (uintptr_t)out | (uintptr_t)scratch | (uintptr_t)bias | (uintptr_t)valp | (uintptr_t)plan->colp) % 16) == 0,
                  "operands must be 16-byte aligned");
     GD_CHECK_ARG(ldx * 4 < (int64_t)1 << 32 && plan->num_rows < kDescId, "row pitch / row count out of range");
+    GD_CHECK_ARG(!tail_rowptr || (tail_col && tail_val), "tail CSR without columns / values");
     BArgs a;
     a.desc = plan->desc; a.colp = reinterpret_cast<const int4*>(plan->colp); a.valp = reinterpret_cast<const float4*>(valp);
     a.row_scale = row_scale; a.x = x; a.bias = bias; a.out = out; a.scratch = scratch;
     a.piece_split = plan->piece_split; a.split_row = plan->split_row; a.split_piece_beg = plan->split_piece_beg;
     a.split_npiece = plan->split_npiece; a.split_ticket = plan->split_ticket;
+    a.tail_rowptr = tail_rowptr; a.tail_col = tail_col; a.tail_val = tail_val;
     a.ldx = ldx; a.ldo = ldo;
     a.num_batches = (int32_t)plan->num_batches; a.per_worker = plan->batches_per_worker; a.feat = feat; a.accumulate = accumulate;
     a.self_coef = self_coef;

@@ -187,3 +187,53 @@ class GCNDeleteEngine:
             if self.loss.static:
                 self.graph = None                     # the incidence buffers are rebuilt: a captured graph is stale
             self.loss.update_negatives(neg_edge_index)
+
+
+class EpochPipeline:
+    """Double-buffered host <-> device plumbing around a captured engine (``capture(dynamic_negatives=True)``):
+    step k's negatives travel pinned host -> device on a copy stream while step k-1 computes, and step k's
+    losses travel device -> pinned host while step k+1 computes; the host only ever waits for the losses of
+    the PREVIOUS step.  Every step still moves its own inputs and its own result - nothing is skipped, the
+    transfers are just overlapped with compute the way a training loop prefetches its next batch."""
+
+    def __init__(self, engine):
+        if engine.graph is None or not engine._graph_dynamic_neg:
+            raise ValueError('EpochPipeline needs engine.capture(dynamic_negatives=True)')
+        self.eng = engine
+        nb = engine.loss.neg_buf
+        self.h2d, self.d2h = torch.cuda.Stream(), torch.cuda.Stream()     # separate queues: an upload never waits behind a read-back
+        self.stage = [torch.empty_like(nb) for _ in range(2)]
+        self.host = [torch.empty(3, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.dev_out = [torch.zeros(3, dtype=torch.float32, device=nb.device) for _ in range(2)]
+        self.staged = [torch.cuda.Event() for _ in range(2)]
+        self.done = [torch.cuda.Event() for _ in range(2)]
+        self.read = [torch.cuda.Event() for _ in range(2)]
+        self.k = 0
+
+    def submit(self, neg_host):
+        """Queue one epoch on ``neg_host`` (pinned ``[2, n_df]`` int64); returns its step index."""
+        k, s = self.k, self.k & 1
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self.h2d):
+            if k >= 2:
+                self.h2d.wait_event(self.done[s])             # step k-2 has consumed this staging buffer
+            self.stage[s].copy_(neg_host, non_blocking=True)
+            self.staged[s].record(self.h2d)
+        main.wait_event(self.staged[s])
+        self.eng.loss.neg_buf.copy_(self.stage[s], non_blocking=True)
+        losses = self.eng.epoch()                             # one graph launch (rebuilds the negative incidence first)
+        if k >= 2:
+            main.wait_event(self.read[s])                     # step k-2's losses have left this device slot
+        self.dev_out[s].copy_(losses, non_blocking=True)      # the graph's loss buffer is overwritten by the next step
+        self.done[s].record(main)
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(self.done[s])
+            self.host[s].copy_(self.dev_out[s], non_blocking=True)
+            self.read[s].record(self.d2h)
+        self.k += 1
+        return k
+
+    def result(self, k):
+        """(loss, loss_r, loss_l) of step ``k`` (must be one of the last two submitted); blocks until it is on the host."""
+        self.read[k & 1].synchronize()
+        return self.host[k & 1]

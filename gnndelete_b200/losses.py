@@ -198,7 +198,9 @@ class EdgeLossPlan:
     def backward(self, z, out=None):
         """dz = d loss / d z for the ``z`` last given to :meth:`forward`."""
         if self.bplan_fixed is not None:
-            out = ops.spmm(self.inc_fixed, z, out=out, valp=self.inc_val[:self.val_off])
+            # one gather: the fixed incidence through its batch plan, this step's negative incidence as the tail CSR
+            tail = (self.neg_rowptr, self.neg_col, self.inc_val[self.val_off:]) if self.neg_m > 0 else None
+            return ops.spmm(self.inc_fixed, z, out=out, valp=self.inc_val[:self.val_off], tail=tail)
         else:
             out = ops.spmm(self.inc_fixed, z, out=out, val=self.inc_val[:self.val_off])
         if self.neg_m > 0:

@@ -28,13 +28,14 @@ def _f32(t):
 
 # ------------------------------------------------------------------ raw kernels
 def spmm(csr: CSR, x, out=None, val=None, col_scale=None, row_scale=None, self_coef=0.0, bias=None,
-         accumulate=False, valp=None):
+         accumulate=False, valp=None, tail=None):
     """``out = row_scale * (A . x) + self_coef * x + bias`` with optional per-entry weights.
 
     Default kernel: the batched aggregation on the CSR's batch plan (``gd_spmm_batched``).  ``valp`` are
     per-slot weights already in the plan's padded layout (``csr.bplan(f, True).slot_of_entry``); a
     constant ``col_scale`` is folded into cached padded weights once.  Per-entry ``val`` in CSR order
-    (or a CSR without a plan-able width) goes through the row-walking kernel ``gd_spmm_acc``."""
+    (or a CSR without a plan-able width) goes through the row-walking kernel ``gd_spmm_acc``.  ``tail`` =
+    ``(rowptr, col, val)`` of a second plain CSR whose entries are added row by row (batched path only)."""
     x = _f32(x)
     n, f = csr.num_rows, x.shape[1]
     if out is None:
@@ -45,10 +46,12 @@ def spmm(csr: CSR, x, out=None, val=None, col_scale=None, row_scale=None, self_c
     if bp is not None:
         if valp is None and col_scale is not None:
             valp = bp.col_scale_weights(col_scale)
-        L.call('gd_spmm_batched', bp.ref, L.ptr(valp), L.ptr(row_scale), L.ptr(x), x.stride(0), f, float(self_coef),
-               L.ptr(bias), L.ptr(out), out.stride(0), L.ptr(bp.scratch(f)), int(bool(accumulate)), L.stream())
+        t_rp, t_col, t_val = tail if tail is not None else (None, None, None)
+        L.call('gd_spmm_batched_tail', bp.ref, L.ptr(valp), L.ptr(t_rp), L.ptr(t_col), L.ptr(t_val), L.ptr(row_scale), L.ptr(x),
+               x.stride(0), f, float(self_coef), L.ptr(bias), L.ptr(out), out.stride(0), L.ptr(bp.scratch(f)),
+               int(bool(accumulate)), L.stream())
         return out
-    assert valp is None, 'padded weights need a batch plan'
+    assert valp is None and tail is None, 'padded weights / a tail CSR need a batch plan'
     L.call('gd_spmm_acc', csr.ref, L.ptr(val), L.ptr(col_scale), L.ptr(row_scale), L.ptr(x), x.stride(0), f,
            float(self_coef), L.ptr(bias), L.ptr(out), out.stride(0), L.ptr(csr.scratch(f)), int(bool(accumulate)),
            L.stream())

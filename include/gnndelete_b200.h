@@ -164,6 +164,15 @@ int gd_spmm_batched(const gd_spmm_bplan_t* plan, const float* valp, const float*
                     int64_t ldx, int32_t feat, float self_coef, const float* bias, float* out, int64_t ldo,
                     float* scratch, int32_t accumulate, gd_stream_t stream);
 
+/* gd_spmm_batched plus a second, plain-CSR operand whose (few) entries are added to every row when it is
+ * flushed:  out[i,:] += sum_{k in tail row i} tail_val[k] * x[tail_col[k],:]  (inside the row scale).
+ * The loss gradient uses it for this step's negative pairs, whose incidence is rebuilt every epoch
+ * (framework/trainer/gnndelete.py:221-225) and therefore has no batch plan.  tail_* nullable. */
+int gd_spmm_batched_tail(const gd_spmm_bplan_t* plan, const float* valp, const int32_t* tail_rowptr,
+                         const int32_t* tail_col, const float* tail_val, const float* row_scale, const float* x,
+                         int64_t ldx, int32_t feat, float self_coef, const float* bias, float* out, int64_t ldo,
+                         float* scratch, int32_t accumulate, gd_stream_t stream);
+
 /* GATConv(heads=1) edge-softmax aggregation (gat.py:11-12; defaults negative_slope=0.2,
  * add_self_loops=True — the CSR must be built with self_loops=1):
  *   a_src[k] = <h_k, att_src>, a_dst[i] = <h_i, att_dst>                 (gd_gat_scores)

@@ -84,6 +84,23 @@ def test_engine_new_negatives_every_epoch(lib, static):
         eng2.capture(dynamic_negatives=True)
         eng2.set_negatives(neg2.to(DEV))
         U.assert_close(eng2.epoch(), want, what='losses through the in-graph negative rebuild')
+        # the double-buffered pipeline returns every step's losses, one step late, and matches the synchronous path
+        from gnndelete_b200.engine import EpochPipeline
+        eng3, eng4 = fresh(neg), fresh(neg)
+        eng3.capture(dynamic_negatives=True)
+        eng4.capture(dynamic_negatives=True)
+        pipe = EpochPipeline(eng3)
+        hosts = [neg.pin_memory(), neg2.pin_memory(), neg.pin_memory(), neg2.pin_memory()]
+        got, last = [], None
+        for h in hosts:
+            k = pipe.submit(h)
+            if last is not None:
+                got.append(pipe.result(last).clone())
+            last = k
+        got.append(pipe.result(last).clone())
+        for h, g_ in zip(hosts, got):
+            eng4.set_negatives(h.to(DEV))
+            assert torch.equal(eng4.epoch().cpu(), g_), 'pipelined step == synchronous step, bitwise'
 
 
 def test_engine_first_step_tight(lib):

@@ -113,6 +113,18 @@ def test_spmm_batched_matches_dense(lib, case, feat, workers):
     U.assert_close(out2, Aw @ x.double(), what=f'batched weighted F={feat} W={workers}')
     again = run(valp, None, 0.0, None, out2.clone(), 1)
     U.assert_close(again, 2 * (Aw @ x.double()), what='batched accumulate')
+    # a second plain CSR added row by row at the flush (this step's negative pairs in the loss gradient)
+    tm = 3 * n
+    ts_, td_ = torch.randint(0, n, (tm,), generator=g), torch.randint(0, n, (tm,), generator=g)
+    tail = build_csr(ts_.to(DEV), td_.to(DEV), n, self_loops=False)
+    tval = torch.randn(tm, generator=g)
+    tval_csr = tval.to(DEV)[tail.eid.long()]
+    T = torch.zeros(n, n, dtype=torch.float64)
+    T.index_put_((td_, ts_), tval.double(), accumulate=True)
+    out3 = torch.empty(n, feat, device=DEV)
+    L.call('gd_spmm_batched_tail', bp.ref, L.ptr(valp), L.ptr(tail.rowptr), L.ptr(tail.col), L.ptr(tval_csr), None, L.ptr(xd),
+           xd.stride(0), feat, 0.0, None, L.ptr(out3), out3.stride(0), L.ptr(bp.scratch(feat)), 0, L.stream())
+    U.assert_close(out3, (Aw + T) @ x.double(), what=f'batched + tail CSR F={feat} W={workers}')
     # bitwise reproducible (piece order is fixed by the plan, not by arrival)
     assert torch.equal(run(valp, None, 0.0, None, torch.empty(n, feat, device=DEV), 0), out2)
 
