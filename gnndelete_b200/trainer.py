@@ -136,9 +136,12 @@ class GNNDeleteTrainer(Trainer):
     log_every = 100      # epochs between device->host loss reads (the reference syncs 3x per epoch)
 
     def train(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
-        if not hasattr(model, 'deletion1') or type(model).__name__ != 'GCNDelete':
-            raise NotImplementedError('the fused epoch engine currently drives GCNDelete; other *Delete models '
-                                      'train through the autograd modules')
+        if not hasattr(model, 'deletion1'):
+            raise NotImplementedError('GNNDeleteTrainer trains the *Delete models (deletion1 / deletion2)')
+        if type(model).__name__ != 'GCNDelete':
+            # GATDelete / GINDelete: the same step body through the autograd modules (every layer is still one
+            # of the CUDA kernels; only the orchestration differs from the fused GCN engine)
+            return self.train_autograd(model, data, optimizer, args)
         # reference dispatch (gnndelete.py:39-44): 'ogbl' datasets take the mini-batch loop (edge-form NI),
         # everything else the full-batch loop whose NI term is the dense S_Df x S_Df block against the
         # original model's pair logits (`logits_ori`, pred_proba.pt).  Without `logits_ori` the edge form
@@ -196,6 +199,58 @@ class GNNDeleteTrainer(Trainer):
                     'optimizer_state': self._optimizer_state(optimizer, eng)},
                    os.path.join(args.checkpoint_dir, 'model_final.pt'))
         return eng
+
+    def train_autograd(self, model, data, optimizer, args):
+        """``train_minibatch``'s step body (gnndelete.py:347-409) on the whole graph for any *Delete model:
+        forward with positional masks (:352), fused decode + DEC + edge-form NI (`EdgeLossFn`), backward
+        through the conv / Del autograd Functions, ``optimizer.step()`` (the caller's optimizer)."""
+        from .losses import EdgeLossPlan, edge_loss
+        dev = torch.device('cuda')
+        model = model.to(dev)
+        data = data.to(dev)
+        ei = data.train_pos_edge_index
+        n_df = int(data.df_mask.sum())
+        gen = torch.Generator(device=dev).manual_seed(getattr(args, 'random_seed', 42))
+        fixed_neg = getattr(data, 'neg_edge_index', None)
+        neg = fixed_neg if fixed_neg is not None else self._negatives(data, n_df, gen)
+        ei_sdf = ei[:, data.sdf_mask].contiguous()
+        with torch.no_grad():
+            z_ori = getattr(data, 'z_ori', None)
+            if z_ori is None:
+                z_ori = model.get_original_embeddings(data.x, ei[:, data.dr_mask].contiguous())
+        ni = ei_sdf[:, ei_sdf[0] < ei_sdf[1]]                                   # gnndelete.py:379-381
+        plan = EdgeLossPlan(ei[:, data.df_mask], neg, ni, data.num_nodes, z_ori=z_ori.contiguous(),
+                            alpha=getattr(args, 'alpha', 0.5), static_negatives=fixed_neg is not None)
+        best_metric, ring, t0 = 0, [], time.time()
+        for epoch in range(args.epochs):
+            model.train()
+            if fixed_neg is None and epoch > 0:
+                plan.update_negatives(self._negatives(data, n_df, gen))
+            z = model(data.x, ei_sdf, data.sdf_node_1hop_mask, data.sdf_node_2hop_mask)       # :352
+            loss, loss_r, loss_l = edge_loss(z, plan)
+            loss.backward()
+            optimizer.step()
+            optimizer.zero_grad()
+            ring.append(torch.stack([loss.detach(), loss_r, loss_l]))
+            last = epoch + 1 == args.epochs
+            if (epoch + 1) % self.log_every == 0 or last or (epoch + 1) % args.valid_freq == 0:
+                vals = torch.stack(ring).cpu()
+                dt = (time.time() - t0) / len(ring)
+                for i, v in enumerate(vals.tolist()):
+                    self.trainer_log['log'].append({'Epoch': epoch + 1 - len(ring) + i, 'train_loss': v[0],
+                                                    'loss_r': v[1], 'loss_l': v[2], 'train_time': dt})
+                ring, t0 = [], time.time()
+            if (epoch + 1) % args.valid_freq == 0:
+                valid_loss, dt_auc, dt_aup, df_auc, df_aup, _, _, valid_log = self.eval(model, data, 'val')
+                valid_log['epoch'] = epoch
+                self.trainer_log['log'].append(valid_log)
+                if dt_auc + df_auc > best_metric:
+                    best_metric = dt_auc + df_auc
+                    torch.save({'model_state': model.state_dict(), 'optimizer_state': optimizer.state_dict()},
+                               os.path.join(args.checkpoint_dir, 'model_best.pt'))
+        torch.save({'model_state': {k: v.to('cpu') for k, v in model.state_dict().items()},
+                    'optimizer_state': optimizer.state_dict()}, os.path.join(args.checkpoint_dir, 'model_final.pt'))
+        return model
 
     @staticmethod
     def _optimizer_state(optimizer, eng):

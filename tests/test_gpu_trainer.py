@@ -65,6 +65,41 @@ def test_gnndelete_trainer_dropin(lib, tmp_path):
     assert os.path.exists(os.path.join(args.checkpoint_dir, 'trainer_log.json'))
 
 
+@pytest.mark.parametrize('gnn', ['gat', 'gin'])
+def test_gnndelete_trainer_gat_gin(lib, tmp_path, gnn):
+    """BASELINE config 2 route (`--gnn gat`) and GIN: the drop-in trainer against the oracle run with the same
+    schedule (6 Adam steps, supplied negatives)."""
+    import framework
+    from oracle import unlearn as OU
+    shape, raw, df, data, neg = U.make_case('pubmed' if gnn == 'gat' else 'cora', 0.1, in_dim=128)
+    args = _args(tmp_path, gnn=gnn, dataset='PubMed')
+    om = U.oracle_model(gnn, shape, data, dtype=torch.float64)
+    init = {k: v.float().clone() for k, v in om.state_dict().items()}
+    d64 = data.clone(); d64.x = data.x.double()
+    with torch.no_grad():
+        zo = om.get_original_embeddings(d64.x, d64.train_pos_edge_index[:, d64.dr_mask])
+    opt = torch.optim.Adam([p for n, p in om.named_parameters() if 'del' in n], lr=args.lr)
+    hist = []
+    for _ in range(args.epochs):
+        loss, _, _, _ = OU.edge_form_loss(om, d64, neg, zo)
+        loss.backward(); opt.step(); opt.zero_grad()
+        hist.append(float(loss))
+    model = framework.get_model(args, data.sdf_node_1hop_mask, data.sdf_node_2hop_mask, num_nodes=data.num_nodes,
+                                num_edge_type=None)
+    assert type(model).__name__ == {'gat': 'GATDelete', 'gin': 'GINDelete'}[gnn]
+    model.load_state_dict(init, strict=False)
+    optimizer = torch.optim.Adam([p for n, p in model.named_parameters() if 'del' in n], lr=args.lr)
+    trainer = framework.get_trainer(args)
+    d = data.clone()
+    d.neg_edge_index = neg.to(DEV)
+    trainer.train(model, d, optimizer, args)
+    U.assert_close(model.deletion1.deletion_weight, om.deletion1.deletion_weight, tol=1e-4, what='W_del1')
+    U.assert_close(model.deletion2.deletion_weight, om.deletion2.deletion_weight, tol=1e-4, what='W_del2')
+    logs = [l['train_loss'] for l in trainer.trainer_log['log'] if 'train_loss' in l]
+    U.assert_close(torch.tensor(logs), torch.tensor(hist), tol=1e-4, what='loss curve')
+    assert os.path.exists(os.path.join(args.checkpoint_dir, 'model_final.pt'))
+
+
 def test_eval_matches_sklearn(lib, tmp_path):
     """Trainer.eval's device AUC/AP against sklearn on the same logits (base.py:247-248)."""
     from sklearn.metrics import average_precision_score, roc_auc_score
