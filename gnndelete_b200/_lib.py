@@ -56,6 +56,7 @@ SIGNATURES = {
     'gd_spmm_batched_workers': (_i32, [_i32, _i32]),
     'gd_spmm_batched': (C.c_int, [_bplan_p, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _i32, _vp]),
     'gd_spmm_batched_tail': (C.c_int, [_bplan_p, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _i32, _vp]),
+    'gd_gemm_rows_tc_batch': (C.c_int, [_vp, _i64, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _i64, _i64, _i32, _vp]),
     'gd_gat_scores': (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     'gd_gat_fwd': (C.c_int, [_csr_p, _vp, _i64, _i32, _vp, _vp, _vp, _f32, _vp, _i64, _vp, _vp, _vp]),
     'gd_gat_bwd_dst': (C.c_int, [_csr_p, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _f32,

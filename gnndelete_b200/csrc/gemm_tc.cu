@@ -783,6 +783,18 @@ extern "C" int gd_gemm_rows_tc(const float* a, int64_t lda, const int32_t* rows,
     }
 }
 
+extern "C" int gd_gemm_rows_tc_batch(const float* a, int64_t lda, int64_t m, int32_t k, const float* b, int64_t b_stride,
+                                     int32_t b_is_nk, int32_t n, float* out, int64_t out_stride, int64_t ldo, int32_t batch,
+                                     gd_stream_t stream) {
+    GD_CHECK_ARG(batch >= 0, "negative batch");
+    for (int32_t i = 0; i < batch; ++i) {
+        const int rc = gd_gemm_rows_tc(a, lda, nullptr, m, k, b + (int64_t)i * b_stride, b_is_nk, n, nullptr, nullptr, nullptr, 0,
+                                       0, 0, out + (int64_t)i * out_stride, ldo, nullptr, nullptr, stream);
+        if (rc != GD_OK) return rc;
+    }
+    return GD_OK;
+}
+
 // out[i] = sum_p partial[p][i] in a fixed order: warp w of a block adds the partials p = w, w + 8, ... for 32
 // consecutive elements (coalesced, all loads independent), then the 8 warp sums are added in warp order.
 __global__ void __launch_bounds__(256) tn_reduce_kernel(const float* __restrict__ partial, int nparts, int64_t count,

@@ -331,6 +331,35 @@ def _rgcn_weights_of(plan):
 GraphPlan.rgcn_weights = property(_rgcn_weights_of)
 
 
+def _rgcn_virtual(plan, transposed):
+    """CSR over the VIRTUAL sources ``rel * N + col`` (the rows of the stacked per-relation transforms
+    ``[R N, F]``) for the transform-then-gather RGCN path; ``None`` when the index would overflow int32."""
+    cache = plan.__dict__.setdefault('_rgcn_vcsr', {})
+    if transposed not in cache:
+        csr = plan.bwd if transposed else plan.fwd
+        num_rel = int(csr.rel.max().item()) + 1 if (csr.rel is not None and csr.nnz) else 1
+        if csr.rel is None or num_rel * plan.num_nodes >= (1 << 31):
+            cache[transposed] = None
+        else:
+            vcol = (csr.rel.long() * plan.num_nodes + csr.col.long()).to(torch.int32).contiguous()
+            cache[transposed] = CSR(csr.rowptr, vcol, csr.eid, None, csr.num_rows, csr.nnz)
+    return cache[transposed]
+
+
+def _rgcn_virtual_weights(plan, transposed, bp):
+    """The per-entry mean weights ``1 / |N_r(i)|`` in the padded slot layout of batch plan ``bp``."""
+    cache = plan.__dict__.setdefault('_rgcn_vw', {})
+    key = (transposed, id(bp))
+    if key not in cache:
+        w_fwd, w_bwd = plan.rgcn_weights
+        cache[key] = bp.pad_values(w_bwd if transposed else w_fwd)
+    return cache[key]
+
+
+GraphPlan.rgcn_virtual = _rgcn_virtual
+GraphPlan.rgcn_virtual_weights = _rgcn_virtual_weights
+
+
 class PlanCache:
     """Two-level cache: tensor identity ``(data_ptr, shape, version)`` first, then a
     content check against the cached copy, so that callers which re-materialise the

@@ -252,6 +252,12 @@ int gd_gemm_rows_tc(const float* a, int64_t lda, const int32_t* rows, int64_t m,
                     const float* out_scale, const float* gate, int64_t ldgate, int32_t relu_in,
                     int32_t relu_out, float* out, int64_t ldo, uint32_t* relu_mask_out,
                     const uint32_t* gate_bits, gd_stream_t stream);
+/* `batch` products of the SAME rows with different B matrices, out_i = a . B_i (B_i = b + i * b_stride,
+ * out_i = out + i * out_stride): the per-relation transforms Y_r = x . W_r of RGCNConv (rgcn.py:17-22)
+ * issued from one call.  No row list, bias, scale or gate. */
+int gd_gemm_rows_tc_batch(const float* a, int64_t lda, int64_t m, int32_t k, const float* b, int64_t b_stride,
+                          int32_t b_is_nk, int32_t n, float* out, int64_t out_stride, int64_t ldo, int32_t batch,
+                          gd_stream_t stream);
 
 /* c[k1,n2] = sum_i a_scale[r(i)] * a[r(i),:k1]^T (outer) g[r(i),:n2] — weight gradient
  * of the contraction above over the (gathered) rows; relu_a applies ReLU to the `a`

@@ -1,6 +1,6 @@
 #!/bin/bash
 {
-python -m pytest tests/test_gpu_trainer.py -x -q 2>&1 | tail -5
-timeout 500 python tools/config_bench.py --epochs 20
+python -m pytest tests/test_gpu_gat_rgcn.py tests/test_gpu_trainer.py -x -q 2>&1 | tail -3
+timeout 500 python tools/config_bench.py --epochs 30 --configs biokg
 } > gpurun_out/check.log 2>&1
-cat gpurun_out/check.log | cut -c1-1200
+cat gpurun_out/check.log | cut -c1-900
