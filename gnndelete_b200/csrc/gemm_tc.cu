@@ -333,7 +333,10 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) gemm_rows_tc_kernel(const Arg
                 *reinterpret_cast<float4*>(ahi + o) = hi;
                 *reinterpret_cast<float4*>(alo + o) = lo;
             }
-            fence_proxy_async();                                   // every writer orders its own stores for the async proxy
+            // No proxy fence here: ptxas lowers fence.proxy.async to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the MEMBAR
+            // waits for this thread's PREFETCHED global loads (the next stages) - it serialised the register ring.
+            // The stores are published by the (release) arrive; the MMA thread, which has no loads in flight,
+            // executes the generic->async proxy fence after it has acquired the barrier.
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -372,6 +375,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) gemm_rows_tc_kernel(const Arg
                 const uint32_t d = tmem_base + acc * 2 * g.n, dc = d + g.n;
                 for (int c = 0; c < kchunks; ++c) {
                     mbar_wait(&full_bar[stage], phase);
+                    fence_proxy_async();                           // the producers' generic stores -> async proxy (see consume())
                     tc_fence_after();
                     const uint32_t ahi = smem_u32(a_ring + stage * 2 * TILE_BYTES), alo = ahi + TILE_BYTES;
                     const uint32_t bhi = smem_u32(b_hi + c * b_tile), blo = smem_u32(b_lo + c * b_tile);
@@ -632,7 +636,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tn_tc_kernel(const TnArgs
                     *reinterpret_cast<float4*>(gt_lo + i * TN_ATOM_COL) = lo;
                 }
             }
-            fence_proxy_async();
+            // (no proxy fence on this side: see gemm_rows_tc_kernel's consume())
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[stage]);               // one arrival per warp
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -660,6 +664,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tn_tc_kernel(const TnArgs
                 const int s_end = min(nstages, (grp + 1) * TN_FLUSH);
                 for (int s = grp * TN_FLUSH; s < s_end; ++s) {
                     mbar_wait(&full_bar[stage], phase);
+                    fence_proxy_async();                           // the producers' generic stores -> async proxy
                     tc_fence_after();
                     const uint32_t ahi = smem_u32(smem + stage * stage_bytes), alo = ahi + TILE_BYTES;
                     const uint32_t ghi = alo + TILE_BYTES, glo = ghi + g_tile;

@@ -79,6 +79,18 @@ class GCNDeleteEngine:
         self.graph = None
         self._graph_dynamic_neg = False
         self.launches_per_epoch = None
+        # the complement-row copies of the Del layers touch rows the gathered-row GEMM does not: they run on a side
+        # stream next to it (fork / join; captured as parallel graph branches)
+        self.side = torch.cuda.Stream()
+
+    def _del_rows(self, src, dst, comp, gemm):
+        """``dst[rows] = gemm(src[rows])`` on the current stream, ``dst[comp] = src[comp]`` concurrently."""
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            ops.copy_rows(src, dst, comp)
+        gemm()
+        cur.wait_stream(self.side)
 
     # ------------------------------------------------------------------ forward
     def layer1(self):
@@ -93,13 +105,12 @@ class GCNDeleteEngine:
             self.layer1()
         w1 = m.deletion1.deletion_weight.detach()
         w2 = m.deletion2.deletion_weight.detach()
-        ops.gemm_rows(self.a1, w1, False, out=self.x1, rows=self.rows1,           # Del1 on S1
-                      relu_mask_out=self.x1_bits)
-        ops.copy_rows(self.a1, self.x1, self.comp1)
+        self._del_rows(self.a1, self.x1, self.comp1, lambda: ops.gemm_rows(                   # Del1 on S1
+            self.a1, w1, False, out=self.x1, rows=self.rows1, relu_mask_out=self.x1_bits))
         ops.gemm_rows(self.x1, m.conv2.lin.weight.detach(), True, out=self.h1, out_scale=p.dinv, relu_in=True)
         ops.spmm(p.fwd, self.h1, out=self.a2, row_scale=p.dinv, bias=m.conv2.bias.detach())
-        ops.gemm_rows(self.a2, w2, False, out=self.z, rows=self.rows2)             # Del2 on S2
-        ops.copy_rows(self.a2, self.z, self.comp2)
+        self._del_rows(self.a2, self.z, self.comp2, lambda: ops.gemm_rows(                    # Del2 on S2
+            self.a2, w2, False, out=self.z, rows=self.rows2))
         return self.loss.forward(self.z)
 
     # ----------------------------------------------------------------- backward
@@ -114,8 +125,8 @@ class GCNDeleteEngine:
             self.losses_total[2:3].copy_(loss_l)
             torch.add(self.loss.losses[0:1], loss_l, alpha=1.0 - self.alpha, out=self.losses_total[0:1])
         ops.gemm_tn_rows(self.a2, self.dz, rows=self.rows2, out=g2)                # dW_del2
-        ops.gemm_rows(self.dz, w2, True, out=self.da2, rows=self.rows2)            # dz[S2] @ W2^T
-        ops.copy_rows(self.dz, self.da2, self.comp2)
+        self._del_rows(self.dz, self.da2, self.comp2, lambda: ops.gemm_rows(                  # dz[S2] @ W2^T
+            self.dz, w2, True, out=self.da2, rows=self.rows2))
         ops.spmm(p.bwd, self.da2, out=self.dh1, col_scale=p.dinv)                  # A^T D^-1/2 dA2
         ops.gemm_rows(self.dh1, m.conv2.lin.weight.detach(), False, out=self.dx1, rows=self.rows1,
                       out_scale=p.dinv, gate=None if self.bitmask else self.x1,
