@@ -38,7 +38,7 @@ constexpr int MMA_WARP = 12;                     // warps 8-11: epilogue (warp %
 constexpr int NUM_THREADS = 13 * 32;
 constexpr int EPI_LD = 36;                       // padded row (floats) of the per-warp epilogue transpose tile
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
-constexpr int PREFETCH = 3;                      // producer register ring depth (stages of loads in flight)
+constexpr int PREFETCH = 4;                      // producer register ring depth (stages of loads in flight)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -162,13 +162,14 @@ struct Args {
     int debug;          // GD_TC_DEBUG bit mask (measurement only): 1 = no epilogue work, 2 = producers do not load, 4 = no MMAs, 8 = epilogue without global stores, 16 = epilogue without TMEM loads
 };
 
-// Warp roles of gemm_rows_tc_kernel: 8 producers, 8 epilogue warps (two per TMEM lane quarter, each
-// taking every other 32-column group), 1 MMA issuer.  Measured (tools/gemm_sweep.py with GD_TC_DEBUG):
+// Warp roles of gemm_rows_tc_kernel: 16 producers, 4 epilogue warps (one per TMEM lane quarter), 1 MMA issuer.  Measured (tools/gemm_sweep.py with GD_TC_DEBUG):
 // with 4 epilogue warps running a flag-generic epilogue the kernel was epilogue bound at 5.5 us per
 // 128 x 128 tile whatever the producers did; the epilogue is therefore specialised at compile time
 // (EPI_* bits) and spread over twice the warps.
-constexpr int ROWS_EPI_WARPS = 8;
-constexpr int ROWS_MMA_WARP = NUM_PRODUCER_WARPS + ROWS_EPI_WARPS;
+constexpr int ROWS_PRODUCER_WARPS = 16;                       // 512 threads: 8 per row, 64 rows per pass, 2 passes per stage
+constexpr int ROWS_PASSES = 128 / (ROWS_PRODUCER_WARPS * 4);
+constexpr int ROWS_EPI_WARPS = 4;
+constexpr int ROWS_MMA_WARP = ROWS_PRODUCER_WARPS + ROWS_EPI_WARPS;
 constexpr int ROWS_THREADS = (ROWS_MMA_WARP + 1) * 32;
 constexpr int RE_COLS = 16;                                   // columns per epilogue step
 constexpr int RE_LD = RE_COLS;                                // row (floats) of the per-warp transpose tile; 16-byte chunk c of row r sits at c ^ ((r >> 1) & 3):
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) gemm_rows_tc_kernel(const Arg
 
     if (tid == 0) {
         // one arrival per warp (after a __syncwarp): 256 per-thread arrivals on one mbarrier serialise
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], NUM_PRODUCER_WARPS); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], ROWS_PRODUCER_WARPS); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], ROWS_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -266,41 +267,42 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) gemm_rows_tc_kernel(const Arg
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    if (warp < NUM_PRODUCER_WARPS) {
+    if (warp < ROWS_PRODUCER_WARPS) {
         // ================================ producers ================================
-        // 256 threads: 8 threads per row (one 16-byte chunk each), 32 rows per pass, 4 passes per stage.
+        // 512 threads: 8 threads per row (one 16-byte chunk each), 64 rows per pass, 2 passes per stage (the per-stage
+        // latency of a producer warp, ~1200 cycles with 4 passes, was the floor of the kernel: twice the warps, half the work each).
         // Loads run PREFETCH stages ahead of the shared-memory stores through a register ring, so
         // ~48 KB of gathers are in flight per SM while earlier stages are split / stored / consumed.
         const int j = tid & 7, r0 = tid >> 3;
         int p_tile = blockIdx.x, p_c = 0;                         // prefetch cursor (tile, k-chunk)
-        const float* psrc[4];
-        int32_t rid_next[4];
-        auto load_rids = [&](int tile, int32_t (&rid)[4]) {
+        const float* psrc[ROWS_PASSES];
+        int32_t rid_next[ROWS_PASSES];
+        auto load_rids = [&](int tile, int32_t (&rid)[ROWS_PASSES]) {
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const int64_t i = (int64_t)tile * BM + r0 + 32 * p;
+            for (int p = 0; p < ROWS_PASSES; ++p) {
+                const int64_t i = (int64_t)tile * BM + r0 + (128 / ROWS_PASSES) * p;
                 rid[p] = (tile < g.num_tiles && i < g.m) ? (g.rows ? __ldg(g.rows + i) : (int32_t)i) : -1;
             }
         };
-        auto set_src = [&](const int32_t (&rid)[4]) {
+        auto set_src = [&](const int32_t (&rid)[ROWS_PASSES]) {
 #pragma unroll
-            for (int p = 0; p < 4; ++p) psrc[p] = rid[p] >= 0 ? g.a + (int64_t)rid[p] * g.lda + j * 4 : nullptr;
+            for (int p = 0; p < ROWS_PASSES; ++p) psrc[p] = rid[p] >= 0 ? g.a + (int64_t)rid[p] * g.lda + j * 4 : nullptr;
         };
         // Whole rows of the tile after next are pulled into L2 with one bulk prefetch per row: the stage loads
         // below touch a row in four 128-byte pieces spread over time, which DRAM serves poorly on its own.
         const bool pf_ok = (g.k & 3) == 0 && !(g.debug & 32);
-        auto l2_prefetch_rows = [&](const int32_t (&rid)[4]) {
+        auto l2_prefetch_rows = [&](const int32_t (&rid)[ROWS_PASSES]) {
             if (j != 0 || !pf_ok) return;
 #pragma unroll
-            for (int p = 0; p < 4; ++p)
+            for (int p = 0; p < ROWS_PASSES; ++p)
                 if (rid[p] >= 0)
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g.a + (int64_t)rid[p] * g.lda), "r"(g.k * 4) : "memory");
         };
-        auto issue = [&](float4 (&buf)[4]) {                       // loads of stage (p_tile, p_c); advance cursor
+        auto issue = [&](float4 (&buf)[ROWS_PASSES]) {                       // loads of stage (p_tile, p_c); advance cursor
             if (p_tile >= g.num_tiles) return;
             const int kbase = p_c * KC + j * 4;
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
+            for (int p = 0; p < ROWS_PASSES; ++p) {
                 buf[p] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (psrc[p] != nullptr && !(g.debug & 2)) {
                     if (kbase + 4 <= g.k) buf[p] = __ldg(reinterpret_cast<const float4*>(psrc[p] + p_c * KC));
@@ -319,17 +321,17 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) gemm_rows_tc_kernel(const Arg
             }
         };
         uint32_t stage = 0, phase = 0;
-        auto consume = [&](const float4 (&buf)[4]) {               // split + store one stage
+        auto consume = [&](const float4 (&buf)[ROWS_PASSES]) {               // split + store one stage
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* ahi = a_ring + stage * 2 * TILE_BYTES;
             uint8_t* alo = ahi + TILE_BYTES;
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
+            for (int p = 0; p < ROWS_PASSES; ++p) {
                 float4 x = buf[p];
                 if (g.relu_in) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
                 float4 hi, lo;
                 split4(x, hi, lo);
-                const uint32_t o = swz(r0 + 32 * p, j);
+                const uint32_t o = swz(r0 + (128 / ROWS_PASSES) * p, j);
                 *reinterpret_cast<float4*>(ahi + o) = hi;
                 *reinterpret_cast<float4*>(alo + o) = lo;
             }
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) gemm_rows_tc_kernel(const Arg
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         };
         {
-            int32_t rid0[4];
+            int32_t rid0[ROWS_PASSES];
             load_rids(p_tile, rid0);
             set_src(rid0);
             load_rids(p_tile + gridDim.x, rid_next);
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) gemm_rows_tc_kernel(const Arg
         }
         const int my_tiles = blockIdx.x < g.num_tiles ? (g.num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
         const int total = my_tiles * kchunks;
-        float4 buf[PREFETCH][4];
+        float4 buf[PREFETCH][ROWS_PASSES];
 #pragma unroll
         for (int d = 0; d < PREFETCH; ++d) issue(buf[d]);
         for (int s = 0; s < total; s += PREFETCH) {
@@ -397,13 +399,12 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) gemm_rows_tc_kernel(const Arg
         __syncwarp();
     } else {
         // ================================ epilogue ================================
-        // thread = accumulator row (TMEM lane).  A warp owns one TMEM lane quarter and every other
-        // 32-column group; each 16-column step is transposed through a per-warp shared-memory tile so
+        // thread = accumulator row (TMEM lane).  A warp owns one TMEM lane quarter (all column groups);
+        // each 16-column step is transposed through a per-warp shared-memory tile so
         // that the (scattered) output rows are written as 64-byte runs (4 lanes x 16 B per row, 8 rows
         // per instruction).
-        const int ew = warp - NUM_PRODUCER_WARPS;
+        const int ew = warp - ROWS_PRODUCER_WARPS;
         const int q = warp & 3;                                    // TMEM lane quarter (hardware: warp id % 4)
-        const int half = ew >> 2;                                  // which 32-column groups: half, half + 2, ...
         const int lr = q * 32 + lane;                              // row inside the tile == TMEM lane
         float* tbuf = epi_buf + ew * (32 * RE_LD);
         const int cl = lane & 3, rl = lane >> 2;                   // coalesced phase: 16-byte chunk / row-in-group
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) gemm_rows_tc_kernel(const Arg
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             if (!(g.debug & 1)) {
-                for (int c32 = half * 32; c32 < g.n; c32 += 64) {
+                for (int c32 = 0; c32 < g.n; c32 += 32) {
                     uint32_t gword = 0xffffffffu, pos_bits = 0;
                     if (has_gbits && r >= 0) gword = __ldg(g.gate_bits + (int64_t)r * nw + (c32 >> 5));
 #pragma unroll
