@@ -95,6 +95,7 @@ def test_gnndelete_trainer_gat_gin(lib, tmp_path, gnn):
     trainer.train(model, d, optimizer, args)
     U.assert_close(model.deletion1.deletion_weight, om.deletion1.deletion_weight, tol=1e-4, what='W_del1')
     U.assert_close(model.deletion2.deletion_weight, om.deletion2.deletion_weight, tol=1e-4, what='W_del2')
+    assert trainer.trainer_log['captured_step'], trainer.trainer_log.get('capture_error')   # the step ran as one CUDA graph
     logs = [l['train_loss'] for l in trainer.trainer_log['log'] if 'train_loss' in l]
     U.assert_close(torch.tensor(logs), torch.tensor(hist), tol=1e-4, what='loss curve')
     assert os.path.exists(os.path.join(args.checkpoint_dir, 'model_final.pt'))

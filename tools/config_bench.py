@@ -53,6 +53,12 @@ for name in a.configs.split(','):
             'deleted': shape.num_deleted, 'dims': [shape.in_dim, shape.hidden_dim, shape.out_dim], 'epochs': a.epochs,
             'epochs_per_s_through_trainer': a.epochs / dt, 'ms_per_epoch': 1e3 * dt / a.epochs,
             'note': 'wall clock around trainer.train (includes plan build of the second call, logging, checkpoint write)'}
+    tt = sorted(l['train_time'] for l in trainer.trainer_log['log'] if 'train_time' in l)
+    if tt:
+        line['epochs_per_s_steady_state'] = 1.0 / tt[len(tt) // 4]       # trainer's own per-epoch time (logged every log_every epochs), lower quartile
+    for k in ('captured_step', 'capture_error'):
+        if k in trainer.trainer_log:
+            line[k] = trainer.trainer_log[k]
     if shape.gnn == 'gcn':                                       # the fused engine alone, CUDA-graph replay
         with torch.no_grad():
             zo = model.get_original_embeddings(data.x, data.train_pos_edge_index[:, data.dr_mask])
