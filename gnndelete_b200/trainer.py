@@ -170,7 +170,10 @@ class GNNDeleteTrainer(Trainer):
                 z_ori = model.get_original_embeddings(data.x, data.train_pos_edge_index[:, data.dr_mask])
         group = optimizer.param_groups[0]
         eng = GCNDeleteEngine(model, data, neg, z_ori=z_ori, lr=group['lr'], betas=group['betas'], eps=group['eps'],
-                              hoist_layer1=True, logits_ori=logits_ori)
+                              hoist_layer1=True, logits_ori=logits_ori, static_negatives=fixed_neg is not None)
+        if getattr(args, 'capture_step', True) and logits_ori is None:
+            # one cudaGraphLaunch per epoch; resampled negatives are written into the graph's staging buffer
+            eng.capture(warmup=2, dynamic_negatives=fixed_neg is None)
         best_metric = 0
         ring = []
         t0 = time.time()
