@@ -12,7 +12,7 @@ __global__ void make_keys_kernel(const int64_t* __restrict__ src, const int64_t*
                                  const int64_t* __restrict__ rel, int64_t E, int64_t N, int R,
                                  int self_loops, int64_t key_drop, int64_t* __restrict__ keys,
                                  int32_t* __restrict__ vals, int32_t* __restrict__ status) {
-    int64_t total = E + (self_loops ? N : 0);
+    int64_t total = E + ((self_loops & 1) ? N : 0);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         if (i < E) {
@@ -20,8 +20,10 @@ __global__ void make_keys_kernel(const int64_t* __restrict__ src, const int64_t*
             int64_t r = rel ? rel[i] : 0;
             bool bad = s < 0 || s >= N || d < 0 || d >= N || r < 0 || r >= R;
             if (bad) atomicAdd(&status[1], 1);
-            bool drop = bad || (self_loops && s == d);
-            keys[i] = drop ? key_drop : ((d * R + r) * N + s);
+            bool drop = bad || ((self_loops & 1) && s == d);
+            // bit 1 of self_loops: order rows only (key = destination): fewer radix passes; the stable sort keeps the
+            // input order inside a row, so the result is still deterministic
+            keys[i] = drop ? key_drop : ((self_loops & 2) ? d : ((d * R + r) * N + s));
             vals[i] = (int32_t)i;
         } else {
             int64_t v = i - E;
@@ -33,6 +35,7 @@ __global__ void make_keys_kernel(const int64_t* __restrict__ src, const int64_t*
 
 // sorted keys -> rowptr / col / rel ; one thread per sorted entry
 __global__ void csr_fill_kernel(const int64_t* __restrict__ keys, const int32_t* __restrict__ vals,
+                                const int64_t* __restrict__ src_if_rows_only,
                                 int64_t total, int64_t N, int R, int64_t key_drop,
                                 int32_t* __restrict__ rowptr, int32_t* __restrict__ col,
                                 int32_t* __restrict__ eid, int32_t* __restrict__ rel_out,
@@ -44,16 +47,22 @@ __global__ void csr_fill_kernel(const int64_t* __restrict__ keys, const int32_t*
         if (i < total) {
             int64_t k = keys[i];
             if (k != key_drop) {
-                int64_t dr = k / N;
-                row_i = dr / R;
-                col[i] = (int32_t)(k - dr * N);
-                eid[i] = vals[i];
-                if (rel_out) rel_out[i] = (int32_t)(dr - row_i * R);
+                if (src_if_rows_only) {
+                    row_i = k;
+                    col[i] = (int32_t)src_if_rows_only[vals[i]];
+                    eid[i] = vals[i];
+                } else {
+                    int64_t dr = k / N;
+                    row_i = dr / R;
+                    col[i] = (int32_t)(k - dr * N);
+                    eid[i] = vals[i];
+                    if (rel_out) rel_out[i] = (int32_t)(dr - row_i * R);
+                }
             }
         }
         if (i > 0) {
             int64_t kp = keys[i - 1];
-            row_p = (kp == key_drop) ? N : (kp / N) / R;
+            row_p = (kp == key_drop) ? N : (src_if_rows_only ? kp : (kp / N) / R);
         }
         // rows (row_p, row_i] start at i
         if (row_i != row_p) {
@@ -145,7 +154,9 @@ extern "C" int gd_csr_from_coo(const int64_t* src, const int64_t* dst, const int
     GD_CHECK_ARG(E >= 0 && N >= 0, "negative size");
     GD_CHECK_ARG(R >= 1, "num_rel must be >= 1");
     GD_CHECK_ARG(rowptr && status, "null output");
-    int64_t total = E + (self_loops ? N : 0);
+    const bool rows_only = (self_loops & 2) != 0;
+    GD_CHECK_ARG(!rows_only || (rel == nullptr && R == 1 && !(self_loops & 1)), "row-order-only build: no relations, no self loops");
+    int64_t total = E + ((self_loops & 1) ? N : 0);
     GD_CHECK_ARG(total < INT32_MAX, "more than 2^31-1 entries");
     GD_CHECK_ARG((double)N * (double)R * (double)N < 9.0e18, "sort key overflows int64");
     if (workspace_bytes < gd_csr_workspace_bytes(E, N))
@@ -156,7 +167,7 @@ extern "C" int gd_csr_from_coo(const int64_t* src, const int64_t* dst, const int
         return GD_OK;
     }
     GD_CHECK_ARG(src && dst && col && eid, "null pointer");
-    int64_t key_drop = N * (int64_t)R * N;   // strictly above every valid key
+    int64_t key_drop = rows_only ? N : N * (int64_t)R * N;   // strictly above every valid key
 
     char* p = static_cast<char*>(workspace);
     int64_t* keys0 = reinterpret_cast<int64_t*>(p); p += align_up(total * sizeof(int64_t));
@@ -172,7 +183,7 @@ extern "C" int gd_csr_from_coo(const int64_t* src, const int64_t* dst, const int
     cub::DoubleBuffer<int64_t> kb(keys0, keys1);
     cub::DoubleBuffer<int32_t> vb(vals0, vals1);
     GD_CUDA(cub::DeviceRadixSort::SortPairs(p, sort_bytes, kb, vb, (int)total, 0, key_bits(key_drop), stream));
-    csr_fill_kernel<<<blocks, threads, 0, stream>>>(kb.Current(), vb.Current(), total, N, R, key_drop,
+    csr_fill_kernel<<<blocks, threads, 0, stream>>>(kb.Current(), vb.Current(), rows_only ? src : nullptr, total, N, R, key_drop,
                                                     rowptr, col, eid, rel_out, status);
     GD_LAUNCH_CHECK();
     return GD_OK;

@@ -172,7 +172,7 @@ class EdgeLossPlan:
         self.neg_dst[:n_df].copy_(nu); self.neg_dst[n_df:].copy_(nv)
         self.neg_src[:n_df].copy_(nv); self.neg_src[n_df:].copy_(nu)
         m = 2 * n_df
-        L.call('gd_csr_from_coo', L.ptr(self.neg_src), L.ptr(self.neg_dst), None, m, self.num_nodes, 1, 0,
+        L.call('gd_csr_from_coo', L.ptr(self.neg_src), L.ptr(self.neg_dst), None, m, self.num_nodes, 1, 2,   # rows ordered only
                L.ptr(self.neg_rowptr), L.ptr(self.neg_col), L.ptr(self.neg_eid), None, L.ptr(self.neg_status),
                L.ptr(self.neg_ws), self.neg_ws_bytes, L.stream())
         L.call('gd_invert_perm', L.ptr(self.neg_eid), m, L.ptr(self.neg_pos), L.stream())

@@ -79,7 +79,10 @@ size_t gd_csr_workspace_bytes(int64_t num_edges, int64_t num_nodes);
  * edge_index[1]) -> CSR sorted by (dst, [rel,] src).
  *   self_loops = 1: PyG add_remaining_self_loops — existing (v,v) entries are
  *                   dropped and one (v,v) per node is inserted (GCNConv, GATConv);
- *   self_loops = 0: entries kept as they are (GINConv, RGCNConv, loss incidence).
+ *   self_loops = 0: entries kept as they are (GINConv, RGCNConv, loss incidence);
+ *   self_loops = 2: as 0, but only the ROWS are ordered (stable sort on the destination alone, fewer radix passes):
+ *                   entries of a row keep their input order.  For per-step structures such as the negative-pair
+ *                   incidence, where any fixed order is as good as the sorted one.  No relations.
  * `rel` (nullable, values in [0, num_rel)) adds the relation as a secondary sort key
  * and is written per entry to `rel_out`.
  * `eid[k]` = column of the input COO that landed at CSR position k, or

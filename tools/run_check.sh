@@ -1,6 +1,13 @@
 #!/bin/bash
 {
-python -m pytest tests/test_gpu_trainer.py tests/test_gpu_engine.py -x -q 2>&1 | tail -3
-timeout 500 python tools/config_bench.py --epochs 1000 --configs cora
+python -m pytest tests/ -m gpu -x -q 2>&1 | tail -3
+python bench.py --no-cpu-baseline
 } > gpurun_out/check.log 2>&1
-cat gpurun_out/check.log | cut -c1-1200
+cat gpurun_out/check.log | python -c "
+import sys, json
+for l in sys.stdin:
+    l=l.strip()
+    if l.startswith('{'):
+        d=json.loads(l); print('value',d['value'],'hoisted',d['value_hoisted'],'e2e',d['e2e']['value'],'sync',d['e2e']['value_step_synchronous']); print(d['roofline']['frac'], d['roofline']['kernel_ms'], d['roofline']['other_kernels'])
+    else: print(l[:200])
+"
