@@ -1,4 +1,6 @@
 // Error reporting and version of the C ABI.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gd {
@@ -8,6 +10,10 @@ void set_error(const std::string& msg) { g_last_error = msg; }
 int fail(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
+}
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("GD_PDL"); return e && e[0] == '1';      // opt-in: measured SLOWER on the Collab epoch (917 vs 1090 epochs/s) }();
+    return on;
 }
 }  // namespace gd
 

@@ -193,6 +193,8 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int np
 
 __global__ void copy_rows_kernel(const float* __restrict__ src, int64_t lds, const int32_t* __restrict__ rows,
                                  int64_t m, int feat, float* __restrict__ dst, int64_t ldd) {
+    pdl_wait();
+    pdl_trigger();
     // one warp per row
     const int lane = threadIdx.x & 31;
     for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; i < m;
@@ -218,6 +220,8 @@ __global__ void relu_fwd_kernel(const float* __restrict__ x, int64_t count, floa
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, float* __restrict__ step, int64_t count, float lr,
                             float beta1, float beta2, float eps) {
+    pdl_wait();
+    pdl_trigger();
     // torch.optim.Adam (single-tensor path): bias corrections from the incremented step
     const float t = *step + 1.0f;
     const float bc1 = 1.0f - powf(beta1, t);
@@ -235,7 +239,11 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
-__global__ void adam_bump_kernel(float* step) { *step += 1.0f; }
+__global__ void adam_bump_kernel(float* step) {
+    pdl_wait();
+    pdl_trigger();
+    *step += 1.0f;
+}
 
 }  // namespace gd
 
@@ -291,7 +299,7 @@ extern "C" int gd_copy_rows(const float* src, int64_t lds, const int32_t* rows, 
     if (m == 0) return GD_OK;
     GD_CHECK_ARG(src && dst && feat > 0, "bad argument");
     int blocks = (int)std::min<int64_t>(ceil_div<int64_t>(m, 8), kNumSMs * 32);
-    copy_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(src, lds, rows, m, feat, dst, ldd);
+    GD_CUDA(launch_pdl(copy_rows_kernel, blocks, 256, 0, as_stream(stream), src, lds, rows, m, feat, dst, ldd));
     GD_LAUNCH_CHECK();
     return GD_OK;
 }
@@ -319,10 +327,10 @@ extern "C" int gd_adam_step(float* param, const float* grad, float* exp_avg, flo
     GD_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && step, "null pointer");
     if (count > 0) {
         int blocks = (int)std::min<int64_t>(ceil_div<int64_t>(count, 256), kNumSMs * 8);
-        adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, step, count, lr, beta1, beta2, eps);
+        GD_CUDA(launch_pdl(adam_kernel, blocks, 256, 0, as_stream(stream), param, grad, exp_avg, exp_avg_sq, step, count, lr, beta1, beta2, eps));
         GD_LAUNCH_CHECK();
     }
-    adam_bump_kernel<<<1, 1, 0, as_stream(stream)>>>(step);
+    GD_CUDA(launch_pdl(adam_bump_kernel, 1, 1, 0, as_stream(stream), step));
     GD_LAUNCH_CHECK();
     return GD_OK;
 }

@@ -222,6 +222,8 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) gemm_rows_tc_kernel(const Arg
                      "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    pdl_wait();                      // barrier init / TMEM allocation above overlap the predecessor's tail
+    pdl_trigger();
     // ---- stage B once (hi / lo, K-major SWIZZLE_128B), all threads; 4 chunks per thread in flight
     {
         const int total = kchunks * g.n * 8;
@@ -562,6 +564,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tn_tc_kernel(const TnArgs
                      "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    pdl_wait();
+    pdl_trigger();
     // rows k1..127 of the A^T tiles are never written by the producers: zero every A^T tile once
     for (int i = tid; i < STAGES * 2 * TILE_BYTES / 16; i += NUM_THREADS) {
         const int s = i / (2 * TILE_BYTES / 16), o = i - s * (2 * TILE_BYTES / 16);
@@ -776,7 +780,7 @@ extern "C" int gd_gemm_rows_tc(const float* a, int64_t lda, const int32_t* rows,
                      ((relu_mask_out || gate_bits) ? tc::EPI_BITS : 0) | (gate ? tc::EPI_GATE : 0);
     auto launch = [&](auto kern) -> int {
         GD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, tc::ROWS_THREADS, smem, stream>>>(g);
+        GD_CUDA(launch_pdl(kern, grid, tc::ROWS_THREADS, smem, stream, g));
         GD_LAUNCH_CHECK();
         return GD_OK;
     };
@@ -806,6 +810,8 @@ extern "C" int gd_gemm_rows_tc_batch(const float* a, int64_t lda, int64_t m, int
 __global__ void __launch_bounds__(256) tn_reduce_kernel(const float* __restrict__ partial, int nparts, int64_t count,
                                                         float* __restrict__ out) {
     __shared__ float red[8][32];
+    gd::pdl_wait();
+    gd::pdl_trigger();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t i = (int64_t)blockIdx.x * 32 + lane;
     float s = 0.f;
@@ -849,10 +855,10 @@ extern "C" int gd_gemm_tn_rows_tc(const float* a, int64_t lda, const float* g, i
                  tc::tn_stages(n2)};
     const size_t smem = 1024 + (size_t)t.stages * (2 * tc::TILE_BYTES + 2 * n2 * 128) + tc::EPI_BYTES;
     GD_CUDA(cudaFuncSetAttribute(tc::gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc::gemm_tn_tc_kernel<<<grid, tc::NUM_THREADS, smem, stream>>>(t);
+    GD_CUDA(launch_pdl(tc::gemm_tn_tc_kernel, grid, tc::NUM_THREADS, smem, stream, t));
     GD_LAUNCH_CHECK();
     const int64_t count = (int64_t)k1 * n2;
-    tn_reduce_kernel<<<(unsigned)ceil_div<int64_t>(count, 32), 256, 0, stream>>>(t.partial, grid, count, c);
+    GD_CUDA(launch_pdl(tn_reduce_kernel, (unsigned)ceil_div<int64_t>(count, 32), 256, 0, stream, (const float*)t.partial, grid, count, c));
     GD_LAUNCH_CHECK();
     return GD_OK;
 }

@@ -35,6 +35,8 @@ __device__ __forceinline__ float pair_dot(const float* z, int64_t ldz, int u, in
 // step costs one memory latency instead of two.
 template <int LANES>
 __global__ void __launch_bounds__(256) edge_loss_fwd_kernel(const EdgeLossArgs a) {
+    pdl_wait();
+    pdl_trigger();
     constexpr int PER_WARP = 32 / LANES;
     const int lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5;
     const int sub = lane / LANES, sl = lane % LANES;
@@ -195,6 +197,8 @@ __global__ void __launch_bounds__(1024) edge_loss_finalize_kernel(const float* _
                                                                  float inv_ndf, float inv_nni, float alpha,
                                                                  float* __restrict__ losses) {
     __shared__ float sr[32], sl_[32];
+    pdl_wait();
+    pdl_trigger();
     float r = 0.f, l = 0.f;
     for (int i = threadIdx.x; i < nparts; i += blockDim.x) { r += partial[2 * i]; l += partial[2 * i + 1]; }
     r = warp_sum(r); l = warp_sum(l);
@@ -286,12 +290,12 @@ extern "C" int gd_edge_loss_fwd_part(const float* z, int64_t ldz, int32_t dim, c
     const bool vec = (ldz % 4 == 0) && ((uintptr_t)z % 16 == 0);
     int grid;
     const int64_t steps = (n_df + 1) / 2 + (n_ni + 3) / 4;
-    if (vec && dim == 64) { grid = edge_loss_grid(steps, 2); edge_loss_fwd_kernel<16><<<grid, 256, 0, stream>>>(a); }
-    else if (vec && dim == 128) { grid = edge_loss_grid(steps, 1); edge_loss_fwd_kernel<32><<<grid, 256, 0, stream>>>(a); }
-    else if (vec && dim == 32) { grid = edge_loss_grid(steps, 4); edge_loss_fwd_kernel<8><<<grid, 256, 0, stream>>>(a); }
+    if (vec && dim == 64) { grid = edge_loss_grid(steps, 2); GD_CUDA(launch_pdl(edge_loss_fwd_kernel<16>, grid, 256, 0, stream, a)); }
+    else if (vec && dim == 128) { grid = edge_loss_grid(steps, 1); GD_CUDA(launch_pdl(edge_loss_fwd_kernel<32>, grid, 256, 0, stream, a)); }
+    else if (vec && dim == 32) { grid = edge_loss_grid(steps, 4); GD_CUDA(launch_pdl(edge_loss_fwd_kernel<8>, grid, 256, 0, stream, a)); }
     else { grid = edge_loss_grid(items, 1); edge_loss_fwd_generic_kernel<<<grid, 256, 0, stream>>>(a); }
     GD_LAUNCH_CHECK();
-    edge_loss_finalize_kernel<<<1, 1024, 0, stream>>>(a.partial, grid, inv_ndf, inv_nni, alpha, losses);
+    GD_CUDA(launch_pdl(edge_loss_finalize_kernel, 1, 1024, 0, stream, (const float*)a.partial, (int)grid, inv_ndf, inv_nni, alpha, losses));
     GD_LAUNCH_CHECK();
     return GD_OK;
 }

@@ -97,6 +97,8 @@ __global__ void __launch_bounds__(256, 4) spmm_batched_kernel(const BArgs a) {
     const int sub = lane / LANES, sl = lane % LANES;
     const unsigned mask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (sub * LANES));
     const int64_t worker = ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5) * PER_WARP + sub;
+    pdl_wait();
+    pdl_trigger();
     const int64_t b0 = worker * a.per_worker;
     if (b0 >= a.num_batches) return;
     const int nb = (int)min((int64_t)a.per_worker, (int64_t)a.num_batches - b0);
@@ -219,10 +221,10 @@ static int launch_flags(const BArgs& a, unsigned blocks, cudaStream_t stream) {
     // the flush variants of the Del-training epoch are compiled without the unused tests: GCN forward
     // (scale + bias), transpose-backward / loss gather (nothing), loss gather + this step's negatives (tail);
     // everything else takes the generic variant
-    if (need == 0) spmm_batched_kernel<LANES, WEIGHTED, 0><<<blocks, 256, 0, stream>>>(a);
-    else if (need == (FLUSH_SCALE | FLUSH_BIAS)) spmm_batched_kernel<LANES, WEIGHTED, FLUSH_SCALE | FLUSH_BIAS><<<blocks, 256, 0, stream>>>(a);
-    else if (need == FLUSH_TAIL) spmm_batched_kernel<LANES, WEIGHTED, FLUSH_TAIL><<<blocks, 256, 0, stream>>>(a);
-    else spmm_batched_kernel<LANES, WEIGHTED, FLUSH_ANY><<<blocks, 256, 0, stream>>>(a);
+    if (need == 0) GD_CUDA(launch_pdl(spmm_batched_kernel<LANES, WEIGHTED, 0>, blocks, 256, 0, stream, a));
+    else if (need == (FLUSH_SCALE | FLUSH_BIAS)) GD_CUDA(launch_pdl(spmm_batched_kernel<LANES, WEIGHTED, FLUSH_SCALE | FLUSH_BIAS>, blocks, 256, 0, stream, a));
+    else if (need == FLUSH_TAIL) GD_CUDA(launch_pdl(spmm_batched_kernel<LANES, WEIGHTED, FLUSH_TAIL>, blocks, 256, 0, stream, a));
+    else GD_CUDA(launch_pdl(spmm_batched_kernel<LANES, WEIGHTED, FLUSH_ANY>, blocks, 256, 0, stream, a));
     GD_LAUNCH_CHECK();
     return GD_OK;
 }
