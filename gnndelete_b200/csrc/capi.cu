@@ -12,7 +12,8 @@ int fail(int code, const std::string& msg) {
     return code;
 }
 bool pdl_enabled() {
-    static const bool on = [] { const char* e = getenv("GD_PDL"); return e && e[0] == '1';      // opt-in: measured SLOWER on the Collab epoch (917 vs 1090 epochs/s) }();
+    // opt-in: measured SLOWER on the Collab epoch (917 vs 1090 epochs/s)
+    static const bool on = [] { const char* e = getenv("GD_PDL"); return e && e[0] == '1'; }();
     return on;
 }
 }  // namespace gd
