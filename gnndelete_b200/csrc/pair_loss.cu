@@ -34,7 +34,7 @@ __device__ __forceinline__ float pair_dot(const float* z, int64_t ldz, int u, in
 // fetched while the rows of the current step are in flight (software pipeline across steps), so a
 // step costs one memory latency instead of two.
 template <int LANES>
-__global__ void __launch_bounds__(256) edge_loss_fwd_kernel(const EdgeLossArgs a) {
+__global__ void __launch_bounds__(256, 4) edge_loss_fwd_kernel(const EdgeLossArgs a) {
     pdl_wait();
     pdl_trigger();
     constexpr int PER_WARP = 32 / LANES;
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) pair_decode_kernel(const float* __restric
 
 static int edge_loss_grid(int64_t items, int per_warp) {
     int64_t blocks = ceil_div<int64_t>(items, 8 * per_warp);
-    return (int)std::max<int64_t>(1, std::min<int64_t>(blocks, kNumSMs * 8));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(blocks, kNumSMs * 4));     // 4 resident CTAs per SM (64 registers): one wave
 }
 
 }  // namespace gd
