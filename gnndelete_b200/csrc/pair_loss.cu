@@ -3,6 +3,8 @@
 // Gather-reduce, L2/HBM bound: each pair reads two (DEC items: four) 256 B rows of z.
 // The gradient w.r.t. z is NOT scattered with atomics: d loss / d logit is written to the
 // two incidence slots of each pair and dz is then one deterministic CSR gather (gd_spmm).
+#include <climits>
+
 #include "common.cuh"
 
 namespace gd {
@@ -41,10 +43,12 @@ __global__ void __launch_bounds__(256, 4) edge_loss_fwd_kernel(const EdgeLossArg
     const int lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5;
     const int sub = lane / LANES, sl = lane % LANES;
     const unsigned mask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (sub * LANES));
-    // steps: [0, S_dec) handle Df items 2s, 2s+1 (pairs i and n_df + i); [S_dec, S_dec + S_ni) handle 4 NI pairs each
-    const int64_t S_dec = (a.n_df + 1) / 2, S_ni = (a.n_ni + 3) / 4, S = S_dec + S_ni;
-    const int64_t G = (int64_t)gridDim.x * 8 * PER_WARP;
-    int64_t st = ((int64_t)blockIdx.x * 8 + warp_in_block) * PER_WARP + sub;
+    // steps: [0, S_dec) handle Df items 2s, 2s+1 (pairs i and n_df + i); [S_dec, S_dec + S_ni) handle 4 NI pairs each.
+    // 32-bit step / pair arithmetic (the host checks P < 2^31): the kernel is instruction bound (ncu: issue slots 68 % busy).
+    const int n_df = (int)a.n_df, n_ni = (int)a.n_ni, own_df = (int)a.own_df, own_ni = (int)a.own_ni;
+    const int S_dec = (n_df + 1) / 2, S_ni = (n_ni + 3) / 4, S = S_dec + S_ni;
+    const int G = (int)gridDim.x * 8 * PER_WARP;
+    int st = ((int)blockIdx.x * 8 + warp_in_block) * PER_WARP + sub;
     float sum_r = 0.f, sum_l = 0.f;
 
     // Pair slot q of a step is OWNED by one lane of the sub-warp (it loads the slot's indices and writes its
@@ -54,19 +58,19 @@ __global__ void __launch_bounds__(256, 4) edge_loss_fwd_kernel(const EdgeLossArg
     constexpr bool T16 = LANES == 16;
     const bool owner = T16 ? (sl & 3) == 0 : sl < 4;
     const int my_q = T16 ? sl >> 2 : sl;
-    auto pair_of = [&](int64_t s, int q) -> int64_t {
-        if (s >= S) return -1;
-        if (s < S_dec) { const int64_t i = 2 * s + (q & 1); return i < a.n_df ? ((q & 2) ? a.n_df + i : i) : -1; }
-        const int64_t j = 4 * (s - S_dec) + q;
-        return j < a.n_ni ? 2 * a.n_df + j : -1;
+    // pair index of this lane's slot at step s (-1: none)
+    auto my_pair = [&](int s) -> int {
+        if (!owner || s >= S) return -1;
+        if (s < S_dec) { const int i = 2 * s + (my_q & 1); return i < n_df ? ((my_q & 2) ? n_df + i : i) : -1; }
+        const int j = 4 * (s - S_dec) + my_q;
+        return j < n_ni ? 2 * n_df + j : -1;
     };
-    auto fetch = [&](int64_t s, int& u, int& v, int& pu_, int& pv_, float& tgt) {
+    auto fetch = [&](int p, bool ni, int& u, int& v, int& pu_, int& pv_, float& tgt) {
         u = -1; v = 0; pu_ = 0; pv_ = 0; tgt = 0.f;
-        const int64_t p = owner ? pair_of(s, my_q) : -1;
         if (p >= 0) {
             u = __ldg(a.pu + p); v = __ldg(a.pv + p);
             pu_ = __ldg(a.pos_u + p); pv_ = __ldg(a.pos_v + p);
-            if (s >= S_dec) tgt = __ldg(a.target + (p - 2 * a.n_df));
+            if (ni) tgt = __ldg(a.target + (p - 2 * n_df));
         }
     };
     unsigned long long zl = reinterpret_cast<unsigned long long>(a.z) + sl * 16;       // this lane's 16 bytes of every row
@@ -77,11 +81,13 @@ __global__ void __launch_bounds__(256, 4) edge_loss_fwd_kernel(const EdgeLossArg
         if (r >= 0) x = __ldg(reinterpret_cast<const float4*>(zl + (unsigned long long)(unsigned)r * pitch));
         return x;
     };
+    int p0 = my_pair(st);
     int u0, v0, pu0, pv0; float t0;
-    fetch(st, u0, v0, pu0, pv0, t0);
+    fetch(p0, st >= S_dec, u0, v0, pu0, pv0, t0);
     while (st < S) {
+        const int p1 = my_pair(st + G);
         int u1, v1, pu1, pv1; float t1;
-        fetch(st + G, u1, v1, pu1, pv1, t1);                       // prefetch the next step's indices
+        fetch(p1, st + G >= S_dec, u1, v1, pu1, pv1, t1);         // prefetch the next step's indices
         float4 ra[4], rb[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -112,23 +118,22 @@ __global__ void __launch_bounds__(256, 4) edge_loss_fwd_kernel(const EdgeLossArg
             mine = sl == 0 ? d[0] : (sl == 1 ? d[1] : (sl == 2 ? d[2] : d[3]));
             other = sl == 0 ? d[2] : (sl == 1 ? d[3] : (sl == 2 ? d[0] : d[1]));
         }
-        if (owner && u0 >= 0) {
-            const int64_t p = pair_of(st, my_q);
+        if (p0 >= 0) {
             float c;
             if (st < S_dec) {
                 const float r = (my_q < 2) ? mine - other : other - mine;      // pos - neg
                 c = (my_q < 2) ? a.c_r * r : -a.c_r * r;
-                if (my_q < 2 && 2 * st + (my_q & 1) < a.own_df) sum_r += r * r;
+                if (my_q < 2 && p0 < own_df) sum_r += r * r;
             } else {
                 const float r = mine - t0;
                 c = a.c_l * r;
-                if (4 * (st - S_dec) + my_q < a.own_ni) sum_l += r * r;
+                if (p0 - 2 * n_df < own_ni) sum_l += r * r;
             }
-            a.logits[p] = mine;
+            a.logits[p0] = mine;
             a.inc_val[pu0] = c;
             a.inc_val[pv0] = c;
         }
-        st += G; u0 = u1; v0 = v1; pu0 = pu1; pv0 = pv1; t0 = t1;
+        st += G; p0 = p1; u0 = u1; v0 = v1; pu0 = pu1; pv0 = pv1; t0 = t1;
     }
     // deterministic block reduction: lanes -> warp -> block (fixed order)
     sum_r = warp_sum(sum_r);
@@ -289,6 +294,7 @@ extern "C" int gd_edge_loss_fwd_part(const float* z, int64_t ldz, int32_t dim, c
     a.c_l = (1.0f - alpha) * 2.0f * inv_nni;
     const bool vec = (ldz % 4 == 0) && ((uintptr_t)z % 16 == 0);
     int grid;
+    GD_CHECK_ARG(2 * n_df + n_ni < (int64_t)INT32_MAX - 8, "more than 2^31 pairs");
     const int64_t steps = (n_df + 1) / 2 + (n_ni + 3) / 4;
     if (vec && dim == 64) { grid = edge_loss_grid(steps, 2); GD_CUDA(launch_pdl(edge_loss_fwd_kernel<16>, grid, 256, 0, stream, a)); }
     else if (vec && dim == 128) { grid = edge_loss_grid(steps, 1); GD_CUDA(launch_pdl(edge_loss_fwd_kernel<32>, grid, 256, 0, stream, a)); }

@@ -1,7 +1,6 @@
 #!/bin/bash
 {
-python -m pytest tests/test_gpu_gcn.py tests/test_gpu_engine.py tests/test_gpu_fullsize.py -x -q 2>&1 | tail -2
-python tools/spmm_bench.py
+python -m pytest tests/ -m gpu -x -q 2>&1 | tail -2
 python bench.py --no-cpu-baseline | python -c "
 import sys, json
 for l in sys.stdin:
