@@ -1,12 +1,8 @@
 #!/bin/bash
 {
-python -m pytest tests/ -m gpu -x -q 2>&1 | tail -2
-python bench.py --no-cpu-baseline | python -c "
-import sys, json
-for l in sys.stdin:
-    l=l.strip()
-    if l.startswith('{'):
-        d=json.loads(l); print('value',d['value'],'hoisted',d['value_hoisted'],'e2e',d['e2e']['value'],'sync',d['e2e']['value_step_synchronous']); print(d['roofline']['kernel_ms'], d['roofline']['other_kernels'])
-"
+python -m pytest tests/test_gpu_gcn.py tests/test_gpu_engine.py tests/test_gpu_fullsize.py -x -q 2>&1 | tail -1
+python tools/gemm_sweep.py 2>&1 | grep -E "tiles/CTA +(1|8|16) " | sed 's/tn128.*//'
+GD_TC_DEBUG=30 python tools/gemm_sweep.py 2>&1 | grep -E "tiles/CTA +(16) " | sed 's/tn128.*//'
+GD_TC_DEBUG=94 python tools/gemm_sweep.py 2>&1 | grep -E "tiles/CTA +(16) " | sed 's/tn128.*//'
 } > gpurun_out/check.log 2>&1
 cat gpurun_out/check.log
