@@ -53,6 +53,9 @@ SIGNATURES = {
     'gd_spmm_plan_build': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'gd_spmm': (C.c_int, [_csr_p, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _vp]),
     'gd_spmm_acc': (C.c_int, [_csr_p, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _i32, _vp]),
+    'gd_spmm_bplan_workspace_bytes': (_sz, [_i64]),
+    'gd_spmm_bplan_count': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _sz, _vp]),
+    'gd_spmm_bplan_fill': (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'gd_spmm_batched_workers': (_i32, [_i32, _i32]),
     'gd_spmm_batched': (C.c_int, [_bplan_p, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _i32, _vp]),
     'gd_spmm_batched_tail': (C.c_int, [_bplan_p, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _i32, _vp]),

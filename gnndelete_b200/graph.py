@@ -91,9 +91,54 @@ class BatchPlan:
     SLOTS = 8
     FLUSH, PIECE = -(1 << 31), 1 << 30
 
-    def __init__(self, rowptr, col, num_rows, nnz, num_workers):
+    def __init__(self, rowptr, col, num_rows, nnz, num_workers, native=None):
+        """``native``: build with the CUDA builder (``gd_spmm_bplan_count`` / ``_fill``; default on CUDA tensors) or with
+        the tensor-op builder below (the CPU-testable statement of the layout; both produce identical arrays)."""
+        self.num_rows = int(num_rows)
+        if native is None:
+            native = rowptr.is_cuda and self.num_rows > 0
+        if native:
+            self._build_native(rowptr, col, int(nnz), int(num_workers))
+        else:
+            self._build_torch(rowptr, col, int(nnz), int(num_workers))
+        self._finish()
+
+    def _build_native(self, rowptr, col, nnz, num_workers):
+        dev, n, S = rowptr.device, self.num_rows, self.SLOTS
+        lib = L.load()
+        ws_bytes = lib.gd_spmm_bplan_workspace_bytes(n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        sizes = torch.zeros(3, dtype=torch.int32, device=dev)
+        L.call('gd_spmm_bplan_count', L.ptr(rowptr, 'i32'), n, int(num_workers), L.ptr(sizes), L.ptr(ws), ws_bytes, L.stream())
+        nb, nsplit, npiece = sizes.tolist()
+        self.num_batches = nb
+        self.num_workers = max(1, min(int(num_workers), max(nb, 1)))
+        per = -(-nb // self.num_workers) if nb else 1
+        self.batches_per_worker = per
+        self.num_workers = -(-nb // per) if nb else 1
+        self.num_slots = (nb + 2) * S
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.desc = torch.empty(nb + 2, **i32)
+        self.colp = torch.empty(self.num_slots, **i32)
+        self.slot_of_entry = torch.empty(max(nnz, 1), dtype=torch.int64, device=dev)
+        self.num_split, self.num_piece = nsplit, npiece
+        if nsplit:
+            self.piece_split = torch.empty(npiece, **i32)
+            self.split_row = torch.empty(nsplit, **i32)
+            self.split_piece_beg = torch.empty(nsplit, **i32)
+            self.split_npiece = torch.empty(nsplit, **i32)
+            self.split_ticket = torch.zeros(nsplit, **i32)
+        else:
+            self.piece_split = self.split_row = self.split_npiece = self.split_piece_beg = self.split_ticket = None
+        L.call('gd_spmm_bplan_fill', L.ptr(rowptr, 'i32'), L.ptr(col, 'i32'), n, nb, per, L.ptr(self.desc), L.ptr(self.colp),
+               L.ptr(self.slot_of_entry), L.ptr(self.piece_split), L.ptr(self.split_row), L.ptr(self.split_piece_beg),
+               L.ptr(self.split_npiece), L.ptr(ws), L.stream())
+        self.slot_of_entry = self.slot_of_entry[:nnz]
+        torch.cuda.current_stream().synchronize()        # `ws` is released below
+
+    def _build_torch(self, rowptr, col, nnz, num_workers):
         dev = rowptr.device
-        n, S = int(num_rows), self.SLOTS
+        n, S = self.num_rows, self.SLOTS
         rp = rowptr.long()
         deg = rp[1:] - rp[:-1]
         nbr = torch.clamp((deg + S - 1) // S, min=1)            # an empty row is one all-padding batch
@@ -150,6 +195,8 @@ class BatchPlan:
             self.split_ticket = torch.zeros(self.num_split, **i32)
         else:
             self.piece_split = self.split_row = self.split_npiece = self.split_piece_beg = self.split_ticket = None
+    def _finish(self):
+        n, nb, per = self.num_rows, self.num_batches, self.batches_per_worker
         self._scratch = {}
         self._cs = {}
         s = L.BplanStruct()

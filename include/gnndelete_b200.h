@@ -154,6 +154,19 @@ typedef struct gd_spmm_bplan {
     int32_t* split_ticket;           /* [num_split] zero-initialised; self re-arming */
 } gd_spmm_bplan_t;
 
+/* Native plan builder (gnndelete_b200/csrc/bplan_build.cu).  gd_spmm_bplan_count writes {num_batches, num_split,
+ * num_piece} to `sizes` (device int32[3]) and leaves its per-row scans in `workspace`; the caller reads the sizes,
+ * allocates desc [num_batches + 2], colp [(num_batches + 2) * 8], slot_of_entry [nnz] (padded slot of every CSR
+ * entry), piece_split [num_piece], split_* [num_split] and calls gd_spmm_bplan_fill with the SAME workspace and
+ * batches_per_worker = ceil(num_batches / min(num_workers, num_batches)). */
+size_t gd_spmm_bplan_workspace_bytes(int64_t num_rows);
+int gd_spmm_bplan_count(const int32_t* rowptr, int64_t num_rows, int32_t num_workers, int32_t* sizes,
+                        void* workspace, size_t workspace_bytes, gd_stream_t stream);
+int gd_spmm_bplan_fill(const int32_t* rowptr, const int32_t* col, int64_t num_rows, int32_t num_batches,
+                       int32_t batches_per_worker, int32_t* desc, int32_t* colp, int64_t* slot_of_entry,
+                       int32_t* piece_split, int32_t* split_row, int32_t* split_piece_beg, int32_t* split_npiece,
+                       const void* workspace, gd_stream_t stream);
+
 /* Number of workers (sub-warps of feat/4 lanes) the device keeps resident for the batched kernel:
  * the plan is balanced for exactly this many.  feat in {32, 64, 128}; 0 otherwise. */
 int32_t gd_spmm_batched_workers(int32_t feat, int32_t weighted);

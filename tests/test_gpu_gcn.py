@@ -68,6 +68,27 @@ def test_spmm_matches_dense(lib, case, feat):
     U.assert_close(out2, ref2, what=f'spmm unweighted F={feat}')
 
 
+@pytest.mark.parametrize('workers', [1, 7, 1000, 9472, 10 ** 6])
+def test_batch_plan_native_builder_bit_exact(lib, case, workers):
+    """The CUDA plan builder and the tensor-op builder (whose walk tests/test_batch_plan.py checks on the CPU)
+    produce identical arrays, for worker counts from 1 to more than there are batches."""
+    from gnndelete_b200.graph import BatchPlan, build_csr
+    shape, raw, df, data, neg = case
+    n = data.num_nodes
+    ei = data.train_pos_edge_index
+    ei = ei[:, ei[1] % 5 != 0]                       # empty rows
+    csr = build_csr(ei[0].to(DEV), ei[1].to(DEV), n, self_loops=False)
+    a = BatchPlan(csr.rowptr, csr.col, n, csr.nnz, workers, native=True)
+    b = BatchPlan(csr.rowptr, csr.col, n, csr.nnz, workers, native=False)
+    for k in ('num_batches', 'num_workers', 'batches_per_worker', 'num_slots', 'num_split', 'num_piece'):
+        assert getattr(a, k) == getattr(b, k), k
+    for k in ('desc', 'colp', 'slot_of_entry', 'piece_split', 'split_row', 'split_piece_beg', 'split_npiece'):
+        x, y = getattr(a, k), getattr(b, k)
+        assert (x is None) == (y is None), k
+        if x is not None:
+            assert torch.equal(x.long(), y.long()), k
+
+
 @pytest.mark.parametrize('feat', [128, 64, 32])
 @pytest.mark.parametrize('workers', [7, 1000, 0])
 def test_spmm_batched_matches_dense(lib, case, feat, workers):
