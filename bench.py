@@ -226,12 +226,19 @@ def run_reference(args, shape):
     epoch, cores = cpu_epoch_runner(shape)
     for _ in range(max(1, min(args.warmup, 2))):
         epoch()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    # every step is one FULL epoch of the workload (about a second on 16 cores); the run is bounded in time instead:
+    # a driver-supplied --steps sized for the GPU arm stops after --cpu-budget-s seconds and reports the steps it timed
+    done, t0 = 0, time.perf_counter()
+    while done < args.steps:
         epoch()
+        done += 1
+        if time.perf_counter() - t0 > args.cpu_budget_s:
+            break
     dt = time.perf_counter() - t0
+    requested, args.steps = args.steps, done
     value = args.steps / dt
-    sample = f'{args.steps} full epochs of the {shape.name} workload (whole graph, no sub-sampling)'
+    sample = (f'{args.steps} full epochs of the {shape.name} workload (whole graph, no sub-sampling)' +
+              (f'; {requested} requested, stopped at the {args.cpu_budget_s:.0f} s CPU budget' if done < requested else ''))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
@@ -330,6 +337,7 @@ def main():
     ap.add_argument('--scale', type=float, default=1.0)
     ap.add_argument('--cpu-epochs', type=int, default=4, help='bounded CPU-baseline sample (epochs)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-budget-s', type=float, default=150.0, help='time cap of the --impl reference loop')
     args = ap.parse_args()
     from gnndelete_b200 import synthetic as S
     shape = S.SHAPES[args.workload].scaled(args.scale)

@@ -9,11 +9,12 @@ registered; asking for one raises ``NotImplementedError``.
 from .models import GCN, GAT, GIN, RGCN, GCNDelete, GATDelete, GINDelete, RGCNDelete
 from .trainer.base import Trainer
 from .trainer.gnndelete import GNNDeleteTrainer
-from .trainer.gnndelete_nodeemb import KGGNNDeleteNodeembTrainer
+from .trainer.gnndelete_nodeemb import GNNDeleteNodeembTrainer, KGGNNDeleteNodeembTrainer
 
 trainer_mapping = {
     'gnndelete': GNNDeleteTrainer,
     'gnndelete_mse': GNNDeleteTrainer,
+    'gnndelete_nodeemb': GNNDeleteNodeembTrainer,
 }
 
 kg_trainer_mapping = {

@@ -1,1 +1,3 @@
-from gnndelete_b200.trainer import KGGNNDeleteNodeembTrainer  # noqa: F401  (reference: framework/trainer/gnndelete_nodeemb.py)
+# reference: framework/trainer/gnndelete_nodeemb.py
+from gnndelete_b200.trainer import GNNDeleteNodeembTrainer, KGGNNDeleteNodeembTrainer  # noqa: F401
+from gnndelete_b200.trainer import get_nodeemb_loss_fct as get_loss_fct  # noqa: F401

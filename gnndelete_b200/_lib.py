@@ -87,6 +87,8 @@ SIGNATURES = {
                                         _i64, _i64, _vp, _sz, _vp]),
     'gd_dense_ni_workspace_bytes': (_sz, [_i64]),
     'gd_dense_ni_fwd_bwd': (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i64, _vp, _f32, _vp, _i64, _vp, _vp, _sz, _vp]),
+    'gd_row_mse_workspace_bytes': (_sz, [_i64]),
+    'gd_row_mse_fwd_bwd': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i64, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _i64, _vp, _vp, _sz, _vp]),
     'gd_add_rows': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     'gd_pair_decode': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     'gd_adam_step': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp]),

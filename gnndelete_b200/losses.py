@@ -282,3 +282,105 @@ class DenseNIPlan:
         L.call('gd_add_rows', L.ptr(self.dzs), self.dzs.stride(0), L.ptr(self.S32), self.n_s, self.dim, L.ptr(dz),
                dz.stride(0), L.stream())
         return self.loss_sum / self.num_pairs
+
+
+def row_mse_incidence(dst_r, src_r, rows_l, num_rows):
+    """Destination-major incidence of the two node-embedding MSE terms (``gd_row_mse_fwd_bwd``).
+
+    Term 0 (``loss_r``): row ``dst_r[i]`` of ``z`` is compared with row ``src_r[i]`` of ``z_ori``;
+    term 1 (``loss_l``): row ``rows_l[j]`` with the same row of ``z_ori``.  Returns int32
+    ``(rowptr[num_rows + 1], code[nnz])`` with ``code = src`` for term 0 and ``-1 - row`` for term 1;
+    within a row the entries keep their input order, term 0 first (stable sort), which fixes the
+    summation order.  Plain tensor ops: runs on whatever device the index tensors live on (setup time)."""
+    dst_r, src_r, rows_l = dst_r.reshape(-1).long(), src_r.reshape(-1).long(), rows_l.reshape(-1).long()
+    if dst_r.numel() != src_r.numel():
+        raise ValueError('loss_r compares equally long row lists (gnndelete_nodeemb.py:200-204)')
+    n = int(num_rows)
+    for name, t in (('dst_r', dst_r), ('src_r', src_r), ('rows_l', rows_l)):
+        if t.numel() and (int(t.min()) < 0 or int(t.max()) >= n):
+            raise IndexError(f'{name} holds row ids outside [0, {n})')
+    dst = torch.cat([dst_r, rows_l])
+    code = torch.cat([src_r, -1 - rows_l])
+    order = torch.argsort(dst, stable=True)
+    counts = torch.bincount(dst, minlength=n)
+    rowptr = torch.zeros(n + 1, dtype=torch.int64, device=dst.device)
+    torch.cumsum(counts, 0, out=rowptr[1:])
+    return rowptr.to(torch.int32).contiguous(), code[order].to(torch.int32).contiguous()
+
+
+class RowMSEPlan:
+    """One layer's node-embedding losses against the frozen original embeddings ``z_ori``
+    (gnndelete_nodeemb.py:196-212; KG step :770-781):
+
+        loss_r = loss_fct(cat(z[pos[0]], z[pos[1]]), cat(z_ori[neg[0]], z_ori[neg[1]]))
+        loss_l = loss_fct(z[node_mask], z_ori[node_mask])
+
+    with ``loss_fct`` = ``nn.MSELoss(reduction)``.  ``mix = (a_r, a_l)`` are the weights of the objective
+    that carries gradient (``alpha, 1 - alpha`` for the layer-wise types, ``alpha, 1`` for ``only*``).
+    ``pos`` / ``neg`` / ``node_mask`` are fixed for the run (the reference samples ``neg_edge`` once,
+    :186-189), so the incidence is built once; :meth:`set_pairs` rebuilds it for resampled negatives."""
+
+    def __init__(self, pos, neg, node_mask, z_ori, mix=(0.5, 0.5), reduction='mean'):
+        if reduction not in ('mean', 'sum'):
+            raise NotImplementedError(reduction)
+        self.z_ori = z_ori.detach().contiguous()
+        if self.z_ori.dtype != torch.float32:
+            raise RuntimeError('gnndelete_b200 kernels compute in fp32')
+        self.n, self.dim = self.z_ori.shape
+        self.reduction = reduction
+        self.mix = (float(mix[0]), float(mix[1]))
+        dev = self.z_ori.device
+        self.rows_l = node_mask.nonzero().squeeze(1) if node_mask.dtype == torch.bool else node_mask.reshape(-1).long()
+        self.losses = torch.zeros(3, dtype=torch.float32, device=dev)
+        self.ws_bytes = L.load().gd_row_mse_workspace_bytes(self.n)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.set_pairs(pos, neg)
+
+    def set_pairs(self, pos, neg):
+        dev = self.z_ori.device
+        dst_r = torch.cat([pos[0], pos[1]]).to(dev)
+        src_r = torch.cat([neg[0], neg[1]]).to(dev)
+        self.m_r, self.m_l = dst_r.numel(), self.rows_l.numel()
+        self.rowptr, self.code = row_mse_incidence(dst_r, src_r, self.rows_l.to(dev), self.n)
+        if self.code.numel() == 0:
+            self.code = torch.zeros(1, dtype=torch.int32, device=dev)
+        nan = float('nan')                           # MSELoss('mean') of an empty selection is nan in the reference too
+        if self.reduction == 'mean':
+            self.w = (1.0 / (self.m_r * self.dim) if self.m_r else nan, 1.0 / (self.m_l * self.dim) if self.m_l else nan)
+        else:
+            self.w = (1.0, 1.0)
+
+    def forward_backward(self, z, dz=None, want_grad=True):
+        """Fills ``self.losses`` = (a_r loss_r + a_l loss_l, loss_r, loss_l) and, unless ``want_grad`` is off,
+        ``dz`` = d losses[0] / d z (every row written).  No host sync."""
+        if z.shape != (self.n, self.dim):
+            raise ValueError(f'expected embeddings of shape {(self.n, self.dim)}, got {tuple(z.shape)}')
+        if want_grad and dz is None:
+            dz = torch.empty(self.n, self.dim, dtype=torch.float32, device=z.device)
+        L.call('gd_row_mse_fwd_bwd', L.ptr(z, 'f32'), z.stride(0), L.ptr(self.z_ori), self.z_ori.stride(0), self.dim, self.n,
+               L.ptr(self.rowptr), L.ptr(self.code), self.w[0], self.w[1], self.mix[0], self.mix[1],
+               L.ptr(dz) if want_grad else None, dz.stride(0) if want_grad else 0, L.ptr(self.losses),
+               L.ptr(self.ws), self.ws_bytes, L.stream())
+        return self.losses, dz
+
+
+class RowMSEFn(torch.autograd.Function):
+    """(a_r loss_r + a_l loss_l, loss_r, loss_l) of one layer as one differentiable op; only the first carries
+    gradient.  Forward and gradient come out of the same kernel pass, so ``backward`` is a scale — it may be
+    called repeatedly (``retain_graph=True`` in the layer-wise schedule, gnndelete_nodeemb.py:224-232)."""
+
+    @staticmethod
+    def forward(ctx, z, plan):
+        z = z.contiguous()
+        losses, dz = plan.forward_backward(z, want_grad=ctx.needs_input_grad[0])
+        ctx.dz = dz
+        return losses.clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        return ctx.dz * gout[0], None
+
+
+def row_mse(z, plan):
+    out = RowMSEFn.apply(z, plan)
+    return out[0], out[1].detach(), out[2].detach()

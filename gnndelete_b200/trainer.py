@@ -348,13 +348,13 @@ class KGGNNDeleteNodeembTrainer(Trainer):
 
     def train(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
         from .kg import negative_sampling_kg
+        from .losses import RowMSEPlan, row_mse
         if not isinstance(optimizer, (list, tuple)) or len(optimizer) != 2:
             raise ValueError('expects the [optimizer1, optimizer2] pair built for *layerwise loss types '
                              '(delete_gnn.py:221-226)')
         dev = torch.device('cuda')
         model = model.to(dev)
         data = data.to(dev)
-        F = torch.nn.functional
         alpha = args.alpha
         non_df = torch.ones(data.x.shape[0], dtype=torch.bool, device=dev)          # :723-727
         non_df[data.directed_df_edge_index.flatten().unique()] = False
@@ -371,32 +371,216 @@ class KGGNNDeleteNodeembTrainer(Trainer):
             z1o, z2o = model.get_original_embeddings(data.x, edge_index, edge_type, return_all_emb=True)
         gen = torch.Generator(device=dev).manual_seed(getattr(args, 'random_seed', 42))
         fixed_neg = getattr(data, 'neg_edge_index', None)
+        # per layer, the four row gathers + two MSEs + their scatter gradients (:770-781) are one kernel pass
+        neg = fixed_neg if fixed_neg is not None else negative_sampling_kg(dec_ei, dec_et, gen)
+        plan1 = RowMSEPlan(dec_ei, neg, m1, z1o, mix=(alpha, 1 - alpha))
+        plan2 = RowMSEPlan(dec_ei, neg, m2, z2o, mix=(alpha, 1 - alpha))
         ring = []
         for epoch in range(args.epochs):
             model.train()
             z1, z2 = model(data.x, edge_index, edge_type, m1, m2, return_all_emb=True)
-            neg = fixed_neg if fixed_neg is not None else negative_sampling_kg(dec_ei, dec_et, gen)
-            e1 = torch.cat([z1[dec_ei[0]], z1[dec_ei[1]]], 0)                        # :770-774
-            e1o = torch.cat([z1o[neg[0]], z1o[neg[1]]], 0)
-            e2 = torch.cat([z2[dec_ei[0]], z2[dec_ei[1]]], 0)
-            e2o = torch.cat([z2o[neg[0]], z2o[neg[1]]], 0)
-            loss_r1, loss_r2 = F.mse_loss(e1, e1o), F.mse_loss(e2, e2o)
-            loss_l1, loss_l2 = F.mse_loss(z1[m1], z1o[m1]), F.mse_loss(z2[m2], z2o[m2])
-            loss1 = alpha * loss_r1 + (1 - alpha) * loss_l1                          # :788-796
+            if fixed_neg is None and epoch > 0:                                      # :764-768, new heads every step
+                neg = negative_sampling_kg(dec_ei, dec_et, gen)
+                plan1.set_pairs(dec_ei, neg)
+                plan2.set_pairs(dec_ei, neg)
+            loss1, loss_r1, loss_l1 = row_mse(z1, plan1)                             # :788-796
+            loss2, loss_r2, loss_l2 = row_mse(z2, plan2)
             loss1.backward(retain_graph=True)
             optimizer[0].step()
             optimizer[0].zero_grad()
-            loss2 = alpha * loss_r2 + (1 - alpha) * loss_l2
             loss2.backward(retain_graph=True)
             optimizer[1].step()
             optimizer[1].zero_grad()
-            ring.append(torch.stack([(loss1 + loss2).detach(), (loss_r1 + loss_r2).detach(),
-                                     (loss_l1 + loss_l2).detach()]))
+            ring.append(torch.stack([(loss1 + loss2).detach(), loss_r1 + loss_r2, loss_l1 + loss_l2]))
             if (epoch + 1) % self.log_every == 0 or epoch + 1 == args.epochs:
                 for i, v in enumerate(torch.stack(ring).cpu().tolist()):
                     self.trainer_log['log'].append({'Epoch': epoch + 1 - len(ring) + i, 'train_loss': v[0],
                                                     'loss_r': v[1], 'loss_l': v[2]})
                 ring = []
         torch.save({'model_state': {k: v.to('cpu') for k, v in model.state_dict().items()}},
+                   os.path.join(args.checkpoint_dir, 'model_final.pt'))
+        return model
+
+
+# ---- node-embedding loss functions of gnndelete_nodeemb.py:19-92 (the non-MSE members run as device tensor ops
+# ---- under autograd; the two MSE members go through the fused gd_row_mse_fwd_bwd kernel instead)
+def _bounded_kld(reduction):
+    def fct(logits, truth):
+        kld = torch.nn.functional.kl_div(torch.log_softmax(logits, -1), torch.softmax(truth, -1), reduction=reduction)
+        return 1 - torch.exp(-kld)
+    return fct
+
+
+def _cosine_distance(reduce):
+    def fct(logits, truth):
+        d = 1 - torch.nn.functional.cosine_similarity(logits, truth)
+        return d.mean() if reduce == 'mean' else d.sum()
+    return fct
+
+
+def _centered(k):
+    # H K H with H = I - 11^T / n, without forming H
+    return k - k.mean(0, keepdim=True) - k.mean(1, keepdim=True) + k.mean()
+
+
+def _gram_linear(x):
+    return x @ x.t()
+
+
+def _gram_rbf(x, sigma=None):
+    g = x @ x.t()
+    d = torch.diag(g)
+    k = d.unsqueeze(0) + d.unsqueeze(1) - 2 * g
+    if sigma is None:
+        sigma = torch.sqrt(torch.median(k[k != 0]).detach())      # the reference takes math.sqrt of it: a constant
+    return torch.exp(-0.5 * k / (sigma * sigma))
+
+
+def _cka(gram):
+    def hsic(a, b):
+        return (_centered(gram(a)) * _centered(gram(b))).sum()
+
+    def fct(x, y):
+        return hsic(x, y) / (torch.sqrt(hsic(x, x)) * torch.sqrt(hsic(y, y)))
+    return fct
+
+
+def get_nodeemb_loss_fct(name):
+    """``gnndelete_nodeemb.py:69-92``.  Returns ``('mse', reduction)`` for the members the fused kernel covers,
+    else a callable ``(logits, truth) -> scalar`` (``rbf_cka`` raises ``NameError`` in the reference - ``math`` is
+    never imported, SURVEY.md §10 #13 - and is implemented as written otherwise)."""
+    if name in ('mse_mean', 'mse_sum'):
+        return ('mse', name[4:])
+    table = {
+        'kld_mean': _bounded_kld('batchmean'), 'kld_sum': _bounded_kld('sum'),
+        'cosine_mean': _cosine_distance('mean'), 'cosine_sum': _cosine_distance('sum'),
+        'linear_cka': _cka(_gram_linear), 'rbf_cka': _cka(_gram_rbf),
+    }
+    if name not in table:
+        raise NotImplementedError(name)
+    return table[name]
+
+
+class GNNDeleteNodeembTrainer(Trainer):
+    """``framework/trainer/gnndelete_nodeemb.py:94-349`` (``GNNDeleteNodeembTrainer``): the layer-wise
+    Deleted-Edge-Consistency / Neighbourhood-Influence objective on NODE EMBEDDINGS, the route
+    ``--unlearning_model gnndelete_nodeemb`` takes and the default ``loss_type`` of ``training_args.py:63-66``.
+
+    Per epoch (:191-299): ``z1, z2 = model(x, ei[:, sdf_mask], return_all_emb=True)`` with the stored masks;
+    ``loss_r{l} = fct(cat(z{l}[Df heads], z{l}[Df tails]), cat(z{l}_ori[neg heads], z{l}_ori[neg tails]))``;
+    ``loss_l{l} = fct(z{l}[S{l} minus Df nodes], z{l}_ori[same rows])``; then the backward / optimizer schedule of
+    ``args.loss_type`` reproduced literally (``both_all`` never clears gradients; the ``*layerwise`` types take
+    the ``[optimizer1, optimizer2]`` pair of delete_gnn.py:221-226).  With ``loss_fct`` ``mse_mean`` / ``mse_sum``
+    the four gathers + MSEs + their scatter gradients of a layer are ONE kernel pass (``losses.RowMSEPlan``).
+    The reference's 'ogbl' mini-batch variant (:352-520, GraphSAINT sampling) is replaced by the same whole-graph
+    step, as in ``GNNDeleteTrainer``.  Negatives are drawn once before the loop (:186-189); a caller that needs
+    parity supplies ``data.neg_edge_index``."""
+
+    log_every = 100
+
+    def train(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
+        return self.train_fullbatch(model, data, optimizer, args, logits_ori, attack_model_all, attack_model_sub)
+
+    def train_fullbatch(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
+        from .losses import RowMSEPlan, row_mse
+        loss_type = self.args.loss_type
+        if loss_type not in ('both_all', 'both_layerwise', 'only2_layerwise', 'only2_all', 'only1'):
+            raise NotImplementedError(loss_type)
+        layerwise = 'layerwise' in loss_type
+        if layerwise != isinstance(optimizer, (list, tuple)) or (layerwise and len(optimizer) != 2):
+            raise ValueError("'*layerwise' loss types take the [optimizer1, optimizer2] pair, the others one optimizer "
+                             '(delete_gnn.py:221-226)')
+        fct = get_nodeemb_loss_fct(self.args.loss_fct)
+        alpha = self.args.alpha
+        dev = torch.device('cuda')
+        model = model.to(dev)
+        data = data.to(dev)
+        ei = data.train_pos_edge_index
+        non_df = torch.ones(data.x.shape[0], dtype=torch.bool, device=dev)             # :171-175
+        non_df[data.directed_df_edge_index.flatten().unique()] = False
+        m1 = data.sdf_node_1hop_mask & non_df
+        m2 = data.sdf_node_2hop_mask & non_df
+        data.sdf_node_1hop_mask_non_df_mask, data.sdf_node_2hop_mask_non_df_mask = m1, m2
+        with torch.no_grad():                                                           # :179-180
+            z1_ori, z2_ori = model.get_original_embeddings(data.x, ei[:, data.dr_mask].contiguous(), return_all_emb=True)
+        pos_edge = ei[:, data.df_mask]                                                  # :200
+        neg_edge = getattr(data, 'neg_edge_index', None)                                # :186-189
+        if neg_edge is None:
+            gen = torch.Generator(device=dev).manual_seed(getattr(args, 'random_seed', 42))
+            neg_edge = torch.randint(0, data.num_nodes, (2, pos_edge.shape[1]), generator=gen, device=dev)
+        ei_sdf = ei[:, data.sdf_mask].contiguous()
+        # weights of (loss_r, loss_l) in the objective that is differentiated, per layer
+        mix = (alpha, 1.0) if loss_type in ('only2_all', 'only1') else (alpha, 1 - alpha)
+        if isinstance(fct, tuple):
+            plan1 = RowMSEPlan(pos_edge, neg_edge, m1, z1_ori, mix=mix, reduction=fct[1])
+            plan2 = RowMSEPlan(pos_edge, neg_edge, m2, z2_ori, mix=mix, reduction=fct[1])
+
+            def layer_losses(z, z_ori, mask, plan):
+                return row_mse(z, plan)
+        else:
+            plan1 = plan2 = None
+
+            def layer_losses(z, z_ori, mask, plan):
+                embed = torch.cat([z[pos_edge[0]], z[pos_edge[1]]], dim=0)             # :203-207
+                embed_ori = torch.cat([z_ori[neg_edge[0]], z_ori[neg_edge[1]]], dim=0)
+                loss_r = fct(embed, embed_ori)                                          # :209-210
+                loss_l = fct(z[mask], z_ori[mask])                                      # :213-214
+                return mix[0] * loss_r + mix[1] * loss_l, loss_r.detach(), loss_l.detach()
+
+        best_metric, ring, t0 = 0, [], time.time()
+        for epoch in range(args.epochs):
+            model.train()
+            z1, z2 = model(data.x, ei_sdf, return_all_emb=True)                         # :195
+            obj1, loss_r1, loss_l1 = layer_losses(z1, z1_ori, m1, plan1)
+            obj2, loss_r2, loss_l2 = layer_losses(z2, z2_ori, m2, plan2)
+            if loss_type == 'both_all':                                                 # :219-229 (no zero_grad)
+                loss_l, loss_r = loss_l1 + loss_l2, loss_r1 + loss_r2
+                loss = obj1 + obj2
+                loss.backward()
+                optimizer.step()
+            elif loss_type == 'both_layerwise':                                         # :231-246
+                loss_l, loss_r = loss_l1 + loss_l2, loss_r1 + loss_r2
+                obj1.backward(retain_graph=True)
+                optimizer[0].step()
+                optimizer[0].zero_grad()
+                obj2.backward(retain_graph=True)
+                optimizer[1].step()
+                optimizer[1].zero_grad()
+                loss = obj1 + obj2
+            elif loss_type == 'only2_layerwise':                                        # :264-279
+                loss_l, loss_r = loss_l1 + loss_l2, loss_r1 + loss_r2
+                optimizer[0].zero_grad()
+                obj2.backward()
+                optimizer[1].step()
+                optimizer[1].zero_grad()
+                loss = obj2
+            elif loss_type == 'only2_all':                                              # :281-289
+                loss_l, loss_r, loss = loss_l2, loss_r2, obj2
+                loss.backward()
+                optimizer.step()
+                optimizer.zero_grad()
+            else:                                                                       # 'only1', :291-299
+                loss_l, loss_r, loss = loss_l1, loss_r1, obj1
+                loss.backward()
+                optimizer.step()
+                optimizer.zero_grad()
+            ring.append(torch.stack([loss.detach(), loss_r, loss_l]))
+            del z1, z2, obj1, obj2, loss
+            last = epoch + 1 == args.epochs
+            if (epoch + 1) % self.log_every == 0 or last or (epoch + 1) % args.valid_freq == 0:
+                vals = torch.stack(ring).cpu()
+                dt = (time.time() - t0) / len(ring)
+                for i, v in enumerate(vals.tolist()):
+                    self.trainer_log['log'].append({'Epoch': epoch + 1 - len(ring) + i, 'train_loss': v[0],
+                                                    'loss_r': v[1], 'loss_l': v[2], 'train_time': dt})
+                ring, t0 = [], time.time()
+            if (epoch + 1) % args.valid_freq == 0:                                      # :310-338
+                valid_loss, dt_auc, dt_aup, df_auc, df_aup, _, _, valid_log = self.eval(model, data, 'val')
+                valid_log['epoch'] = epoch
+                self.trainer_log['log'].append(valid_log)
+                if dt_auc + df_auc > best_metric:
+                    best_metric = dt_auc + df_auc
+                    torch.save({'model_state': model.state_dict()}, os.path.join(args.checkpoint_dir, 'model_best.pt'))
+        torch.save({'model_state': {k: v.to('cpu') for k, v in model.state_dict().items()}},     # :341-346
                    os.path.join(args.checkpoint_dir, 'model_final.pt'))
         return model

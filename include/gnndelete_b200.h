@@ -350,6 +350,25 @@ int gd_dense_ni_fwd_bwd(const float* zs, int64_t ldz, int32_t dim, int64_t n_s, 
 int gd_add_rows(const float* src, int64_t lds, const int32_t* rows, int64_t m, int32_t feat, float* dst,
                 int64_t ldd, gd_stream_t stream);
 
+/* Node-embedding MSE terms of the layer-wise Del losses, forward + gradient in one pass
+ * (framework/trainer/gnndelete_nodeemb.py:196-212 `GNNDeleteNodeembTrainer.train_fullbatch`,
+ * :770-781 `KGGNNDeleteNodeembTrainer.train`):
+ *   term 0  loss_r = MSE(cat(z[h], z[t]), cat(z_ref[h'], z_ref[t']))   (Deleted Edge Consistency)
+ *   term 1  loss_l = MSE(z[rows], z_ref[rows])                          (Neighbourhood Influence)
+ * given as ONE destination-major incidence over the rows of z: `rowptr[n + 1]`, and per entry
+ * `code >= 0` -> term 0 against z_ref[code], `code < 0` -> term 1 against z_ref[-1 - code].
+ *   S_t       = sum over the entries of term t of |z[r] - z_ref[partner]|^2
+ *   losses[1] = w0 * S_0, losses[2] = w1 * S_1      (w_t = 1 / (M_t * dim) for 'mse_mean', 1 for 'mse_sum')
+ *   losses[0] = a0 * losses[1] + a1 * losses[2]     (the mixed objective, e.g. a0 = alpha, a1 = 1 - alpha)
+ *   dz[r, :]  = d losses[0] / d z[r, :]             (every row written, zeros where a row has no entry;
+ *                                                    dz NULL: forward only)
+ * Deterministic: no atomics, summation order fixed by the incidence and the launch shape. */
+size_t gd_row_mse_workspace_bytes(int64_t n);
+int gd_row_mse_fwd_bwd(const float* z, int64_t ldz, const float* z_ref, int64_t ldref, int32_t dim, int64_t n,
+                       const int32_t* rowptr, const int32_t* code, float w0, float w1, float a0, float a1,
+                       float* dz, int64_t lddz, float* losses, void* workspace, size_t workspace_bytes,
+                       gd_stream_t stream);
+
 /* logits[p] = sum_d z[u_p,d] * w[t_p,d] * z[v_p,d]  (w, t nullable => plain dot).
  * GCN.decode (gcn.py:26-35) / RGCN.decode DistMult (rgcn.py:40-47). */
 int gd_pair_decode(const float* z, int64_t ldz, int32_t dim, const int32_t* pair_u,

@@ -147,3 +147,111 @@ def kg_step_losses(model, data, neg_edge_index, num_edge_type, alpha=0.5):
     loss2 = alpha * loss_r2 + (1 - alpha) * loss_l2                         # :793
     return loss1, loss2, dict(loss_r1=loss_r1, loss_r2=loss_r2, loss_l1=loss_l1, loss_l2=loss_l2,
                               z1=z1, z2=z2, decoding_edge_index=dec_ei, decoding_edge_type=pos_et[dec])
+
+
+def _centering(K):
+    """``gnndelete_nodeemb.py:31-36``: H K H with the explicit centring matrix."""
+    n = K.shape[0]
+    H = torch.eye(n, dtype=K.dtype) - torch.ones(n, n, dtype=K.dtype) / n
+    return H @ K @ H
+
+
+def _rbf(X, sigma=None):
+    """``gnndelete_nodeemb.py:38-46`` (with the ``math`` import the reference forgot, SURVEY.md §10 #13)."""
+    import math
+    GX = X @ X.T
+    KX = torch.diag(GX) - GX + (torch.diag(GX) - GX).T
+    if sigma is None:
+        sigma = math.sqrt(torch.median(KX[KX != 0]).item())
+    return torch.exp(KX * (-0.5 / (sigma * sigma)))
+
+
+def _cka(gram):
+    """``gnndelete_nodeemb.py:48-66``: HSIC(X, Y) / sqrt(HSIC(X, X) HSIC(Y, Y))."""
+    def hsic(X, Y):
+        return torch.sum(_centering(gram(X)) * _centering(gram(Y)))
+    return lambda X, Y: hsic(X, Y) / (torch.sqrt(hsic(X, X)) * torch.sqrt(hsic(Y, Y)))
+
+
+def nodeemb_loss_fct(name):
+    """``gnndelete_nodeemb.py:19-29, 69-92`` (``get_loss_fct``)."""
+    if name == 'mse_mean':
+        return torch.nn.MSELoss(reduction='mean')
+    if name == 'mse_sum':
+        return torch.nn.MSELoss(reduction='sum')
+    if name in ('kld_mean', 'kld_sum'):
+        red = 'batchmean' if name == 'kld_mean' else 'sum'
+        return lambda logits, truth: 1 - torch.exp(-F.kl_div(F.log_softmax(logits, -1), truth.softmax(-1), reduction=red))
+    if name == 'cosine_mean':
+        return lambda logits, truth: (1 - F.cosine_similarity(logits, truth)).mean()
+    if name == 'cosine_sum':
+        return lambda logits, truth: (1 - F.cosine_similarity(logits, truth)).sum()
+    if name == 'linear_cka':
+        return _cka(lambda X: X @ X.T)
+    if name == 'rbf_cka':
+        return _cka(_rbf)
+    raise NotImplementedError(name)
+
+
+def nodeemb_epoch(model, data, neg_edge, z1_ori, z2_ori, optimizer, loss_type='both_layerwise', alpha=0.5,
+                  loss_fct='mse_mean'):
+    """One epoch of ``GNNDeleteNodeembTrainer.train_fullbatch``, ``gnndelete_nodeemb.py:191-299``, INCLUDING the
+    backward / optimizer schedule of the chosen ``loss_type`` (the branches differ in which gradients are
+    cleared: ``both_all`` never zeroes them, ``*_layerwise`` leave loss2's deletion1 gradient in ``.grad``).
+    ``optimizer`` is the ``[optimizer1, optimizer2]`` pair for ``*layerwise`` types (delete_gnn.py:221-226), one
+    Adam over both Del weights otherwise.  ``neg_edge`` is drawn once before the loop in the reference (:186-189)
+    and supplied here.  Returns (loss, loss_r, loss_l) as logged (:301-307)."""
+    fct = nodeemb_loss_fct(loss_fct)
+    non_df = torch.ones(data.x.shape[0], dtype=torch.bool)                  # :171-175
+    non_df[data.directed_df_edge_index.flatten().unique()] = False
+    m1 = data.sdf_node_1hop_mask & non_df
+    m2 = data.sdf_node_2hop_mask & non_df
+    z1, z2 = model(data.x, data.train_pos_edge_index[:, data.sdf_mask], return_all_emb=True)     # :195
+    pos_edge = data.train_pos_edge_index[:, data.df_mask]                   # :200
+    embed1 = torch.cat([z1[pos_edge[0]], z1[pos_edge[1]]], dim=0)           # :203-207
+    embed1_ori = torch.cat([z1_ori[neg_edge[0]], z1_ori[neg_edge[1]]], dim=0)
+    embed2 = torch.cat([z2[pos_edge[0]], z2[pos_edge[1]]], dim=0)
+    embed2_ori = torch.cat([z2_ori[neg_edge[0]], z2_ori[neg_edge[1]]], dim=0)
+    loss_r1 = fct(embed1, embed1_ori)                                       # :209-210
+    loss_r2 = fct(embed2, embed2_ori)
+    loss_l1 = fct(z1[m1], z1_ori[m1])                                       # :213-214
+    loss_l2 = fct(z2[m2], z2_ori[m2])
+    if loss_type == 'both_all':                                             # :219-229
+        loss_l, loss_r = loss_l1 + loss_l2, loss_r1 + loss_r2
+        loss = alpha * loss_r + (1 - alpha) * loss_l
+        loss.backward()
+        optimizer.step()
+    elif loss_type == 'both_layerwise':                                     # :231-246
+        loss_l, loss_r = loss_l1 + loss_l2, loss_r1 + loss_r2
+        loss1 = alpha * loss_r1 + (1 - alpha) * loss_l1
+        loss1.backward(retain_graph=True)
+        optimizer[0].step()
+        optimizer[0].zero_grad()
+        loss2 = alpha * loss_r2 + (1 - alpha) * loss_l2
+        loss2.backward(retain_graph=True)
+        optimizer[1].step()
+        optimizer[1].zero_grad()
+        loss = loss1 + loss2
+    elif loss_type == 'only2_layerwise':                                    # :264-279
+        loss_l, loss_r = loss_l1 + loss_l2, loss_r1 + loss_r2
+        optimizer[0].zero_grad()
+        loss2 = alpha * loss_r2 + (1 - alpha) * loss_l2
+        loss2.backward()
+        optimizer[1].step()
+        optimizer[1].zero_grad()
+        loss = loss2
+    elif loss_type == 'only2_all':                                          # :281-289
+        loss_l, loss_r = loss_l2, loss_r2
+        loss = loss_l + alpha * loss_r
+        loss.backward()
+        optimizer.step()
+        optimizer.zero_grad()
+    elif loss_type == 'only1':                                              # :291-299
+        loss_l, loss_r = loss_l1, loss_r1
+        loss = loss_l + alpha * loss_r
+        loss.backward()
+        optimizer.step()
+        optimizer.zero_grad()
+    else:
+        raise NotImplementedError(loss_type)
+    return loss.detach(), loss_r.detach(), loss_l.detach()
