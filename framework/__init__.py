@@ -2,16 +2,21 @@
 
 Same import paths and factory signatures as ``/root/reference/framework/__init__.py``
 (``get_model`` :51-59, ``get_trainer`` :62-67), backed by the B200 kernels in
-``gnndelete_b200``.  The reference's baselines (retrain, gradient ascent, Descent-to-
-Delete, GraphEraser, membership inference …) are out of scope and are not
-registered; asking for one raises ``NotImplementedError``.
+``gnndelete_b200``.  Registered: the GNNDelete trainers (edge-logit and node-embedding
+objectives, homogeneous and KG) plus the two loops that produce / re-produce the model they
+start from (``original``, ``retrain``).  The other baselines
+(gradient ascent, Descent-to-Delete, GraphEraser, membership inference …) are out of scope
+ and are not registered; asking for one raises ``NotImplementedError``.
 """
 from .models import GCN, GAT, GIN, RGCN, GCNDelete, GATDelete, GINDelete, RGCNDelete
 from .trainer.base import Trainer
+from .trainer.retrain import RetrainTrainer
 from .trainer.gnndelete import GNNDeleteTrainer
 from .trainer.gnndelete_nodeemb import GNNDeleteNodeembTrainer, KGGNNDeleteNodeembTrainer
 
 trainer_mapping = {
+    'original': Trainer,
+    'retrain': RetrainTrainer,
     'gnndelete': GNNDeleteTrainer,
     'gnndelete_mse': GNNDeleteTrainer,
     'gnndelete_nodeemb': GNNDeleteNodeembTrainer,

@@ -369,8 +369,10 @@ class RGCNConvFn(torch.autograd.Function):
 
 class GATAggregateFn(torch.autograd.Function):
     """out_i = sum_k softmax_i(LeakyReLU(a_src[k] + a_dst[i])) h_k + bias over the self-looped
-    CSR (GATConv heads=1).  Differentiable w.r.t. ``h`` only — on the Del path the attention
-    vectors and bias are frozen."""
+    CSR (GATConv heads=1).  On the Del path only ``h`` needs a gradient (attention vectors and bias are
+    frozen); when the original model is trained (``Trainer.train_fullbatch``,
+    base.py:75-142) the attention-vector gradients ``h^T d a_src`` / ``h^T d a_dst`` and the bias gradient
+    come from the per-node score gradients the backward kernels already produce."""
 
     @staticmethod
     def forward(ctx, h, att_src, att_dst, bias, plan, slope):
@@ -397,10 +399,8 @@ class GATAggregateFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         h, att_src, att_dst, a_src, a_dst, rowmax, rowden, out, b = ctx.saved_tensors
-        if any(ctx.needs_input_grad[1:4]):
-            raise NotImplementedError('gradients of the GAT attention vectors / bias are outside the Del hot path')
-        if not ctx.needs_input_grad[0]:
-            return (None,) * 6
+        if not any(ctx.needs_input_grad[:3]):
+            return None, None, None, (gout.sum(0) if ctx.needs_input_grad[3] else None), None, None
         plan = ctx.plan
         gout = gout.contiguous()
         n, c = h.shape
@@ -417,4 +417,7 @@ class GATAggregateFn(torch.autograd.Function):
                L.stream())
         L.call('gd_gat_bwd_src', plan.bwd.ref, L.ptr(alpha_t), L.ptr(dpre_t), L.ptr(gout), gout.stride(0), c,
                L.ptr(att_src), L.ptr(att_dst), L.ptr(da_dst), L.ptr(dh), dh.stride(0), L.ptr(da_src), L.stream())
-        return dh, None, None, None, None, None
+        g_src = torch.mv(h.t(), da_src).view(1, 1, -1) if ctx.needs_input_grad[1] else None    # a_src = h att_src
+        g_dst = torch.mv(h.t(), da_dst).view(1, 1, -1) if ctx.needs_input_grad[2] else None
+        g_bias = gout.sum(0) if ctx.needs_input_grad[3] else None
+        return (dh if ctx.needs_input_grad[0] else None), g_src, g_dst, g_bias, None, None

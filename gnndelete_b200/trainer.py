@@ -37,6 +37,83 @@ class Trainer:
         with open(os.path.join(args.checkpoint_dir, 'training_args.json'), 'w') as f:
             json.dump({k: v for k, v in vars(args).items() if _jsonable(v)}, f)
 
+    # ---- training of the ORIGINAL model (base.py:66-142): produces the checkpoint the unlearning path starts from
+    def negative_sampler(self, data, edge_index, count, epoch):
+        """Negatives of one epoch.  PyG's ``negative_sampling`` (base.py:84-87) is randomised rejection sampling and
+        not reproducible across implementations: uniform random pairs here; parity runs replace
+        this hook (or supply ``data.train_neg_edge_index`` = a fixed ``[2, count]`` tensor)."""
+        fixed = getattr(data, 'train_neg_edge_index', None)
+        if fixed is not None:
+            return fixed
+        if getattr(self, '_neg_gen', None) is None:
+            self._neg_gen = torch.Generator(device=edge_index.device).manual_seed(getattr(self.args, 'random_seed', 42))
+        return torch.randint(0, data.num_nodes, (2, int(count)), generator=self._neg_gen, device=edge_index.device)
+
+    def _train_edges(self, data):
+        """Message-passing / supervision edge set and the number of negatives (base.py:84-92)."""
+        ei = data.train_pos_edge_index
+        count = int(data.dtrain_mask.sum()) if hasattr(data, 'dtrain_mask') else ei.shape[1]
+        return ei, count
+
+    best_by = 'valid_loss'        # base.py:120 keeps the lowest validation loss; RetrainTrainer the best dt_auc + df_auc
+
+    def train(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
+        """``Trainer.train`` (base.py:66-73).  Both reference loops (full-batch and the GraphSAINT mini-batch one
+        for 'ogbl' datasets) run the step below; here the whole graph is always the batch."""
+        return self.train_fullbatch(model, data, optimizer, args)
+
+    def train_fullbatch(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
+        """``Trainer.train_fullbatch`` (base.py:75-142) / ``RetrainTrainer.train_fullbatch`` (retrain.py:38-131):
+        per epoch new negatives, ``z = model(x, edges)``, ``BCEWithLogits(decode(z, edges, neg), labels)``, backward
+        to EVERY parameter, ``optimizer.step()``.  Forward and backward run on the same kernels as the unlearning
+        path (aggregation, tcgen05 GEMMs incl. their weight gradients, pair decode + incidence gather)."""
+        dev = torch.device('cuda')
+        model = model.to(dev)
+        data = data.to(dev)
+        t_start = time.time()
+        best_valid_loss, best_metric, best_epoch = 1000000, 0, 0
+        ring = []
+        for epoch in range(args.epochs):
+            model.train()
+            ei, count = self._train_edges(data)
+            neg_edge_index = self.negative_sampler(data, ei, count, epoch)
+            z = model(data.x, ei)
+            logits = model.decode(z, ei, neg_edge_index)
+            label = self.get_link_labels(ei, neg_edge_index)
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, label)
+            loss.backward()
+            optimizer.step()
+            optimizer.zero_grad()
+            ring.append(loss.detach())
+            last = epoch + 1 == args.epochs
+            if (epoch + 1) % self.log_every == 0 or last or (epoch + 1) % args.valid_freq == 0:
+                for i, v in enumerate(torch.stack(ring).cpu().tolist()):
+                    self.trainer_log['log'].append({'epoch': epoch + 1 - len(ring) + i, 'train_loss': v})
+                ring = []
+            if (epoch + 1) % args.valid_freq == 0:
+                valid_loss, dt_auc, dt_aup, df_auc, df_aup, _, _, valid_log = self.eval(model, data, 'val')
+                valid_log['epoch'] = epoch
+                self.trainer_log['log'].append(valid_log)
+                if self.best_by == 'valid_loss':
+                    better = valid_loss < best_valid_loss
+                else:
+                    better = dt_auc + (df_auc if df_auc == df_auc else 0.0) > best_metric
+                if better:
+                    best_valid_loss, best_metric, best_epoch = valid_loss, dt_auc + (df_auc if df_auc == df_auc else 0.0), epoch
+                    torch.save({'model_state': model.state_dict(), 'optimizer_state': optimizer.state_dict()},
+                               os.path.join(args.checkpoint_dir, 'model_best.pt'))
+                    if self.best_by == 'valid_loss':
+                        torch.save(z.detach(), os.path.join(args.checkpoint_dir, 'node_embeddings.pt'))     # base.py:131
+        self.trainer_log['training_time'] = time.time() - t_start
+        torch.save({'model_state': model.state_dict(), 'optimizer_state': optimizer.state_dict()},
+                   os.path.join(args.checkpoint_dir, 'model_final.pt'))
+        self.trainer_log['best_epoch'] = best_epoch
+        self.trainer_log['best_valid_loss' if self.best_by == 'valid_loss' else 'best_metric'] = \
+            best_valid_loss if self.best_by == 'valid_loss' else best_metric
+        return model
+
+    log_every = 100
+
     @torch.no_grad()
     def get_link_labels(self, pos_edge_index, neg_edge_index):
         e = pos_edge_index.size(1) + neg_edge_index.size(1)
@@ -71,14 +148,12 @@ class Trainer:
                 for _ in range(num_df_resamples):
                     self.df_pos_edge.append(torch.randperm(dr_edges.shape[1], generator=g)[:n_df].to(z.device))
             dr_logit = model.decode(z, dr_edges).sigmoid()
-            lab = torch.cat([torch.zeros(n_df, device=z.device), torch.ones(n_df, device=z.device)])
-            aucs, aups = [], []
-            for idx in self.df_pos_edge:
-                lg = torch.cat([df_logit, dr_logit[idx]])
-                aucs.append(metrics.roc_auc(lab, lg, as_tensor=True))
-                aups.append(metrics.average_precision(lab, lg, as_tensor=True))
-            df_auc = torch.stack(aucs).mean().item()
-            df_aup = torch.stack(aups).mean().item()
+            # the 500 (Df vs random-Dr-sample) problems of base.py:264-280 in two batched passes
+            idx = self.df_pos_edge if torch.is_tensor(self.df_pos_edge) else torch.stack(self.df_pos_edge)
+            self.df_pos_edge = idx
+            aucs, aups = metrics.resampled_auc_ap(df_logit, dr_logit, idx)
+            df_auc = aucs.mean().item()
+            df_aup = aups.mean().item()
         else:
             df_auc = df_aup = float('nan')
         logit_all_pair = (z @ z.t()).cpu() if pred_all else None
@@ -121,6 +196,18 @@ def _jsonable(v):
         return True
     except TypeError:
         return False
+
+
+class RetrainTrainer(Trainer):
+    """``framework/trainer/retrain.py:28-131``: the retrain-from-scratch baseline - the same BCE link-prediction loop
+    on the RETAINED edges (``train_pos_edge_index[:, dr_mask]``, as many negatives as retained edges, :56-63), best
+    checkpoint by ``dt_auc + df_auc`` (:106-116)."""
+
+    best_by = 'metric'
+
+    def _train_edges(self, data):
+        ei = data.train_pos_edge_index[:, data.dr_mask].contiguous()
+        return ei, int(data.dr_mask.sum())
 
 
 class GNNDeleteTrainer(Trainer):

@@ -255,3 +255,21 @@ def nodeemb_epoch(model, data, neg_edge, z1_ori, z2_ori, optimizer, loss_type='b
     else:
         raise NotImplementedError(loss_type)
     return loss.detach(), loss_r.detach(), loss_l.detach()
+
+
+def link_train_epoch(model, data, neg_edge_index, optimizer, retrain=False):
+    """One epoch of ``Trainer.train_fullbatch`` (``framework/trainer/base.py:80-98``) or, with ``retrain``,
+    of ``RetrainTrainer.train_fullbatch`` (``framework/trainer/retrain.py:56-72``: the same step on the
+    retained edges): BCE link prediction on (edges, supplied negatives), backward to every parameter, step."""
+    ei = data.train_pos_edge_index
+    if retrain:
+        ei = ei[:, data.dr_mask]
+    z = model(data.x, ei)
+    logits = model.decode(z, ei, neg_edge_index)
+    label = torch.zeros(ei.shape[1] + neg_edge_index.shape[1], dtype=logits.dtype)     # get_link_labels, base.py:45-50
+    label[:ei.shape[1]] = 1.
+    loss = F.binary_cross_entropy_with_logits(logits, label)
+    loss.backward()
+    optimizer.step()
+    optimizer.zero_grad()
+    return loss.detach()

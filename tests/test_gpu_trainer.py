@@ -120,6 +120,13 @@ def test_eval_matches_sklearn(lib, tmp_path):
     assert dt_auc == pytest.approx(roc_auc_score(label, logits), abs=1e-9)
     assert dt_aup == pytest.approx(average_precision_score(label, logits), abs=1e-9)
     assert 0 <= df_auc <= 1 and len(df_logit) == d.directed_df_edge_index.shape[1]
+    # Df-vs-resampled-Dr AUC / AP (base.py:264-280): the batched device version against sklearn, sample by sample
+    dr_logit = m.decode(z, d.train_pos_edge_index[:, d.dr_mask]).sigmoid().cpu()
+    lab = [0] * len(df_logit) + [1] * len(df_logit)
+    aucs = [roc_auc_score(lab, df_logit + dr_logit[i.cpu()].tolist()) for i in tr.df_pos_edge]
+    aups = [average_precision_score(lab, df_logit + dr_logit[i.cpu()].tolist()) for i in tr.df_pos_edge]
+    assert len(aucs) == 5
+    assert df_auc == pytest.approx(sum(aucs) / 5, abs=1e-9) and df_aup == pytest.approx(sum(aups) / 5, abs=1e-9)
 
 
 def test_kg_trainer_matches_reference_schedule(lib, tmp_path):
