@@ -9,7 +9,7 @@ start from (``original``, ``retrain``).  The other base
  and are not registered; asking for one raises ``NotImplementedError``.
 """
 from .models import GCN, GAT, GIN, RGCN, GCNDelete, GATDelete, GINDelete, RGCNDelete
-from .trainer.base import Trainer
+from .trainer.base import Trainer, KGTrainer
 from .trainer.retrain import RetrainTrainer
 from .trainer.gnndelete import GNNDeleteTrainer
 from .trainer.gnndelete_nodeemb import GNNDeleteNodeembTrainer, KGGNNDeleteNodeembTrainer
@@ -23,6 +23,7 @@ trainer_mapping = {
 }
 
 kg_trainer_mapping = {
+    'original': KGTrainer,            # eval / test only: KG training of the original model is not accelerated
     'gnndelete': KGGNNDeleteNodeembTrainer,
     'gnndelete_nodeemb': KGGNNDeleteNodeembTrainer,
 }

@@ -1,1 +1,1 @@
-from gnndelete_b200.trainer import Trainer  # noqa: F401  (reference: framework/trainer/base.py)
+from gnndelete_b200.trainer import Trainer, KGTrainer  # noqa: F401  (reference: framework/trainer/base.py)

@@ -415,7 +415,62 @@ class GNNDeleteTrainer(Trainer):
         return optimizer.state_dict()
 
 
-class KGGNNDeleteNodeembTrainer(Trainer):
+class KGTrainer(Trainer):
+    """Evaluation side of ``framework/trainer/base.py:394-692`` (``KGTrainer``) for the RGCN models: DistMult decode
+    of the val / test triples on the ``dr_mask`` message-passing edges, BCE + AUC / AP on Dt - on the raw logits,
+    the KG variant applies no sigmoid there (:508-514) - and AUC / AP of the deleted triples against
+    ``num_df_resamples`` random samples of retained forward triples (:517-540).  KG training of the original model
+    (:395-492, GraphSAINT mini-batches, relation-weight gradients) is outside the accelerated path."""
+
+    def train(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
+        raise NotImplementedError('training the original RGCN model (KGTrainer.train, base.py:395-492) is outside the '
+                                  'accelerated hot path')
+
+    @torch.no_grad()
+    def eval(self, model, data, stage='val', pred_all=False, num_df_resamples=500):
+        model.eval()
+        pos, neg = data[f'{stage}_pos_edge_index'], data[f'{stage}_neg_edge_index']
+        et = data[f'{stage}_edge_type']
+        z = model(data.x, data.edge_index[:, data.dr_mask].contiguous(), data.edge_type[data.dr_mask].contiguous())
+        logits = model.decode(z, torch.cat([pos, neg], dim=-1), torch.cat([et, et], dim=-1))
+        label = self.get_link_labels(pos, neg)
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, label).item()
+        dt_auc = metrics.roc_auc(label, logits)
+        dt_aup = metrics.average_precision(label, logits)
+        if self.args.unlearning_model in ['original']:
+            df_logit = torch.empty(0, device=z.device)
+        else:
+            df_logit = model.decode(z, data.directed_df_edge_index, data.directed_df_edge_type).sigmoid()
+        n_df = df_logit.numel()
+        if n_df > 0:
+            dr_mask = data.dr_mask[:data.dr_mask.shape[0] // 2]                      # forward-direction triples
+            dr_logit = model.decode(z, data.train_pos_edge_index[:, dr_mask].contiguous(),
+                                    data.train_edge_type[dr_mask].contiguous()).sigmoid()
+            if len(self.df_pos_edge) == 0:       # the reference redraws the 500 samples on every call; cached here
+                g = torch.Generator(device='cpu').manual_seed(getattr(self.args, 'random_seed', 42))
+                self.df_pos_edge = torch.stack([torch.randperm(dr_logit.numel(), generator=g)[:n_df]
+                                                for _ in range(num_df_resamples)]).to(z.device)
+            aucs, aups = metrics.resampled_auc_ap(df_logit, dr_logit, self.df_pos_edge)
+            df_auc, df_aup = aucs.mean().item(), aups.mean().item()
+        else:
+            df_auc = df_aup = float('nan')
+        logit_all_pair = (z @ z.t()).cpu() if pred_all else None
+        log = {
+            f'{stage}_loss': loss, f'{stage}_dt_auc': dt_auc, f'{stage}_dt_aup': dt_aup,
+            f'{stage}_df_auc': df_auc, f'{stage}_df_aup': df_aup,
+            f'{stage}_df_logit_mean': df_logit.mean().item() if n_df else float('nan'),
+            f'{stage}_df_logit_std': df_logit.std(unbiased=False).item() if n_df else float('nan'),
+        }
+        return loss, dt_auc, dt_aup, df_auc, df_aup, df_logit.tolist(), logit_all_pair, log
+
+    @torch.no_grad()
+    def test(self, model, data, model_retrain=None, attack_model_all=None, attack_model_sub=None, ckpt='ckpt'):
+        """``base.py:570-640``; the default ``ckpt='ckpt'`` never reloads the best checkpoint (the reference compares
+        ``ckpt is 'best'``, SURVEY.md §10 #14) - kept."""
+        return super().test(model, data, ckpt=ckpt)
+
+
+class KGGNNDeleteNodeembTrainer(KGTrainer):
     """``framework/trainer/gnndelete_nodeemb.py:659-846`` (``KGGNNDeleteNodeembTrainer``),
     the route ``--gnn rgcn --unlearning_model gnndelete[_nodeemb]`` dispatches to.
 
@@ -429,9 +484,6 @@ class KGGNNDeleteNodeembTrainer(Trainer):
     computed once instead of once per step."""
 
     log_every = 10
-
-    def eval(self, model, data, stage='val', pred_all=False, num_df_resamples=500):
-        raise NotImplementedError('KG evaluation (KGTrainer.eval, base.py:394-692) is outside the accelerated hot path')
 
     def train(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
         from .kg import negative_sampling_kg
@@ -462,7 +514,7 @@ class KGGNNDeleteNodeembTrainer(Trainer):
         neg = fixed_neg if fixed_neg is not None else negative_sampling_kg(dec_ei, dec_et, gen)
         plan1 = RowMSEPlan(dec_ei, neg, m1, z1o, mix=(alpha, 1 - alpha))
         plan2 = RowMSEPlan(dec_ei, neg, m2, z2o, mix=(alpha, 1 - alpha))
-        ring = []
+        ring, best_metric = [], 0
         for epoch in range(args.epochs):
             model.train()
             z1, z2 = model(data.x, edge_index, edge_type, m1, m2, return_all_emb=True)
@@ -484,6 +536,14 @@ class KGGNNDeleteNodeembTrainer(Trainer):
                     self.trainer_log['log'].append({'Epoch': epoch + 1 - len(ring) + i, 'train_loss': v[0],
                                                     'loss_r': v[1], 'loss_l': v[2]})
                 ring = []
+            if (epoch + 1) % args.valid_freq == 0:                                   # :815-841
+                del z1, z2, loss1, loss2
+                valid_loss, dt_auc, dt_aup, df_auc, df_aup, _, _, valid_log = self.eval(model, data, 'val')
+                valid_log['epoch'] = epoch
+                self.trainer_log['log'].append(valid_log)
+                if dt_auc + df_auc > best_metric:
+                    best_metric = dt_auc + df_auc
+                    torch.save({'model_state': model.state_dict()}, os.path.join(args.checkpoint_dir, 'model_best.pt'))
         torch.save({'model_state': {k: v.to('cpu') for k, v in model.state_dict().items()}},
                    os.path.join(args.checkpoint_dir, 'model_final.pt'))
         return model

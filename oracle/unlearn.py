@@ -273,3 +273,27 @@ def link_train_epoch(model, data, neg_edge_index, optimizer, retrain=False):
     optimizer.step()
     optimizer.zero_grad()
     return loss.detach()
+
+
+def split_edges(data, perm, val_ratio=0.05, test_ratio=0.1):
+    """``train_test_split_edges_no_neg_adj_mask`` (``prepare_dataset.py:31-136``), homogeneous branch, with the
+    permutation supplied: ``row < col`` edges, permuted, ``[test | val | train]`` (:45-50, :63-67, :99-100, :117-118).
+    Returns (train, test, val) directed edge lists; the sampled negatives are random in the reference."""
+    import math
+    row, col = data.edge_index
+    mask = row < col
+    row, col = row[mask], col[mask]
+    n_v = int(math.floor(val_ratio * row.size(0)))
+    n_t = int(math.floor(test_ratio * row.size(0)))
+    row, col = row[perm], col[perm]
+    train = torch.stack([row[n_v + n_t:], col[n_v + n_t:]], dim=0)
+    test = torch.stack([row[:n_t], col[:n_t]], dim=0)
+    val = torch.stack([row[n_t:n_t + n_v], col[n_t:n_t + n_v]], dim=0)
+    return train, test, val
+
+
+def df_candidate_masks(train_pos_edge_index, test_pos_edge_index, num_nodes):
+    """``prepare_dataset.py:203-215, 262-265``: edges inside / outside the 2-hop subgraph of the test edges."""
+    _, _, _, mask = P.k_hop_subgraph(test_pos_edge_index.flatten().unique(), 2, train_pos_edge_index,
+                                     num_nodes=num_nodes)
+    return {'out': ~mask, 'in': mask}

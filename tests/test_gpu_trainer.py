@@ -170,6 +170,56 @@ def test_kg_trainer_matches_reference_schedule(lib, tmp_path):
     U.assert_close(model.deletion2.deletion_weight, om.deletion2.deletion_weight, tol=1e-4, what='kg W_del2')
 
 
+def test_kg_eval_matches_sklearn_and_oracle(lib, tmp_path):
+    """KGTrainer.eval (base.py:494-566): DistMult logits against the oracle's decode, Dt AUC / AP on the raw logits and
+    the Df-vs-resampled-Dr AUC / AP against sklearn; then the trainer's validation / best-checkpoint leg."""
+    import framework
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    from gnndelete_b200 import synthetic as S
+    from oracle import unlearn as OU
+    net = 51
+    shape = dataclasses.replace(S.SHAPES['biokg'].scaled(0.002), num_edge_type=net)
+    raw = S.make_graph(shape, seed=42)
+    df = S.sample_df_mask(shape.num_edges, shape.num_deleted, seed=42)
+    data = OU.build_unlearning_data(raw, df, num_edge_type=net)
+    args = _args(tmp_path, gnn='rgcn', unlearning_model='gnndelete_nodeemb', dataset='ogbl-biokg', epochs=2, valid_freq=1,
+                 num_edge_type=net)
+    om = U.oracle_model('rgcn', shape, data, dtype=torch.float64, num_nodes=shape.num_nodes, num_edge_type=net)
+    model = framework.get_model(args, data.sdf_node_1hop_mask, data.sdf_node_2hop_mask, num_nodes=shape.num_nodes,
+                                num_edge_type=net)
+    model.load_state_dict({k: v.float().clone() for k, v in om.state_dict().items()}, strict=False)
+    model = model.to(DEV)
+    trainer = framework.get_trainer(args)
+    d = data.clone().to(DEV)
+    loss, dt_auc, dt_aup, df_auc, df_aup, df_logit, _, log = trainer.eval(model, d, 'val', num_df_resamples=4)
+    with torch.no_grad():
+        zo = om(data.x, data.edge_index[:, data.dr_mask], data.edge_type[data.dr_mask])
+        ei = torch.cat([data.val_pos_edge_index, data.val_neg_edge_index], -1)
+        et = torch.cat([data.val_edge_type, data.val_edge_type], -1)
+        want = om.decode(zo, ei, et)
+        z = model(d.x, d.edge_index[:, d.dr_mask].contiguous(), d.edge_type[d.dr_mask].contiguous())
+        got = model.decode(z, ei.to(DEV), et.to(DEV))
+        half = d.dr_mask[:d.dr_mask.shape[0] // 2]
+        dr_logit = model.decode(z, d.train_pos_edge_index[:, half].contiguous(), d.train_edge_type[half].contiguous()).sigmoid().cpu()
+    U.assert_close(got, want, what='KG val logits')
+    label = torch.cat([torch.ones(data.val_pos_edge_index.shape[1]), torch.zeros(data.val_neg_edge_index.shape[1])])
+    assert dt_auc == pytest.approx(roc_auc_score(label, got.cpu()), abs=1e-9)
+    assert dt_aup == pytest.approx(average_precision_score(label, got.cpu()), abs=1e-9)
+    assert len(df_logit) == data.directed_df_edge_index.shape[1] and trainer.df_pos_edge.shape == (4, len(df_logit))
+    lab = [0] * len(df_logit) + [1] * len(df_logit)
+    aucs = [roc_auc_score(lab, df_logit + dr_logit[i.cpu()].tolist()) for i in trainer.df_pos_edge]
+    aups = [average_precision_score(lab, df_logit + dr_logit[i.cpu()].tolist()) for i in trainer.df_pos_edge]
+    assert df_auc == pytest.approx(sum(aucs) / 4, abs=1e-9) and df_aup == pytest.approx(sum(aups) / 4, abs=1e-9)
+    # training with validation every epoch
+    optimizer = [torch.optim.Adam(model.deletion1.parameters(), lr=args.lr),
+                 torch.optim.Adam(model.deletion2.parameters(), lr=args.lr)]
+    trainer.train(model, data.clone(), optimizer, args)
+    vals = [l for l in trainer.trainer_log['log'] if 'val_dt_auc' in l]
+    assert len(vals) == 2 and os.path.exists(os.path.join(args.checkpoint_dir, 'model_best.pt'))
+    trainer.test(model, d)
+    assert 0.0 <= trainer.trainer_log['dt_auc'] <= 1.0 and trainer.logit_all_pair is None      # 'ogbl': no all-pair logits
+
+
 def test_negative_sampling_kg_permutes_heads_within_relation(lib):
     from gnndelete_b200.kg import negative_sampling_kg
     g = torch.Generator().manual_seed(0)
