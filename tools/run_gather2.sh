@@ -1,5 +1,9 @@
 #!/bin/bash
+# builds the two microbenchmarks if needed (the binaries are not tracked), then sweeps them
 mkdir -p gpurun_out
+for t in gather_bench gather_bench2; do
+  [ -x tools/$t ] || nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o tools/$t tools/$t.cu -lcuda || exit 1
+done
 B=tools/gather_bench2
 {
 timeout 60 tools/gather_bench | head -12
