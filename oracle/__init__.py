@@ -13,6 +13,9 @@ tensors, does not import as shipped (``framework/__init__.py:10`` imports a
 missing module) and delegates the arithmetic to an unpinned, uninstalled
 PyTorch-Geometric (2.0.3 … 2.2.x by API usage).  The oracle's authority rests on
 line-by-line correspondence with the cited in-tree files, PyG's published
-default-path semantics, float64 ``gradcheck`` and an independent
-dense-matrix / networkx cross-check in ``tests/test_oracle.py``.
+default-path semantics, float64 ``gradcheck``, an independent
+dense-matrix / networkx cross-check, and the known-answer vectors of PyG's own docstrings
+and unit tests (``k_hop_subgraph``, ``to_undirected``, ``softmax``, ``add_remaining_self_loops``;
+written down from the published sources, not executed against an install) in
+``tests/test_oracle.py``.
 """
