@@ -214,7 +214,7 @@ def cpu_epoch_runner(shape, seed=42):
         loss.backward()
         opt.step()
         opt.zero_grad()
-        return float(loss)
+        return float(loss.detach())
 
     return epoch, cores
 
@@ -243,7 +243,7 @@ def run_reference(args, shape):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(shape, 'cpu'),
+        'config': workload_config(shape), 'where': 'host CPU',
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'note': 'PyTorch-Geometric is not installable here; the reference arm is the oracle restatement run with '
@@ -252,14 +252,14 @@ def run_reference(args, shape):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(shape, where):
+def workload_config(shape, where=None):
+    """Identical for the native and the reference arm (the driver pairs their lines by metric and config)."""
     return {
         'workload': f'GCNDelete edge unlearning, {shape.name}-shaped synthetic power-law graph '
                     f'({shape.num_nodes} nodes / {shape.num_edges} directed train edges / {shape.num_deleted} deleted), '
                     f'{shape.in_dim}->{shape.hidden_dim}->{shape.out_dim}, edge-form NI loss, full graph per step',
         'epoch': 'fwd (both convs recomputed) + decode + DEC/NI loss + bwd to Del weights + Adam',
         'l2': 'per-epoch working set ~0.9 GB > 126 MB L2, no flush between steps',
-        'where': where,
     }
 
 
@@ -465,7 +465,7 @@ def main():
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(shape, 'B200'),
+        'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(shape), 'where': 'B200',
         'value_hoisted': world * args.steps / (ms_h / 1e3), 'ms_per_step_hoisted': ms_h / args.steps,
         'roofline': roofline, 'e2e': e2e, 'gpu_launches': int(launches_per_epoch * args.steps),
         'launches_per_epoch': int(launches_per_epoch), 'clocks': clocks,
