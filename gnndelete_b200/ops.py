@@ -18,6 +18,11 @@ from .graph import CSR
 
 # 'tc': tcgen05 tensor-core path where the shape allows, 'simt': exact-fp32 CUDA-core path only
 GEMM_BACKEND = os.environ.get('GD_GEMM', 'tc')
+# EXPERIMENT (opt-in, prepared but not yet measured on a B200): run a 128-wide unweighted aggregation as two 64-wide
+# column passes.  The 120 MB source of the Collab layer-1 aggregation only just fits the 126 MB L2 (50 % hit rate, 410 MB
+# of DRAM reads for 120 MB of compulsory source bytes, profiles/r1_spmm_batched_ncu_full.md); each half-pass gathers
+# 256-byte half rows from a 60 MB footprint like the 64-wide launches that run at 12.3 TB/s of L2 traffic.
+SPLIT128 = os.environ.get('GD_SPMM_SPLIT128', '0') == '1'
 
 
 def _f32(t):
@@ -43,6 +48,14 @@ def spmm(csr: CSR, x, out=None, val=None, col_scale=None, row_scale=None, self_c
         out = torch.empty(n, f, dtype=torch.float32, device=x.device)
     weighted = valp is not None or col_scale is not None
     bp = csr.bplan(f, weighted) if val is None and x.stride(0) % 4 == 0 and out.stride(0) % 4 == 0 else None
+    if bp is not None and SPLIT128 and f == 128 and valp is None and tail is None and csr.bplan(64, weighted) is not None:
+        bp64 = csr.bplan(64, weighted)
+        v64 = bp64.col_scale_weights(col_scale) if col_scale is not None else None
+        for off in (0, 256):                         # byte offset of the column half inside every row
+            L.call('gd_spmm_batched_tail', bp64.ref, L.ptr(v64), None, None, None, L.ptr(row_scale), L.ptr(x) + off,
+                   x.stride(0), 64, float(self_coef), None if bias is None else L.ptr(bias) + off, L.ptr(out) + off,
+                   out.stride(0), L.ptr(bp64.scratch(64)), int(bool(accumulate)), L.stream())
+        return out
     if bp is not None:
         if valp is None and col_scale is not None:
             valp = bp.col_scale_weights(col_scale)
