@@ -18,11 +18,12 @@ from .graph import CSR
 
 # 'tc': tcgen05 tensor-core path where the shape allows, 'simt': exact-fp32 CUDA-core path only
 GEMM_BACKEND = os.environ.get('GD_GEMM', 'tc')
-# EXPERIMENT (opt-in, prepared but not yet measured on a B200): run a 128-wide unweighted aggregation as two 64-wide
-# column passes.  The 120 MB source of the Collab layer-1 aggregation only just fits the 126 MB L2 (50 % hit rate, 410 MB
-# of DRAM reads for 120 MB of compulsory source bytes, profiles/r1_spmm_batched_ncu_full.md); each half-pass gathers
-# 256-byte half rows from a 60 MB footprint like the 64-wide launches that run at 12.3 TB/s of L2 traffic.
-SPLIT128 = os.environ.get('GD_SPMM_SPLIT128', '0') == '1'
+# A 128-wide unweighted aggregation runs as two 64-wide column passes (GD_SPMM_SPLIT128=0 restores the single pass).
+# The 120 MB source of the Collab layer-1 aggregation only just fits the 126 MB L2 (50 % hit rate, 410 MB of DRAM reads
+# for 120 MB of compulsory source bytes, profiles/r1_spmm_batched_ncu_full.md); each half-pass gathers 256-byte half
+# rows from a 60 MB footprint like the 64-wide launches.  Measured 121.3 -> 112.7 us, epoch 1118 -> 1137 epochs/s
+# (profiles/r1_split128_ab.md).
+SPLIT128 = os.environ.get('GD_SPMM_SPLIT128', '1') == '1'
 
 
 def _f32(t):
