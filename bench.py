@@ -200,11 +200,13 @@ def cpu_epoch_runner(shape, seed=42):
     torch.set_num_threads(cores)
     raw = S.make_graph(shape, seed=seed, device='cpu')
     df = S.sample_df_mask(shape.num_edges, shape.num_deleted, seed=seed)
-    data = OU.build_unlearning_data(raw, df)
+    data = OU.build_unlearning_data(raw, df, num_edge_type=shape.num_edge_type or None)
     neg = S.supplied_negatives(shape.num_nodes, int(data.df_mask.sum()), seed=seed + 1)
     args = types.SimpleNamespace(in_dim=shape.in_dim, hidden_dim=shape.hidden_dim, out_dim=shape.out_dim)
     torch.manual_seed(seed)
-    model = OM.GCNDelete(args, data.sdf_node_1hop_mask, data.sdf_node_2hop_mask)
+    if shape.gnn == 'rgcn':
+        return _cpu_kg_step_runner(shape, data, args), cores
+    model = OM.DELETE_MODELS[shape.gnn](args, data.sdf_node_1hop_mask, data.sdf_node_2hop_mask)
     opt = torch.optim.Adam([p for n, p in model.named_parameters() if 'del' in n], lr=1e-3)
     with torch.no_grad():
         z_ori = model.get_original_embeddings(data.x, data.train_pos_edge_index[:, data.dr_mask])
@@ -217,6 +219,28 @@ def cpu_epoch_runner(shape, seed=42):
         return float(loss.detach())
 
     return epoch, cores
+
+
+def _cpu_kg_step_runner(shape, data, args):
+    """BASELINE config 4: the KG node-embedding step (gnndelete_nodeemb.py:744-798) with the per-relation Python loop of
+    PyG's RGCNConv - forward, original embeddings, two backward passes, two Adam steps."""
+    from oracle import models as OM
+    from oracle import unlearn as OU
+    net = shape.num_edge_type
+    model = OM.RGCNDelete(args, shape.num_nodes, net, data.sdf_node_1hop_mask, data.sdf_node_2hop_mask)
+    pos_ei, pos_et = data.edge_index[:, data.df_mask], data.edge_type[data.df_mask]
+    dec = pos_et < net
+    neg = OU.negative_sampling_kg(pos_ei[:, dec], pos_et[dec], generator=torch.Generator().manual_seed(43))
+    o1 = torch.optim.Adam(model.deletion1.parameters(), lr=1e-3)
+    o2 = torch.optim.Adam(model.deletion2.parameters(), lr=1e-3)
+
+    def step():
+        loss1, loss2, _ = OU.kg_step_losses(model, data, neg, net, alpha=0.5)
+        loss1.backward(retain_graph=True); o1.step(); o1.zero_grad()
+        loss2.backward(retain_graph=True); o2.step(); o2.zero_grad()
+        return float((loss1 + loss2).detach())
+
+    return step
 
 
 def run_reference(args, shape):
@@ -240,7 +264,8 @@ def run_reference(args, shape):
     sample = (f'{args.steps} full epochs of the {shape.name} workload (whole graph, no sub-sampling)' +
               (f'; {requested} requested, stopped at the {args.cpu_budget_s:.0f} s CPU budget' if done < requested else ''))
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'impl': 'reference', 'metric': METRIC if shape.name.startswith('collab') else f'Del-training epochs/s on {shape.name} shape',
+        'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(shape), 'where': 'host CPU',
@@ -255,10 +280,13 @@ def run_reference(args, shape):
 def workload_config(shape, where=None):
     """Identical for the native and the reference arm (the driver pairs their lines by metric and config)."""
     return {
-        'workload': f'GCNDelete edge unlearning, {shape.name}-shaped synthetic power-law graph '
+        'workload': f'{shape.gnn.upper()}Delete edge unlearning, {shape.name}-shaped synthetic power-law graph '
                     f'({shape.num_nodes} nodes / {shape.num_edges} directed train edges / {shape.num_deleted} deleted), '
-                    f'{shape.in_dim}->{shape.hidden_dim}->{shape.out_dim}, edge-form NI loss, full graph per step',
-        'epoch': 'fwd (both convs recomputed) + decode + DEC/NI loss + bwd to Del weights + Adam',
+                    f'{shape.in_dim}->{shape.hidden_dim}->{shape.out_dim}, ' +
+                    ('node-embedding DEC/NI losses (KG step)' if shape.gnn == 'rgcn' else 'edge-form NI loss') +
+                    ', full graph per step',
+        'epoch': ('fwd + original embeddings + two backward passes + two Adam steps' if shape.gnn == 'rgcn' else
+                  'fwd (both convs recomputed) + decode + DEC/NI loss + bwd to Del weights + Adam'),
         'l2': 'per-epoch working set ~0.9 GB > 126 MB L2, no flush between steps',
     }
 
