@@ -18,12 +18,16 @@ from .graph import CSR
 
 # 'tc': tcgen05 tensor-core path where the shape allows, 'simt': exact-fp32 CUDA-core path only
 GEMM_BACKEND = os.environ.get('GD_GEMM', 'tc')
-# A 128-wide unweighted aggregation runs as two 64-wide column passes (GD_SPMM_SPLIT128=0 restores the single pass).
-# The 120 MB source of the Collab layer-1 aggregation only just fits the 126 MB L2 (50 % hit rate, 410 MB of DRAM reads
-# for 120 MB of compulsory source bytes, profiles/r1_spmm_batched_ncu_full.md); each half-pass gathers 256-byte half
-# rows from a 60 MB footprint like the 64-wide launches.  Measured 121.3 -> 112.7 us, epoch 1118 -> 1137 epochs/s
-# (profiles/r1_split128_ab.md).
-SPLIT128 = os.environ.get('GD_SPMM_SPLIT128', '1') == '1'
+# A 128-wide aggregation whose source matrix is about the size of the L2 runs as two 64-wide column passes
+# (GD_SPMM_SPLIT128=0: never, =force: at every size).  The 120 MB source of the Collab layer-1 aggregation only just fits
+# the 126 MB L2 (50 % hit rate, 410 MB of DRAM reads for 120 MB of compulsory source bytes,
+# profiles/r1_spmm_batched_ncu_full.md); each half-pass gathers 256-byte half rows from a 60 MB footprint like the 64-wide
+# launches.  Measured 121.3 -> 112.7 us, epoch 1118 -> 1137 epochs/s (profiles/r1_split128_ab.md).  Sources far below the
+# L2 size gain nothing from a second launch, sources far above it (config 5) do not become L2 resident by halving.
+_SPLIT128_MODE = os.environ.get('GD_SPMM_SPLIT128', '1')
+SPLIT128 = _SPLIT128_MODE != '0'
+L2_BYTES = 126 << 20
+SPLIT128_SOURCE_BYTES = (0, float('inf')) if _SPLIT128_MODE == 'force' else (L2_BYTES // 2, 2 * L2_BYTES)
 
 
 def _f32(t):
@@ -49,7 +53,9 @@ def spmm(csr: CSR, x, out=None, val=None, col_scale=None, row_scale=None, self_c
         out = torch.empty(n, f, dtype=torch.float32, device=x.device)
     weighted = valp is not None or col_scale is not None
     bp = csr.bplan(f, weighted) if val is None and x.stride(0) % 4 == 0 and out.stride(0) % 4 == 0 else None
-    if bp is not None and SPLIT128 and f == 128 and valp is None and tail is None and csr.bplan(64, weighted) is not None:
+    if bp is not None and SPLIT128 and f == 128 and valp is None and tail is None \
+            and SPLIT128_SOURCE_BYTES[0] < x.shape[0] * x.stride(0) * 4 <= SPLIT128_SOURCE_BYTES[1] \
+            and csr.bplan(64, weighted) is not None:
         bp64 = csr.bplan(64, weighted)
         v64 = bp64.col_scale_weights(col_scale) if col_scale is not None else None
         for off in (0, 256):                         # byte offset of the column half inside every row

@@ -68,6 +68,49 @@ def test_spmm_matches_dense(lib, case, feat):
     U.assert_close(out2, ref2, what=f'spmm unweighted F={feat}')
 
 
+def test_spmm_two_pass_128_wide(lib, case, monkeypatch):
+    """A 128-wide aggregation as two 64-wide column passes (`ops.SPLIT128`, on by default for sources about the size of
+    the L2, forced here at test size): same result as the dense product and as the single pass, weighted (with self term and bias) and unweighted."""
+    from gnndelete_b200 import ops
+    from gnndelete_b200.graph import build_csr
+    shape, raw, df, data, neg = case
+    ei = data.train_pos_edge_index
+    n = data.num_nodes
+    csr = build_csr(ei[0].to(DEV), ei[1].to(DEV), n, self_loops=False)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(n, 128, generator=g)
+    rs, cs = torch.rand(n, generator=g) + 0.5, torch.rand(n, generator=g) + 0.5
+    bias = torch.randn(128, generator=g)
+    A = torch.zeros(n, n, dtype=torch.float64)
+    A.index_put_((ei[1], ei[0]), torch.ones(ei.shape[1], dtype=torch.float64), accumulate=True)
+    ref_w = rs.double().view(-1, 1) * (A @ (cs.double().view(-1, 1) * x.double())) + 0.5 * x.double() + bias.double()
+    ref_u = A @ x.double()
+    xd, rsd, csd, bd = x.to(DEV), rs.to(DEV), cs.to(DEV), bias.to(DEV)
+
+    def run():
+        w = ops.spmm(csr, xd, col_scale=csd, row_scale=rsd, self_coef=0.5, bias=bd)
+        u = ops.spmm(csr, xd)
+        return w, u
+
+    monkeypatch.setattr(ops, 'SPLIT128', True)
+    monkeypatch.setattr(ops, 'SPLIT128_SOURCE_BYTES', (0, float('inf')))
+    run()                                                       # builds the 64-wide plans / cached weights
+    c0 = lib.gd_launch_count()
+    w2, u2 = run()
+    n_two = lib.gd_launch_count() - c0
+    monkeypatch.setattr(ops, 'SPLIT128', False)
+    run()
+    c0 = lib.gd_launch_count()
+    w1, u1 = run()
+    n_one = lib.gd_launch_count() - c0
+    assert n_two > n_one, 'the two-pass path was not taken'
+    U.assert_close(w2, ref_w, what='two-pass weighted')
+    U.assert_close(u2, ref_u, what='two-pass unweighted')
+    # same sums in a different piece order (the 64- and 128-wide plans cut long rows at different places)
+    U.assert_close(w2, w1, tol=5e-6, what='two-pass vs single pass')
+    U.assert_close(u2, u1, tol=5e-6, what='two-pass vs single pass, unweighted')
+
+
 @pytest.mark.parametrize('workers', [1, 7, 1000, 9472, 10 ** 6])
 def test_batch_plan_native_builder_bit_exact(lib, case, workers):
     """The CUDA plan builder and the tensor-op builder (whose walk tests/test_batch_plan.py checks on the CPU)
