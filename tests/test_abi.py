@@ -5,6 +5,8 @@ import os
 import re
 import subprocess
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, 'include', 'gnndelete_b200.h')
 
@@ -70,3 +72,34 @@ def test_product_never_imports_the_oracle():
             if f.endswith('.py'):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
+
+
+def _struct_fields(name):
+    """Field names and C types of `typedef struct <tag> { ... } <name>;` in the header, in order."""
+    text = re.sub(r'/\*.*?\*/', '', open(HEADER).read(), flags=re.S)
+    body = re.search(r'typedef\s+struct\s+\w+\s*\{([^{}]*)\}\s*' + name + r'\s*;', text).group(1)
+    out = []
+    for decl in body.split(';'):
+        decl = decl.strip()
+        if decl:
+            m = re.match(r'(.*?)(\w+)$', decl, flags=re.S)
+            out.append((m.group(2), ' '.join(m.group(1).split())))
+    return out
+
+
+@pytest.mark.parametrize('cname,pyname', [('gd_csr_t', 'CsrStruct'), ('gd_spmm_bplan_t', 'BplanStruct')])
+def test_ctypes_structs_match_the_header(cname, pyname):
+    """The plain-struct arguments are laid out by hand on the Python side: same fields, order and widths."""
+    from gnndelete_b200 import _lib
+    want = _struct_fields(cname)
+    got = getattr(_lib, pyname)._fields_
+    assert [n for n, _ in want] == [n for n, _ in got]
+    for (name, ctype), (_, pytype) in zip(want, got):
+        if '*' in ctype:
+            assert pytype is ctypes.c_void_p, name
+        elif ctype == 'int64_t':
+            assert pytype is ctypes.c_int64, name
+        elif ctype == 'int32_t':
+            assert pytype is ctypes.c_int32, name
+        else:
+            raise AssertionError(f'unhandled C type {ctype!r} for {name}')
