@@ -103,3 +103,31 @@ def test_ctypes_structs_match_the_header(cname, pyname):
             assert pytype is ctypes.c_int32, name
         else:
             raise AssertionError(f'unhandled C type {ctype!r} for {name}')
+
+
+def test_ctypes_signatures_match_the_prototypes():
+    """Every prototype of the header against the hand-written ctypes table: parameter count and, per parameter,
+    pointer / 64-bit / 32-bit / float class (a wrong width in a ctypes call corrupts arguments silently)."""
+    from gnndelete_b200 import _lib
+    text = re.sub(r'/\*.*?\*/', '', open(HEADER).read(), flags=re.S)
+    protos = dict(re.findall(r'\b(gd_[a-z0-9_]+)\s*\(([^()]*)\)\s*;', text))
+    assert sorted(protos) == sorted(_lib.SIGNATURES)
+
+    def cls(c_decl):
+        c_decl = ' '.join(c_decl.split())
+        if c_decl in ('void', ''):
+            return None
+        if '*' in c_decl or c_decl.startswith('gd_stream_t'):
+            return ctypes.c_void_p
+        for key, t in (('int64_t', ctypes.c_int64), ('int32_t', ctypes.c_int32), ('size_t', ctypes.c_size_t),
+                       ('float', ctypes.c_float)):
+            if c_decl.startswith(key + ' ') or c_decl == key:
+                return t
+        raise AssertionError(f'unhandled parameter {c_decl!r}')
+
+    for name, params in protos.items():
+        want = [cls(p) for p in params.split(',')]
+        want = [w for w in want if w is not None]
+        got = list(_lib.SIGNATURES[name][1])
+        got = [ctypes.c_void_p if isinstance(g, type) and issubclass(g, ctypes._Pointer) else g for g in got]
+        assert got == want, f'{name}: ctypes {got} vs header {want}'
