@@ -131,3 +131,27 @@ def test_ctypes_signatures_match_the_prototypes():
         got = list(_lib.SIGNATURES[name][1])
         got = [ctypes.c_void_p if isinstance(g, type) and issubclass(g, ctypes._Pointer) else g for g in got]
         assert got == want, f'{name}: ctypes {got} vs header {want}'
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path, lib):
+    """The boundary is a C ABI: the header compiles as C99 and as C++, and a C program links against the library and
+    calls its host-side entry points (no device needed)."""
+    from gnndelete_b200 import _lib
+    for std, lang in (('c99', 'c'), ('c++17', 'c++')):
+        r = subprocess.run(['gcc' if lang == 'c' else 'g++', f'-std={std}', '-Wall', '-pedantic', '-fsyntax-only', '-x', lang,
+                            HEADER], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    src = tmp_path / 'probe.c'
+    src.write_text('#include <stdio.h>\n#include "gnndelete_b200.h"\n'
+                   'int main(void) {\n'
+                   '    printf("%d %zu %zu\\n", gd_version(), gd_csr_workspace_bytes(1000, 100), gd_row_mse_workspace_bytes(10));\n'
+                   '    return gd_last_error() == NULL;\n}\n')
+    exe = tmp_path / 'probe'
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run(['gcc', '-std=c99', str(src), '-I', os.path.dirname(HEADER), '-L', libdir, '-lgnndelete_b200',
+                        f'-Wl,-rpath,{libdir}', '-o', str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    version, csr_ws, mse_ws = r.stdout.split()
+    assert int(version) >= 100 and int(csr_ws) > 0 and int(mse_ws) > 0
