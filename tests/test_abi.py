@@ -155,3 +155,19 @@ def test_header_is_plain_c_and_links_from_c(tmp_path, lib):
     assert r.returncode == 0, r.stderr
     version, csr_ws, mse_ws = r.stdout.split()
     assert int(version) >= 100 and int(csr_ws) > 0 and int(mse_ws) > 0
+
+
+def test_argument_errors_are_reported_not_crashed(lib):
+    """Error behaviour of the boundary: invalid arguments come back as negative status codes with a message in
+    gd_last_error() before anything touches the device."""
+    vp = ctypes.c_void_p
+    one = vp(16)                                   # any non-NULL address: the calls below must fail before dereferencing it
+    rc = lib.gd_row_mse_fwd_bwd(None, 64, one, 64, 64, 10, one, one, 1.0, 1.0, 0.5, 0.5, None, 0, one, one, 1 << 20, None)
+    assert rc == -1 and b'gd_row_mse_fwd_bwd' in lib.gd_last_error()
+    rc = lib.gd_row_mse_fwd_bwd(one, 32, one, 64, 64, 10, one, one, 1.0, 1.0, 0.5, 0.5, None, 0, one, one, 1 << 20, None)
+    assert rc == -1 and b'leading dimension' in lib.gd_last_error()
+    rc = lib.gd_row_mse_fwd_bwd(one, 64, one, 64, 64, 10, one, one, 1.0, 1.0, 0.5, 0.5, None, 0, one, one, 8, None)
+    assert rc == -3 and b'workspace' in lib.gd_last_error()
+    rc = lib.gd_pair_decode(None, 64, 64, one, one, 5, None, None, one, None)
+    assert rc == -1 and b'gd_pair_decode' in lib.gd_last_error()
+    assert lib.gd_pair_decode(None, 64, 64, None, None, 0, None, None, None, None) == 0      # empty input: nothing to do
