@@ -226,6 +226,8 @@ class GNNDeleteTrainer(Trainer):
     def train(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
         if not hasattr(model, 'deletion1'):
             raise NotImplementedError('GNNDeleteTrainer trains the *Delete models (deletion1 / deletion2)')
+        if getattr(args, 'saint_minibatch', False):
+            return self.train_minibatch(model, data, optimizer, args)
         if type(model).__name__ != 'GCNDelete':
             # GATDelete / GINDelete: the same step body through the autograd modules (every layer is still one
             # of the CUDA kernels; only the orchestration differs from the fused GCN engine)
@@ -236,6 +238,87 @@ class GNNDeleteTrainer(Trainer):
         # is used for every graph.
         dense = logits_ori is not None and 'ogbl' not in self.args.dataset
         return self.train_edge_form(model, data, optimizer, args, logits_ori if dense else None)
+
+    def train_minibatch(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
+        """``train_minibatch`` (gnndelete.py:311-450) with its GraphSAINT random-walk batches - opt-in through
+        ``args.saint_minibatch`` (the default for every dataset is the whole-graph step above, which needs no sampling on
+        a 180 GB device).  Per batch (:347-409): forward on the batch's ``sdf`` edges with the batch's node masks passed
+        positionally, as many uniform negatives as the batch holds Df entries, ``loss_e = MSE(df logits, negative
+        logits)``, edge-form ``loss_l`` on the batch's ``sdf`` edges with ``u < v``, ``0.5 / 0.5`` mix (or the ablation
+        variants, :391-398), backward, ``optimizer.step()``.
+
+        Two things differ from the reference, both documented defects there: ``z_ori`` is the base model's embedding on
+        the ``dr_mask`` edges (the reference's ``get_embedding`` reads an unset ``data.dtrain_mask``);
+        a batch without Df entries (or without NI pairs) contributes 0 for that term instead of ``MSE(empty) = nan``.
+        Kept as in the reference unless ``args.saint_global_z_ori`` is set: the NI target indexes the FULL-graph
+        ``z_ori`` with the batch-LOCAL node ids (:379-383).  Composed of calls the GPU tests cover one by one (model
+        forward with positional masks, ``decode``, MSE, backward); the loop itself has not been run on a B200 yet."""
+        from .sampler import GraphSAINTRandomWalkSampler
+        F = torch.nn.functional
+        dev = torch.device(getattr(args, 'device', 'cuda'))     # the loop is device agnostic; the CUDA models are not
+        model = model.to(dev)
+        data = data.to(dev)
+        ei = data.train_pos_edge_index
+        with torch.no_grad():
+            z_ori = getattr(data, 'z_ori', None)
+            if z_ori is None:
+                z_ori = model.get_original_embeddings(data.x, ei[:, data.dr_mask].contiguous())
+        data.edge_index = ei                                                             # :331-332
+        data.node_id = torch.arange(data.x.shape[0], device=dev)
+        gen = torch.Generator(device=dev).manual_seed(getattr(args, 'random_seed', 42))
+        loader = GraphSAINTRandomWalkSampler(data, batch_size=args.batch_size, walk_length=2, num_steps=args.num_steps,
+                                             generator=gen)
+        unl = self.args.unlearning_model
+        global_ids = bool(getattr(args, 'saint_global_z_ori', False))
+        best_metric = 0
+        for epoch in range(args.epochs):
+            model.train()
+            sums, steps, t0 = torch.zeros(3, device=dev), 0, time.time()
+            for batch in loader:
+                bei = batch.edge_index
+                sdf_edges = bei[:, batch.sdf_mask].contiguous()
+                z = model(batch.x, sdf_edges, batch.sdf_node_1hop_mask, batch.sdf_node_2hop_mask)       # :352
+                neg_size = int(batch.df_mask.sum())                                                      # :356-360
+                zero = z.sum() * 0.0
+                if neg_size > 0:
+                    neg = torch.randint(0, z.size(0), (2, neg_size), generator=gen, device=dev)
+                    df_logits = model.decode(z, bei[:, batch.df_mask].contiguous(), neg)                # :362-363
+                    loss_e = F.mse_loss(df_logits[:neg_size], df_logits[neg_size:])
+                else:
+                    loss_e = zero
+                lower = sdf_edges[0] < sdf_edges[1]                                                      # :379-381
+                row, col = sdf_edges[0][lower], sdf_edges[1][lower]
+                if row.numel() > 0:
+                    src_r, src_c = (batch.node_id[row], batch.node_id[col]) if global_ids else (row, col)
+                    target = (z_ori[src_r] * z_ori[src_c]).sum(dim=-1)                                   # :383
+                    loss_l = F.mse_loss(model.decode(z, torch.stack([row, col])), target)              # :384-386
+                else:
+                    loss_l = zero
+                if 'ablation_random' in unl:                                                             # :390-398
+                    loss_l, loss = zero.detach(), loss_e
+                elif 'ablation_locality' in unl:
+                    loss_e, loss = zero.detach(), loss_l
+                else:
+                    loss = 0.5 * loss_e + 0.5 * loss_l
+                loss.backward()
+                optimizer.step()
+                optimizer.zero_grad()
+                sums += torch.stack([loss.detach(), loss_e.detach(), loss_l.detach()])
+                steps += 1
+            v = (sums / max(steps, 1)).tolist()
+            self.trainer_log['log'].append({'Epoch': epoch, 'train_loss': v[0], 'loss_r': v[1], 'loss_l': v[2],
+                                            'train_time': (time.time() - t0) / max(steps, 1)})
+            if (epoch + 1) % args.valid_freq == 0:                                                       # :416-443
+                valid_loss, dt_auc, dt_aup, df_auc, df_aup, _, _, valid_log = self.eval(model, data, 'val')
+                valid_log['epoch'] = epoch
+                self.trainer_log['log'].append(valid_log)
+                if dt_auc + df_auc > best_metric:
+                    best_metric = dt_auc + df_auc
+                    torch.save({'model_state': model.state_dict(), 'optimizer_state': optimizer.state_dict()},
+                               os.path.join(args.checkpoint_dir, 'model_best.pt'))
+        torch.save({'model_state': {k: v.to('cpu') for k, v in model.state_dict().items()},
+                    'optimizer_state': optimizer.state_dict()}, os.path.join(args.checkpoint_dir, 'model_final.pt'))
+        return model
 
     def _negatives(self, data, count, generator):
         """Uniform random pairs (``negative_sampling`` is randomised rejection sampling in
