@@ -67,7 +67,7 @@ class Trainer:
         per epoch new negatives, ``z = model(x, edges)``, ``BCEWithLogits(decode(z, edges, neg), labels)``, backward
         to EVERY parameter, ``optimizer.step()``.  Forward and backward run on the same kernels as the unlearning
         path (aggregation, tcgen05 GEMMs incl. their weight gradients, pair decode + incidence gather)."""
-        dev = torch.device('cuda')
+        dev = torch.device(getattr(args, 'device', 'cuda'))       # host loop is device agnostic; the CUDA models are not
         model = model.to(dev)
         data = data.to(dev)
         t_start = time.time()
@@ -722,7 +722,7 @@ class GNNDeleteNodeembTrainer(Trainer):
                              '(delete_gnn.py:221-226)')
         fct = get_nodeemb_loss_fct(self.args.loss_fct)
         alpha = self.args.alpha
-        dev = torch.device('cuda')
+        dev = torch.device(getattr(args, 'device', 'cuda'))       # host loop is device agnostic; the CUDA models are not
         model = model.to(dev)
         data = data.to(dev)
         ei = data.train_pos_edge_index
