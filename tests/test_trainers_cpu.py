@@ -110,3 +110,70 @@ def test_original_and_retrain_loops_match_the_oracle(tmp_path, mode):
     trainer.save_log()
     assert os.path.exists(os.path.join(args.checkpoint_dir, 'pred_proba.pt'))
     assert tuple(torch.load(os.path.join(args.checkpoint_dir, 'pred_proba.pt')).shape) == (shape.num_nodes, shape.num_nodes)
+
+
+def _sk_df_metrics(df_logit, dr_logit, samples):
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    lab = [0] * len(df_logit) + [1] * len(df_logit)
+    aucs = [roc_auc_score(lab, df_logit + dr_logit[i].tolist()) for i in samples]
+    aups = [average_precision_score(lab, df_logit + dr_logit[i].tolist()) for i in samples]
+    return sum(aucs) / len(aucs), sum(aups) / len(aups)
+
+
+def test_eval_matches_the_reference_formulas(tmp_path):
+    """`Trainer.eval` (base.py:229-305) with the oracle's GCNDelete: BCE on the sigmoid outputs (sic), Dt AUC / AP and the
+    resampled Df-vs-Dr AUC / AP against sklearn, which is what the reference calls."""
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    from gnndelete_b200.trainer import Trainer
+    shape, raw, df, data, neg = U.make_case('cora', 0.05)
+    om = U.oracle_model('gcn', shape, data)
+    tr = Trainer(_args(tmp_path, unlearning_model='gnndelete'))
+    loss, dt_auc, dt_aup, df_auc, df_aup, df_logit, _, log = tr.eval(om, data, 'val', num_df_resamples=6)
+    with torch.no_grad():
+        z = om(data.x, data.train_pos_edge_index[:, data.dr_mask])
+        prob = om.decode(z, data.val_pos_edge_index, data.val_neg_edge_index).sigmoid()
+        dr_logit = om.decode(z, data.train_pos_edge_index[:, data.dr_mask]).sigmoid()
+    label = torch.cat([torch.ones(data.val_pos_edge_index.shape[1]), torch.zeros(data.val_neg_edge_index.shape[1])])
+    assert loss == pytest.approx(torch.nn.functional.binary_cross_entropy_with_logits(prob, label).item(), rel=1e-6)
+    assert dt_auc == pytest.approx(roc_auc_score(label, prob), abs=1e-9)
+    assert dt_aup == pytest.approx(average_precision_score(label, prob), abs=1e-9)
+    assert len(df_logit) == data.directed_df_edge_index.shape[1] and tr.df_pos_edge.shape == (6, len(df_logit))
+    want_auc, want_aup = _sk_df_metrics(df_logit, dr_logit, tr.df_pos_edge)
+    assert df_auc == pytest.approx(want_auc, abs=1e-9) and df_aup == pytest.approx(want_aup, abs=1e-9)
+    assert log['val_df_logit_mean'] == pytest.approx(sum(df_logit) / len(df_logit), rel=1e-5)
+    # 'original': no Df leg (base.py:251-252)
+    tr2 = Trainer(_args(tmp_path, unlearning_model='original'))
+    out = tr2.eval(om, data, 'test')
+    assert out[3] != out[3] and out[5] == []
+
+
+def test_kg_eval_matches_the_reference_formulas(tmp_path):
+    """`KGTrainer.eval` (base.py:494-566) with the oracle's RGCNDelete: DistMult logits, Dt metrics on the RAW logits, the
+    Df leg on forward-direction retained triples."""
+    import dataclasses
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    from gnndelete_b200 import synthetic as S
+    from gnndelete_b200.trainer import KGTrainer
+    from oracle import unlearn as OU
+    net = 9
+    shape = dataclasses.replace(S.SHAPES['biokg'].scaled(0.002), num_edge_type=net)
+    raw = S.make_graph(shape, seed=42)
+    df = S.sample_df_mask(shape.num_edges, shape.num_deleted, seed=42)
+    data = OU.build_unlearning_data(raw, df, num_edge_type=net)
+    om = U.oracle_model('rgcn', shape, data, num_nodes=shape.num_nodes, num_edge_type=net)
+    tr = KGTrainer(_args(tmp_path, unlearning_model='gnndelete_nodeemb', gnn='rgcn', dataset='ogbl-biokg', num_edge_type=net))
+    loss, dt_auc, dt_aup, df_auc, df_aup, df_logit, pair, log = tr.eval(om, data, 'val', num_df_resamples=5)
+    with torch.no_grad():
+        z = om(data.x, data.edge_index[:, data.dr_mask], data.edge_type[data.dr_mask])
+        ei = torch.cat([data.val_pos_edge_index, data.val_neg_edge_index], -1)
+        logits = om.decode(z, ei, torch.cat([data.val_edge_type, data.val_edge_type]))
+        half = data.dr_mask[:data.dr_mask.shape[0] // 2]
+        dr_logit = om.decode(z, data.train_pos_edge_index[:, half], data.train_edge_type[half]).sigmoid()
+    label = torch.cat([torch.ones(data.val_pos_edge_index.shape[1]), torch.zeros(data.val_neg_edge_index.shape[1])])
+    assert loss == pytest.approx(torch.nn.functional.binary_cross_entropy_with_logits(logits, label).item(), rel=1e-6)
+    assert dt_auc == pytest.approx(roc_auc_score(label, logits), abs=1e-9)
+    assert dt_aup == pytest.approx(average_precision_score(label, logits), abs=1e-9)
+    want_auc, want_aup = _sk_df_metrics(df_logit, dr_logit, tr.df_pos_edge)
+    assert df_auc == pytest.approx(want_auc, abs=1e-9) and df_aup == pytest.approx(want_aup, abs=1e-9) and pair is None
+    with pytest.raises(NotImplementedError):
+        tr.train(om, data, None, None)
