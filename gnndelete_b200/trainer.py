@@ -60,7 +60,59 @@ class Trainer:
     def train(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
         """``Trainer.train`` (base.py:66-73).  Both reference loops (full-batch and the GraphSAINT mini-batch one
         for 'ogbl' datasets) run the step below; here the whole graph is always the batch."""
+        if getattr(args, 'saint_minibatch', False):
+            return self.train_minibatch(model, data, optimizer, args)
         return self.train_fullbatch(model, data, optimizer, args)
+
+    def train_minibatch(self, model, data, optimizer, args):
+        """``Trainer.train_minibatch`` (base.py:144-227), opt-in through ``args.saint_minibatch``: GraphSAINT random-walk
+        batches (``batch_size=args.batch_size, walk_length=2, num_steps=args.num_steps``) of the training graph, per batch
+        as many uniform negatives as the batch has edges (``negative_sampling``'s default count, :160-162), the BCE step,
+        evaluation on the whole graph every ``valid_freq`` epochs.  A batch without edges is skipped (BCE of nothing is
+        nan in the reference).  Host loop tested on the CPU with the oracle's models; not yet run on a B200."""
+        from .data import GraphData
+        from .sampler import GraphSAINTRandomWalkSampler
+        dev = torch.device(getattr(args, 'device', 'cuda'))
+        model = model.to(dev)
+        data = data.to(dev)
+        ei, _ = self._train_edges(data)
+        graph = GraphData(num_nodes=int(data.num_nodes), edge_index=ei, x=data.x)         # all the step reads (:148, :158-160)
+        gen = torch.Generator(device=dev).manual_seed(getattr(args, 'random_seed', 42))
+        loader = GraphSAINTRandomWalkSampler(graph, batch_size=args.batch_size, walk_length=2, num_steps=args.num_steps,
+                                             generator=gen)
+        t_start = time.time()
+        best_valid_loss, best_epoch = 1000000, 0
+        for epoch in range(args.epochs):
+            model.train()
+            total, steps = torch.zeros((), device=dev), 0
+            for batch in loader:
+                bei = batch.edge_index
+                if bei.shape[1] == 0:
+                    continue
+                z = model(batch.x, bei)
+                neg_edge_index = torch.randint(0, z.size(0), (2, bei.shape[1]), generator=gen, device=dev)
+                logits = model.decode(z, bei, neg_edge_index)
+                label = self.get_link_labels(bei, neg_edge_index)
+                loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, label)
+                loss.backward()
+                optimizer.step()
+                optimizer.zero_grad()
+                total += loss.detach()
+                steps += 1
+            self.trainer_log['log'].append({'epoch': epoch, 'train_loss': (total / max(steps, 1)).item()})
+            if (epoch + 1) % args.valid_freq == 0:
+                valid_loss, dt_auc, dt_aup, df_auc, df_aup, _, _, valid_log = self.eval(model, data, 'val')
+                valid_log['epoch'] = epoch
+                self.trainer_log['log'].append(valid_log)
+                if valid_loss < best_valid_loss:
+                    best_valid_loss, best_epoch = valid_loss, epoch
+                    torch.save({'model_state': model.state_dict(), 'optimizer_state': optimizer.state_dict()},
+                               os.path.join(args.checkpoint_dir, 'model_best.pt'))
+        self.trainer_log['training_time'] = time.time() - t_start
+        torch.save({'model_state': model.state_dict(), 'optimizer_state': optimizer.state_dict()},
+                   os.path.join(args.checkpoint_dir, 'model_final.pt'))
+        self.trainer_log['best_epoch'], self.trainer_log['best_valid_loss'] = best_epoch, best_valid_loss
+        return model
 
     def train_fullbatch(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
         """``Trainer.train_fullbatch`` (base.py:75-142) / ``RetrainTrainer.train_fullbatch`` (retrain.py:38-131):

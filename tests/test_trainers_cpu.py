@@ -177,3 +177,22 @@ def test_kg_eval_matches_the_reference_formulas(tmp_path):
     assert df_auc == pytest.approx(want_auc, abs=1e-9) and df_aup == pytest.approx(want_aup, abs=1e-9) and pair is None
     with pytest.raises(NotImplementedError):
         tr.train(om, data, None, None)
+
+
+@pytest.mark.parametrize('mode', ['original', 'retrain'])
+def test_original_minibatch_loop(tmp_path, mode):
+    """`Trainer.train_minibatch` (base.py:144-227) over GraphSAINT batches, opt-in: runs, learns, evaluates, checkpoints."""
+    import framework
+    shape, raw, df, data, _ = U.make_case('cora', 0.05)
+    args = _args(tmp_path, unlearning_model=mode, epochs=3, valid_freq=3, lr=0.01, saint_minibatch=True, batch_size=128,
+                 num_steps=4, dataset='ogbl-collab')
+    model = U.oracle_model('gcn', shape, data, delete=False)
+    w0 = {k: v.clone() for k, v in model.state_dict().items()}
+    trainer = framework.get_trainer(args)
+    trainer.train(model, data.clone(), torch.optim.Adam(model.parameters(), lr=args.lr), args)
+    steps = [l for l in trainer.trainer_log['log'] if 'train_loss' in l]
+    assert len(steps) == 3 and all(l['train_loss'] == l['train_loss'] and l['train_loss'] > 0 for l in steps)
+    assert any(not torch.equal(model.state_dict()[k], v) for k, v in w0.items())
+    assert len([l for l in trainer.trainer_log['log'] if 'val_dt_auc' in l]) == 1
+    for f in ('model_best.pt', 'model_final.pt'):
+        assert os.path.exists(os.path.join(args.checkpoint_dir, f)), f
