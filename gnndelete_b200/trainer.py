@@ -761,7 +761,80 @@ class GNNDeleteNodeembTrainer(Trainer):
     log_every = 100
 
     def train(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
+        if getattr(args, 'saint_minibatch', False):
+            return self.train_minibatch(model, data, optimizer, args)
         return self.train_fullbatch(model, data, optimizer, args, logits_ori, attack_model_all, attack_model_sub)
+
+    def train_minibatch(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
+        """``GNNDeleteNodeembTrainer.train_minibatch`` (gnndelete_nodeemb.py:352-494), opt-in through
+        ``args.saint_minibatch``: GraphSAINT random-walk batches; per batch the original embeddings of the BATCH graph
+        (all of its edges, :397-399), the Del forward on the batch's ``sdf`` edges with the batch's masks, uniform
+        negatives, the four node-embedding MSEs and - always - the ``both_layerwise`` schedule with the
+        ``[optimizer1, optimizer2]`` pair (:431-441).  A term over an empty selection contributes 0 (nan in the
+        reference).  Device tensor ops under autograd; host loop tested on the CPU with the oracle's models, not yet
+        run on a B200."""
+        from .sampler import GraphSAINTRandomWalkSampler
+        if not isinstance(optimizer, (list, tuple)) or len(optimizer) != 2:
+            raise ValueError('the mini-batch loop steps the [optimizer1, optimizer2] pair (gnndelete_nodeemb.py:431-441)')
+        F = torch.nn.functional
+        alpha = self.args.alpha
+        dev = torch.device(getattr(args, 'device', 'cuda'))
+        model = model.to(dev)
+        data = data.to(dev)
+        non_df = torch.ones(data.x.shape[0], dtype=torch.bool, device=dev)                  # :369-373
+        non_df[data.directed_df_edge_index.flatten().unique()] = False
+        data.sdf_node_1hop_mask_non_df_mask = data.sdf_node_1hop_mask & non_df
+        data.sdf_node_2hop_mask_non_df_mask = data.sdf_node_2hop_mask & non_df
+        data.edge_index = data.train_pos_edge_index                                          # :376-377
+        data.node_id = torch.arange(data.x.shape[0], device=dev)
+        gen = torch.Generator(device=dev).manual_seed(getattr(args, 'random_seed', 42))
+        loader = GraphSAINTRandomWalkSampler(data, batch_size=args.batch_size, walk_length=2, num_steps=args.num_steps,
+                                             generator=gen)
+
+        def mse(a, b):
+            return F.mse_loss(a, b) if a.numel() else a.sum() * 0.0
+
+        best_metric = 0
+        for epoch in range(args.epochs):
+            model.train()
+            sums, steps, t0 = torch.zeros(3, device=dev), 0, time.time()
+            for batch in loader:
+                bei = batch.edge_index
+                with torch.no_grad():                                                        # :397-399
+                    z1_ori, z2_ori = model.get_original_embeddings(batch.x, bei, return_all_emb=True)
+                z1, z2 = model(batch.x, bei[:, batch.sdf_mask].contiguous(), batch.sdf_node_1hop_mask,
+                               batch.sdf_node_2hop_mask, return_all_emb=True)               # :403
+                pos_edge = bei[:, batch.df_mask]                                             # :406-411
+                neg_edge = torch.randint(0, batch.x.shape[0], (2, pos_edge.shape[1]), generator=gen, device=dev)
+                m1, m2 = batch.sdf_node_1hop_mask_non_df_mask, batch.sdf_node_2hop_mask_non_df_mask
+                loss_r1 = mse(torch.cat([z1[pos_edge[0]], z1[pos_edge[1]]]), torch.cat([z1_ori[neg_edge[0]], z1_ori[neg_edge[1]]]))
+                loss_r2 = mse(torch.cat([z2[pos_edge[0]], z2[pos_edge[1]]]), torch.cat([z2_ori[neg_edge[0]], z2_ori[neg_edge[1]]]))
+                loss_l1 = mse(z1[m1], z1_ori[m1])                                            # :424-425
+                loss_l2 = mse(z2[m2], z2_ori[m2])
+                loss1 = alpha * loss_r1 + (1 - alpha) * loss_l1                              # :431-441
+                loss1.backward(retain_graph=True)
+                optimizer[0].step()
+                optimizer[0].zero_grad()
+                loss2 = alpha * loss_r2 + (1 - alpha) * loss_l2
+                loss2.backward(retain_graph=True)
+                optimizer[1].step()
+                optimizer[1].zero_grad()
+                sums += torch.stack([(loss1 + loss2).detach(), (loss_r1 + loss_r2).detach(), (loss_l1 + loss_l2).detach()])
+                steps += 1
+                del z1, z2, loss1, loss2
+            v = (sums / max(steps, 1)).tolist()
+            self.trainer_log['log'].append({'epoch': epoch, 'train_loss': v[0], 'train_loss_r': v[1], 'train_loss_l': v[2],
+                                            'train_time': (time.time() - t0) / max(steps, 1)})
+            if (epoch + 1) % args.valid_freq == 0:                                          # :464-487
+                valid_loss, dt_auc, dt_aup, df_auc, df_aup, _, _, valid_log = self.eval(model, data, 'val')
+                valid_log['epoch'] = epoch
+                self.trainer_log['log'].append(valid_log)
+                if dt_auc + df_auc > best_metric:
+                    best_metric = dt_auc + df_auc
+                    torch.save({'model_state': model.state_dict()}, os.path.join(args.checkpoint_dir, 'model_best.pt'))
+        torch.save({'model_state': {k: v.to('cpu') for k, v in model.state_dict().items()}},
+                   os.path.join(args.checkpoint_dir, 'model_final.pt'))
+        return model
 
     def train_fullbatch(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
         from .losses import RowMSEPlan, row_mse

@@ -196,3 +196,26 @@ def test_original_minibatch_loop(tmp_path, mode):
     assert len([l for l in trainer.trainer_log['log'] if 'val_dt_auc' in l]) == 1
     for f in ('model_best.pt', 'model_final.pt'):
         assert os.path.exists(os.path.join(args.checkpoint_dir, f)), f
+
+
+def test_nodeemb_minibatch_loop(tmp_path):
+    """`GNNDeleteNodeembTrainer.train_minibatch` (gnndelete_nodeemb.py:352-494) over GraphSAINT batches, opt-in."""
+    import framework
+    shape, raw, df, data, neg = U.make_case('cora', 0.05)
+    args = _args(tmp_path, epochs=2, valid_freq=2, saint_minibatch=True, batch_size=96, num_steps=3, dataset='ogbl-collab',
+                 unlearning_model='gnndelete_nodeemb', alpha=0.5)
+    model = U.oracle_model('gcn', shape, data)
+    for n, p in model.named_parameters():
+        if 'del' not in n:
+            p.requires_grad_(False)
+    w0 = [model.deletion1.deletion_weight.detach().clone(), model.deletion2.deletion_weight.detach().clone()]
+    optimizer = [torch.optim.Adam(model.deletion1.parameters(), lr=1e-3), torch.optim.Adam(model.deletion2.parameters(), lr=1e-3)]
+    trainer = framework.get_trainer(args)
+    trainer.train(model, data.clone(), optimizer, args)
+    rows = [l for l in trainer.trainer_log['log'] if 'train_loss' in l]
+    assert len(rows) == 2 and all(r['train_loss'] == r['train_loss'] and r['train_loss'] > 0 for r in rows)
+    assert all(r['train_loss'] == pytest.approx(0.5 * r['train_loss_r'] + 0.5 * r['train_loss_l'], rel=1e-5) for r in rows)
+    assert not torch.equal(model.deletion1.deletion_weight, w0[0]) and not torch.equal(model.deletion2.deletion_weight, w0[1])
+    assert len([l for l in trainer.trainer_log['log'] if 'val_dt_auc' in l]) == 1
+    with pytest.raises(ValueError):
+        trainer.train(model, data.clone(), optimizer[0], args)
