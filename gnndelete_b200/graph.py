@@ -425,23 +425,28 @@ class PlanCache:
     def get(self, edge_index, edge_type, key, builder):
         ident = (self._ident(edge_index), self._ident(edge_type), key)
         hit = self._by_id.get(ident)
-        if hit is not None:
-            return hit
+        # an identity hit only counts for the very tensor objects it was recorded for (kept alive by the entry): the
+        # caching allocator hands the address of a freed ``ei[:, mask]`` temporary to the next edge set of that shape
+        if hit is not None and hit[0] is edge_index and hit[1] is edge_type:
+            return hit[2]
         for ei, et, k, plan in self._entries:
             if k == key and ei.shape == edge_index.shape and ei.device == edge_index.device \
                     and torch.equal(ei, edge_index) and (et is None) == (edge_type is None) \
                     and (et is None or (et.shape == edge_type.shape and torch.equal(et, edge_type))):
-                self._by_id[ident] = plan
+                self._remember(ident, edge_index, edge_type, plan)
                 return plan
         plan = builder()
         self._entries.append((edge_index.clone(), None if edge_type is None else edge_type.clone(), key, plan))
         if len(self._entries) > self.max_entries:
             self._entries.pop(0)
             self._by_id.clear()
-        if len(self._by_id) > 64:
-            self._by_id.clear()
-        self._by_id[ident] = plan
+        self._remember(ident, edge_index, edge_type, plan)
         return plan
+
+    def _remember(self, ident, edge_index, edge_type, plan):
+        if len(self._by_id) >= 16:       # the identity level pins the keyed tensors: keep it small
+            self._by_id.clear()
+        self._by_id[ident] = (edge_index, edge_type, plan)
 
 
 _GLOBAL_CACHE = PlanCache()

@@ -284,6 +284,29 @@ class DenseNIPlan:
         return self.loss_sum / self.num_pairs
 
 
+class DenseNIFn(torch.autograd.Function):
+    """``weight * loss_l`` of :class:`DenseNIPlan` as a differentiable op (forward and ``dz`` come out of the same
+    kernel pass); second output: the unweighted ``loss_l`` for logging."""
+
+    @staticmethod
+    def forward(ctx, z, plan):
+        z = z.contiguous()
+        dz = torch.zeros_like(z)
+        loss_l = plan.forward_backward(z, dz).reshape(())
+        ctx.dz = dz
+        out = torch.stack([loss_l * plan.weight, loss_l])
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        return ctx.dz * gout[0], None
+
+
+def dense_ni_loss(z, plan):
+    out = DenseNIFn.apply(z, plan)
+    return out[0], out[1].detach()
+
+
 def row_mse_incidence(dst_r, src_r, rows_l, num_rows):
     """Destination-major incidence of the two node-embedding MSE terms (``gd_row_mse_fwd_bwd``).
 

@@ -150,14 +150,18 @@ class DeletionLayer(nn.Module):
         self._rows_cache = {}
 
     def rows(self, mask, num_nodes, device):
-        key = (mask.data_ptr(), tuple(mask.shape), mask._version, str(device))
+        """``(rows, complement)`` of ``mask``, cached per mask TENSOR: the entry keeps a reference to the tensor it was
+        built from and is only a hit for that very object at the same version - a freed per-batch mask whose storage
+        address is handed to the next batch's mask (GraphSAINT loops) is a different object and is recomputed."""
+        key = (mask.data_ptr(), tuple(mask.shape), str(device))
         hit = self._rows_cache.get(key)
-        if hit is None:
-            if len(self._rows_cache) > 8:
-                self._rows_cache.clear()
-            hit = rows_of(mask.to(device), num_nodes)
-            self._rows_cache[key] = hit
-        return hit
+        if hit is not None and hit[0] is mask and hit[1] == mask._version:
+            return hit[2]
+        if len(self._rows_cache) > 8:
+            self._rows_cache.clear()
+        out = rows_of(mask.to(device), num_nodes)
+        self._rows_cache[key] = (mask, mask._version, out)
+        return out
 
     def forward(self, x, mask=None):
         if mask is None:

@@ -225,6 +225,10 @@ class Trainer:
             path = os.path.join(self.args.checkpoint_dir, 'model_best.pt')
             if os.path.exists(path):
                 model.load_state_dict(torch.load(path, map_location=data.x.device)['model_state'])
+            else:
+                # the reference raises here (base.py:313-315); no best checkpoint means the validation metric never
+                # improved (e.g. a NaN df_auc): evaluate the final weights, but say so in the log
+                self.trainer_log['best_checkpoint_missing'] = True
         pred_all = 'ogbl' not in self.args.dataset
         loss, dt_auc, dt_aup, df_auc, df_aup, df_logit, logit_all_pair, test_log = self.eval(model, data, 'test', pred_all)
         self.trainer_log['dt_loss'] = loss
@@ -234,6 +238,10 @@ class Trainer:
         self.logit_all_pair = logit_all_pair
         self.trainer_log['df_auc'] = df_auc
         self.trainer_log['df_aup'] = df_aup
+        self.trainer_log['auc_sum'] = dt_auc + df_auc                     # base.py:327-330
+        self.trainer_log['aup_sum'] = dt_aup + df_aup
+        self.trainer_log['auc_gap'] = abs(dt_auc - df_auc)
+        self.trainer_log['aup_gap'] = abs(dt_aup - df_aup)
         return loss, dt_auc, dt_aup, df_auc, df_aup, df_logit, logit_all_pair, test_log
 
     def save_log(self):
@@ -280,16 +288,26 @@ class GNNDeleteTrainer(Trainer):
             raise NotImplementedError('GNNDeleteTrainer trains the *Delete models (deletion1 / deletion2)')
         if getattr(args, 'saint_minibatch', False):
             return self.train_minibatch(model, data, optimizer, args)
+        # reference dispatch (gnndelete.py:39-44): 'ogbl' datasets take the mini-batch loop (edge-form NI),
+        # everything else the full-batch loop whose NI term is the dense S_Df x S_Df block against the
+        # original model's pair logits (`logits_ori`, pred_proba.pt) - for every architecture.  Without
+        # `logits_ori` the edge form is used for every graph.
+        dense = logits_ori is not None and 'ogbl' not in self.args.dataset
         if type(model).__name__ != 'GCNDelete':
             # GATDelete / GINDelete: the same step body through the autograd modules (every layer is still one
             # of the CUDA kernels; only the orchestration differs from the fused GCN engine)
-            return self.train_autograd(model, data, optimizer, args)
-        # reference dispatch (gnndelete.py:39-44): 'ogbl' datasets take the mini-batch loop (edge-form NI),
-        # everything else the full-batch loop whose NI term is the dense S_Df x S_Df block against the
-        # original model's pair logits (`logits_ori`, pred_proba.pt).  Without `logits_ori` the edge form
-        # is used for every graph.
-        dense = logits_ori is not None and 'ogbl' not in self.args.dataset
+            return self.train_autograd(model, data, optimizer, args, logits_ori if dense else None)
         return self.train_edge_form(model, data, optimizer, args, logits_ori if dense else None)
+
+    def _loss_mix(self):
+        """Weight of ``loss_e`` in the objective (gnndelete.py:390-398): the ablation variants keep one term only;
+        otherwise the hard-coded 0.5 / 0.5 mix (``args.alpha`` is ignored there, SURVEY.md §10 #9)."""
+        unl = getattr(self.args, 'unlearning_model', '') or ''
+        if 'ablation_random' in unl:
+            return 1.0
+        if 'ablation_locality' in unl:
+            return 0.0
+        return 0.5
 
     def train_minibatch(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
         """``train_minibatch`` (gnndelete.py:311-450) with its GraphSAINT random-walk batches - opt-in through
@@ -379,7 +397,7 @@ class GNNDeleteTrainer(Trainer):
         return torch.randint(0, data.num_nodes, (2, count), generator=generator, device=data.x.device)
 
     def train_edge_form(self, model, data, optimizer, args, logits_ori=None):
-        dev = torch.device('cuda')
+        dev = self._cuda_device(args)
         model = model.to(dev)
         data = data.to(dev)
         n_df = int(data.df_mask.sum())
@@ -390,12 +408,29 @@ class GNNDeleteTrainer(Trainer):
             z_ori = getattr(data, 'z_ori', None)
             if z_ori is None and logits_ori is None:
                 z_ori = model.get_original_embeddings(data.x, data.train_pos_edge_index[:, data.dr_mask])
+        # the engine trains exactly the two Del weights with ONE Adam hyper-parameter set (delete_gnn.py:215-241):
+        # refuse an optimizer that holds anything else instead of silently ignoring it
+        want = {id(model.deletion1.deletion_weight), id(model.deletion2.deletion_weight)}
+        have = {id(p) for g in optimizer.param_groups for p in g['params']}
+        if have != want:
+            raise ValueError('GNNDeleteTrainer(GCNDelete) expects an optimizer over deletion1/deletion2.deletion_weight only')
         group = optimizer.param_groups[0]
+        for g in optimizer.param_groups[1:]:
+            if (g['lr'], g['betas'], g['eps']) != (group['lr'], group['betas'], group['eps']):
+                raise ValueError('per-group Adam hyper-parameters are not supported by the fused GCNDelete epoch')
         eng = GCNDeleteEngine(model, data, neg, z_ori=z_ori, lr=group['lr'], betas=group['betas'], eps=group['eps'],
-                              hoist_layer1=True, logits_ori=logits_ori, static_negatives=fixed_neg is not None)
+                              hoist_layer1=True, logits_ori=logits_ori, static_negatives=fixed_neg is not None,
+                              alpha=self._loss_mix())
+        self.engine = eng
         if getattr(args, 'capture_step', True) and logits_ori is None:
             # one cudaGraphLaunch per epoch; resampled negatives are written into the graph's staging buffer
-            eng.capture(warmup=2, dynamic_negatives=fixed_neg is None)
+            try:
+                eng.capture(warmup=2, dynamic_negatives=fixed_neg is None)
+            except Exception as exc:                            # capture is an optimisation: fall back to eager epochs
+                self.trainer_log['capture_error'] = repr(exc)
+                eng.graph = None
+                torch.cuda.synchronize()
+        self.trainer_log['captured_step'] = eng.graph is not None
         best_metric = 0
         ring = []
         t0 = time.time()
@@ -424,14 +459,21 @@ class GNNDeleteTrainer(Trainer):
         torch.save({'model_state': {k: v.to('cpu') for k, v in model.state_dict().items()},
                     'optimizer_state': self._optimizer_state(optimizer, eng)},
                    os.path.join(args.checkpoint_dir, 'model_final.pt'))
-        return eng
+        return model
 
-    def train_autograd(self, model, data, optimizer, args):
+    @staticmethod
+    def _cuda_device(args):
+        dev = torch.device(getattr(args, 'device', None) or 'cuda')
+        if dev.type != 'cuda':
+            raise RuntimeError('gnndelete_b200 has no CPU path: args.device must be a CUDA device')
+        return dev
+
+    def train_autograd(self, model, data, optimizer, args, logits_ori=None):
         """``train_minibatch``'s step body (gnndelete.py:347-409) on the whole graph for any *Delete model:
         forward with positional masks (:352), fused decode + DEC + edge-form NI (`EdgeLossFn`), backward
         through the conv / Del autograd Functions, ``optimizer.step()`` (the caller's optimizer)."""
-        from .losses import EdgeLossPlan, edge_loss
-        dev = torch.device('cuda')
+        from .losses import DenseNIPlan, EdgeLossPlan, dense_ni_loss, edge_loss
+        dev = self._cuda_device(args)
         model = model.to(dev)
         data = data.to(dev)
         ei = data.train_pos_edge_index
@@ -445,8 +487,16 @@ class GNNDeleteTrainer(Trainer):
             if z_ori is None:
                 z_ori = model.get_original_embeddings(data.x, ei[:, data.dr_mask].contiguous())
         ni = ei_sdf[:, ei_sdf[0] < ei_sdf[1]]                                   # gnndelete.py:379-381
+        alpha = self._loss_mix()
+        dense = None
+        if logits_ori is not None:
+            # train_fullbatch's NI term (gnndelete.py:163-193, 239-241): the dense S2 x S2 sigmoid block against the
+            # original model's pair logits, for every architecture - the edge-form pairs are dropped
+            dense = DenseNIPlan(data.sdf_node_2hop_mask, ei[:, data.df_mask], logits_ori, data.num_nodes,
+                                model.deletion2.dim, weight=1.0 - alpha)
+            ni = ni[:, :0]
         plan = EdgeLossPlan(ei[:, data.df_mask], neg, ni, data.num_nodes, z_ori=z_ori.contiguous(),
-                            alpha=getattr(args, 'alpha', 0.5), static_negatives=fixed_neg is not None)
+                            alpha=alpha, static_negatives=fixed_neg is not None)
         # The step (forward, fused loss, backward through the autograd Functions, Adam on the Del weights) is
         # captured into ONE CUDA graph: on PubMed-sized graphs the ~40 launches of a step are host-launch bound
         # when issued from Python.  Adam runs through gd_adam_step (device-side step counter) on the optimizer's
@@ -460,6 +510,9 @@ class GNNDeleteTrainer(Trainer):
         def step():
             z = model(data.x, ei_sdf, data.sdf_node_1hop_mask, data.sdf_node_2hop_mask)       # :352
             loss, loss_r, loss_l = edge_loss(z, plan)
+            if dense is not None:                         # loss = alpha * loss_r  (no NI pairs)  + (1 - alpha) * dense NI
+                wl, loss_l = dense_ni_loss(z, dense)
+                loss = loss + wl
             loss.backward()
             for p, st in zip(params, state):
                 ops.adam_step(p.data, p.grad, st['m'], st['v'], st['step'], group['lr'], group['betas'][0],
