@@ -9,9 +9,12 @@ set (BOTH conv layers recomputed — hoisting the frozen layer-1 conv is reporte
 separately as ``value_hoisted``) -> decode on (Df, supplied negatives) ->
 0.5*MSE(pos,neg) + 0.5*NI(edge form) -> backward to deletion{1,2}.deletion_weight -> Adam.
 
-N > 1: the Collab-shaped graph fits one GPU ("small graphs stay on one GPU"), so ranks
-run independent replicas (different seeds = different deletion requests), no data-path
-collective; value = all ranks' epochs / max-over-ranks device time ("scaling": "weak").
+N > 1: the Collab-shaped graph fits one GPU ("small graphs stay on one GPU"), so for the headline ``value`` the ranks
+run independent replicas (different seeds = different deletion requests), no data-path collective ("scaling": "weak").
+The line ADDITIONALLY carries a ``partitioned`` block: BASELINE config 5 (10 M nodes / 200 M edges) row-partitioned
+over the same N ranks (gnndelete_b200/dist.py, NCCL halo exchange), parity-checked against the single-GPU engine on a
+1/16-scale graph before it is timed, with the one-GPU point of the same engine measured in the same invocation on
+rank 0, the efficiency, the halo bytes and the device time inside each collective.
 """
 from __future__ import annotations
 
@@ -22,6 +25,7 @@ import statistics
 import subprocess
 import sys
 import time
+import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -30,8 +34,10 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 METRIC = 'Del-training epochs/s on OGB-Collab shape'
-NCU_DRAM_BYTES_SPMM_L2 = 108_790_272 + 45_636_864     # profiles/r1_spmm_batched_ncu_full.md (dram read + write, F=64 launch)
 UNIT = 'epochs/s'
+ARITH = ('fp32 storage and accumulation; dense contractions on tcgen05 tensor cores as 3xTF32 (hi/lo operand split, '
+         'fp32-level accuracy, 1e-5 vs the fp64 oracle); aggregation / loss kernels plain fp32')
+NCU_TRAFFIC_JSON = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
 
 
 # --------------------------------------------------------------------------- utils
@@ -42,6 +48,17 @@ def load_peaks():
             p = json.load(f)
         return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def measured_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch group from the last committed `ncu --set full` capture
+    (written by tools/ncu_traffic.py next to the commit it was taken at); None when there is no capture."""
+    try:
+        with open(NCU_TRAFFIC_JSON) as f:
+            t = json.load(f)
+        return t['kernels'][key]['dram_bytes'], {'commit': t.get('commit'), 'report': t.get('report')}
+    except (OSError, KeyError, ValueError):
+        return None, None
 
 
 class ClockSampler:
@@ -113,16 +130,15 @@ def max_over_ranks(value, world, dev):
 
 
 # ------------------------------------------------------------------------ workload
-def build_case(shape, seed, dev):
+def build_case(shape, seed, dev, gen_device='cpu', with_eval_edges=True):
     """Synthetic inputs + masks (CUDA mask pipeline) + random-init model + z_ori."""
-    import types
     from gnndelete_b200 import synthetic as S
     from gnndelete_b200 import masks as MK
     from gnndelete_b200 import models as M
-    raw = S.make_graph(shape, seed=seed, device='cpu').to(dev)
-    df = S.sample_df_mask(shape.num_edges, shape.num_deleted, seed=seed, device='cpu').to(dev)
+    raw = S.make_graph(shape, seed=seed, device=gen_device, with_eval_edges=with_eval_edges).to(dev)
+    df = S.sample_df_mask(shape.num_edges, shape.num_deleted, seed=seed, device=gen_device).to(dev)
     data = MK.build_unlearning_data(raw, df)
-    neg = S.supplied_negatives(shape.num_nodes, int(data.df_mask.sum()), seed=seed + 1, device='cpu').to(dev)
+    neg = S.supplied_negatives(shape.num_nodes, int(data.df_mask.sum()), seed=seed + 1, device=gen_device).to(dev)
     args = types.SimpleNamespace(in_dim=shape.in_dim, hidden_dim=shape.hidden_dim, out_dim=shape.out_dim)
     torch.manual_seed(seed)
     model = M.GCNDelete(args, data.sdf_node_1hop_mask, data.sdf_node_2hop_mask).to(dev)
@@ -131,13 +147,30 @@ def build_case(shape, seed, dev):
     return data, neg, model, z_ori
 
 
-def spmm_algo_bytes(n, nnz, feat):
-    """rowptr + col + deg^-1/2 + read N*F + write N*F, fp32, int32 ids."""
-    return 4 * (n + 1) + 4 * nnz + 4 * n + 4 * n * feat + 4 * n * feat
+# SURVEY.md §8(d) algorithmic (compulsory) bytes: every operand once, int32 ids, fp32 elements
+def spmm_algo_bytes(n, nnz, feat, src_elt=4):
+    """rowptr + col + deg^-1/2 + read N*F + write N*F."""
+    return 4 * (n + 1) + 4 * nnz + 4 * n + src_elt * n * feat + 4 * n * feat
 
 
-def time_kernels(eng, steps):
-    """Eager epochs with CUDA events around each aggregation launch (on the launch stream)."""
+def gemm_algo_bytes(m, k, n, gathered):
+    return (4 * m if gathered else 0) + 4 * m * (k + n) + 4 * k * n
+
+
+def loss_algo_bytes(n_df, n_ni, n, out):
+    """decode + DEC + NI(edge form) fwd+bwd with precomputed target logits: pair ids, targets, z read once, dz written."""
+    p = 2 * n_df + n_ni
+    return 8 * p + 4 * n_ni + 4 * n * out + 4 * n * out
+
+
+def khop_algo_bytes(e, n):
+    """2 calls (2 hops + 1 hop) over E directed edges incl. the reference's bool-byte outputs."""
+    return (2 + 1) * 8 * e + 2 * 8 * e + 2 * e // 8 + 5 * n // 8 + 2 * e + 2 * n
+
+
+def time_kernels(eng, data, steps):
+    """Eager epochs with CUDA events around each launch group (on the launch stream); ms averages."""
+    from gnndelete_b200 import masks as MK
     from gnndelete_b200 import ops
     st = torch.cuda.current_stream()
     rec = {}
@@ -148,29 +181,33 @@ def time_kernels(eng, steps):
         rec.setdefault(name, []).append((a, b))
 
     m, p = eng.model, eng.plan
+    W1, W2 = m.conv1.lin.weight.detach(), m.conv2.lin.weight.detach()
     for _ in range(steps):
-        ops.gemm_rows(eng.x, m.conv1.lin.weight.detach(), True, out=eng.h0, out_scale=p.dinv)
+        timed('gemm_xw1', lambda: ops.gemm_rows(eng.x, W1, True, out=eng.h0, out_scale=p.dinv))
         timed('spmm_l1_f128', lambda: ops.spmm(p.fwd, eng.h0, out=eng.a1, row_scale=p.dinv, bias=m.conv1.bias.detach()))
-        eng._layer1_done = True
-        hoist, eng.hoist = eng.hoist, True
-        # forward with the layer-2 aggregation bracketed
         w1 = m.deletion1.deletion_weight.detach(); w2 = m.deletion2.deletion_weight.detach()
-        ops.gemm_rows(eng.a1, w1, False, out=eng.x1, rows=eng.rows1, relu_mask_out=eng.x1_bits)
+        timed('gemm_del1', lambda: ops.gemm_rows(eng.a1, w1, False, out=eng.x1, rows=eng.rows1, relu_mask_out=eng.x1_bits))
         ops.copy_rows(eng.a1, eng.x1, eng.comp1)
-        ops.gemm_rows(eng.x1, m.conv2.lin.weight.detach(), True, out=eng.h1, out_scale=p.dinv, relu_in=True)
+        timed('gemm_xw2', lambda: ops.gemm_rows(eng.x1, W2, True, out=eng.h1, out_scale=p.dinv, relu_in=True))
         timed('spmm_l2_f64', lambda: ops.spmm(p.fwd, eng.h1, out=eng.a2, row_scale=p.dinv, bias=m.conv2.bias.detach()))
-        ops.gemm_rows(eng.a2, w2, False, out=eng.z, rows=eng.rows2)
+        timed('gemm_del2', lambda: ops.gemm_rows(eng.a2, w2, False, out=eng.z, rows=eng.rows2))
         ops.copy_rows(eng.a2, eng.z, eng.comp2)
-        timed('edge_loss_fwd', lambda: eng.loss.forward(eng.z))
-        timed('edge_loss_bwd_spmm', lambda: eng.loss.backward(eng.z, out=eng.dz))
-        ops.gemm_tn_rows(eng.a2, eng.dz, rows=eng.rows2, out=eng.params[1].grad)
-        ops.gemm_rows(eng.dz, w2, True, out=eng.da2, rows=eng.rows2)
+        timed('loss_fwd_bwd', lambda: (eng.loss.forward(eng.z, dz_out=eng.dz), eng.loss.backward(eng.z, out=eng.dz)))
+        timed('gemm_dw2', lambda: ops.gemm_tn_rows(eng.a2, eng.dz, rows=eng.rows2, out=eng.params[1].grad))
+        timed('gemm_da2', lambda: ops.gemm_rows(eng.dz, w2, True, out=eng.da2, rows=eng.rows2))
         ops.copy_rows(eng.dz, eng.da2, eng.comp2)
         timed('spmm_bwd_f64', lambda: ops.spmm(p.bwd, eng.da2, out=eng.dh1, col_scale=p.dinv))
-        ops.gemm_rows(eng.dh1, m.conv2.lin.weight.detach(), False, out=eng.dx1, rows=eng.rows1,
-                      out_scale=p.dinv, gate=None if eng.bitmask else eng.x1, gate_bits=eng.x1_bits)
-        ops.gemm_tn_rows(eng.a1, eng.dx1, rows=eng.rows1, out=eng.params[0].grad)
-        eng.hoist = hoist
+        timed('gemm_dx1', lambda: ops.gemm_rows(eng.dh1, W2, False, out=eng.dx1, rows=eng.rows1, out_scale=p.dinv,
+                                                gate=None if eng.bitmask else eng.x1, gate_bits=eng.x1_bits))
+        timed('gemm_dw1', lambda: ops.gemm_tn_rows(eng.a1, eng.dx1, rows=eng.rows1, out=eng.params[0].grad))
+    # deletion-mask construction (setup path, A9): the 2-hop + 1-hop k_hop masks of delete_gnn.py:128-151 on the DIRECTED
+    # edge list (rebuilt here from the symmetrised one); each call ends with a host read of its status word, so the
+    # bracket includes one launch gap
+    ei = data.train_pos_edge_index
+    keep = ei[0] < ei[1]
+    dir_ei, seed = ei[:, keep].contiguous(), data.df_mask[keep].contiguous()
+    for _ in range(min(steps, 5)):
+        timed('khop_masks_2hop_1hop', lambda: (MK.khop_masks(dir_ei, seed, 2, data.num_nodes), MK.khop_masks(dir_ei, seed, 1, data.num_nodes)))
     torch.cuda.synchronize()
     return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in rec.items()}
 
@@ -192,7 +229,6 @@ def timed_epochs(eng, steps, world):
 def cpu_epoch_runner(shape, seed=42):
     """The reference's CPU path for the same epoch: the oracle restatement executed with
     PyG's op sequence (eager PyTorch fp32 autograd) on all host cores."""
-    import types
     from gnndelete_b200 import synthetic as S
     from oracle import models as OM
     from oracle import unlearn as OU
@@ -264,7 +300,7 @@ def run_reference(args, shape):
     sample = (f'{args.steps} full epochs of the {shape.name} workload (whole graph, no sub-sampling)' +
               (f'; {requested} requested, stopped at the {args.cpu_budget_s:.0f} s CPU budget' if done < requested else ''))
     line = {
-        'impl': 'reference', 'metric': METRIC if shape.name.startswith('collab') else f'Del-training epochs/s on {shape.name} shape',
+        'impl': 'reference', 'metric': metric_name(shape),
         'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -272,9 +308,14 @@ def run_reference(args, shape):
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'note': 'PyTorch-Geometric is not installable here; the reference arm is the oracle restatement run with '
-                "PyG's op sequence (eager PyTorch CPU autograd), parity unpinned",
+                "PyG's op sequence (eager PyTorch CPU autograd) on ONE host process with all host threads, parity "
+                'unpinned; at N > 1 it is still one process (the N-GPU native line is N replicas)',
     }
     print(json.dumps(line), flush=True)
+
+
+def metric_name(shape):
+    return METRIC if shape.name.startswith('collab') else f'Del-training epochs/s on {shape.name} shape'
 
 
 def workload_config(shape, where=None):
@@ -288,71 +329,132 @@ def workload_config(shape, where=None):
         'epoch': ('fwd + original embeddings + two backward passes + two Adam steps' if shape.gnn == 'rgcn' else
                   'fwd (both convs recomputed) + decode + DEC/NI loss + bwd to Del weights + Adam'),
         'l2': 'per-epoch working set ~0.9 GB > 126 MB L2, no flush between steps',
+        'arith': ARITH,
     }
 
 
 # ---------------------------------------------------------- row-partitioned config
-def run_partitioned(args, shape, rank, local, world, dev, lib):
-    """BASELINE config 5: GCNDelete on the power-law graph, 1-D row partitioned over the ranks with an
-    NCCL all-gather halo exchange per layer (strong scaling: the graph is fixed, ranks split its rows).
-    The graph is generated on the device with the same seed on every rank."""
-    import types
-    from gnndelete_b200 import masks as MK
+def _partition_parity(rank, world, dev, wire, scale=1.0 / 16):
+    """Before anything is timed: the partitioned engine over the N ranks against the single-GPU engine on a
+    1/16-scale power-law graph - losses and both Del gradients after the first step, weights after 3 steps."""
+    import dataclasses
     from gnndelete_b200 import models as M
     from gnndelete_b200 import synthetic as S
     from gnndelete_b200.dist import PartitionedGCNDeleteEngine
     from gnndelete_b200.engine import GCNDeleteEngine
-    t_setup = time.perf_counter()
-    raw = S.make_graph(shape, seed=42, device=dev, with_eval_edges=False)
-    df = S.sample_df_mask(shape.num_edges, shape.num_deleted, seed=42, device=dev)
-    data = MK.build_unlearning_data(raw, df)
-    del raw
-    neg = S.supplied_negatives(shape.num_nodes, int(data.df_mask.sum()), seed=43, device=dev)
+    shape = S.SHAPES['powerlaw10m'].scaled(scale)
+    data, neg, model, z_ori = build_case(shape, 42, dev, gen_device=dev, with_eval_edges=False)
+    init = {k: v.clone() for k, v in model.state_dict().items()}
     margs = types.SimpleNamespace(in_dim=shape.in_dim, hidden_dim=shape.hidden_dim, out_dim=shape.out_dim)
-    torch.manual_seed(42)
-    model = M.GCNDelete(margs, data.sdf_node_1hop_mask, data.sdf_node_2hop_mask).to(dev)
-    with torch.no_grad():
-        z_ori = model.get_original_embeddings(data.x, data.train_pos_edge_index[:, data.dr_mask])
+    m2 = M.GCNDelete(margs, data.sdf_node_1hop_mask, data.sdf_node_2hop_mask).to(dev)
+    m2.load_state_dict(init)
+    part = PartitionedGCNDeleteEngine(model, data, neg, z_ori, wire=wire, world=world, rank=rank)
+    one = GCNDeleteEngine(m2, data, neg, z_ori=z_ori, hoist_layer1=False, static_negatives=True)
+    part.forward(); part.backward()
+    one.forward_backward()
+
+    def rel(a, b):
+        return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+    err = {'losses': rel(part.losses, one.loss.losses),
+           'dW_del1': rel(model.deletion1.deletion_weight.grad, m2.deletion1.deletion_weight.grad),
+           'dW_del2': rel(model.deletion2.deletion_weight.grad, m2.deletion2.deletion_weight.grad)}
+    part.adam_step(); one.adam_step()
+    for _ in range(2):
+        part.epoch(); one.epoch()
+    err['W_del1_after_3_steps'] = rel(model.deletion1.deletion_weight, m2.deletion1.deletion_weight)
+    err['W_del2_after_3_steps'] = rel(model.deletion2.deletion_weight, m2.deletion2.deletion_weight)
+    tol = 2e-2 if wire == 'bf16' else 1e-5
+    ok = all(v <= tol for v in err.values())
+    out = {'graph': f'{shape.name}: {shape.num_nodes} nodes / {shape.num_edges} directed edges', 'tolerance': tol,
+           'wire': wire, 'rel_err_vs_single_gpu_engine': err, 'ok': ok}
+    del part, one, data, model, m2
     from gnndelete_b200 import graph as G
+    G._GLOBAL_CACHE = G.PlanCache()
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_partitioned(args, shape, rank, local, world, dev, lib, wire='bf16', one_gpu_point=True):
+    """BASELINE config 5: GCNDelete on the power-law graph, 1-D row partitioned over the ranks (strong scaling: the
+    graph is fixed, ranks split its rows).  The graph is generated on the device with the same seed on every rank.
+    Returns the ``partitioned`` block (identical on every rank)."""
+    from gnndelete_b200 import graph as G
+    from gnndelete_b200.dist import PartitionedGCNDeleteEngine
+    steps = max(3, min(args.steps, args.partition_steps))
+    warm = max(3, min(args.warmup, 5))
+    parity = _partition_parity(rank, world, dev, wire) if (world > 1 and shape.num_nodes >= 1_000_000) else None
+    if parity is not None and not parity['ok']:
+        raise RuntimeError(f'partitioned epoch disagrees with the single-GPU engine: {parity}')
+    t_setup = time.perf_counter()
+    data, neg, model, z_ori = build_case(shape, 42, dev, gen_device=dev, with_eval_edges=False)
     G._GLOBAL_CACHE = G.PlanCache()                      # drop the dr-edge plan before the engines allocate
     torch.cuda.empty_cache()
-    if world > 1:
-        eng = PartitionedGCNDeleteEngine(model, data, neg, z_ori)
-    else:
-        eng = GCNDeleteEngine(model, data, neg, z_ori=z_ori, hoist_layer1=False)
-    setup_s = time.perf_counter() - t_setup
-    eng.epoch()                                       # first epoch: also builds the batch plans (one-time launches)
-    c0 = lib.gd_launch_count()
-    eng.epoch()
-    launches = lib.gd_launch_count() - c0
-    for _ in range(args.warmup):
+    init = {k: v.clone() for k, v in model.state_dict().items()}
+    n = shape.num_nodes
+    nnz = int(data.sdf_mask.sum()) + n
+
+    def measure(w, r, group_world):
+        """epochs/s of the partitioned engine over ``w`` ranks (w == 1: no process group, this rank alone)."""
+        model.load_state_dict(init)
+        eng = PartitionedGCNDeleteEngine(model, data, neg, z_ori, wire=wire, world=w, rank=r)
+        torch.cuda.synchronize()
+        eng.epoch()                                       # first epoch: also builds the batch plans (one-time launches)
+        c0 = lib.gd_launch_count()
         eng.epoch()
+        launches = lib.gd_launch_count() - c0
+        for _ in range(warm):
+            eng.epoch()
+        eng.comm_events = []
+        ms = timed_epochs(eng, steps, group_world)
+        comm = eng.comm_ms()
+        eng.comm_events = None
+        ms = max_over_ranks(ms, group_world, dev)
+        out = {'ms_per_step': ms / steps, 'value': steps / (ms / 1e3), 'launches_per_epoch': int(launches),
+               'comm_ms_per_epoch': {k: v / steps for k, v in comm.items()}, 'losses_last': eng.losses.tolist(),
+               'halo_bytes_per_epoch_per_rank_received': int(eng.halo_bytes_per_epoch * (w - 1) / w) if w > 1 else 0,
+               'rows_per_rank': [b[1] - b[0] for b in eng.plan.bounds]}
+        del eng
+        torch.cuda.empty_cache()
+        return out
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms = max_over_ranks(timed_epochs(eng, args.steps, world), world, dev)
+    res = measure(world, rank, world)
     clocks = sampler.stop() if rank == 0 else None
-    losses = (eng.losses if world > 1 else eng.loss.losses).tolist()
-    n = shape.num_nodes
-    nnz = int(data.sdf_mask.sum()) + n
-    halo = 3 * 4 * shape.out_dim * n + 4 * shape.hidden_dim * n          # bytes all-gathered per epoch (H0, H1, z, dA2)
-    line = {
-        'metric': 'Del-training epochs/s, row-partitioned power-law graph', 'value': args.steps / (ms / 1e3), 'unit': UNIT,
-        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
-        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'GCNDelete edge unlearning, {shape.name} power-law graph ({n} nodes / {shape.num_edges} '
-                               f'directed edges / {shape.num_deleted} deleted), 128->128->64, 1-D row partition over '
-                               f'{world} GPU(s), NCCL all-gather halo exchange, both convs recomputed',
-                   'nnz_message_passing': nnz, 'halo_bytes_per_epoch_total': halo if world > 1 else 0,
-                   'l2': 'feature matrices (>= 0.25 GB each) exceed the 126 MB L2, no flush'},
-        'gpu_launches': int(launches * args.steps), 'launches_per_epoch': int(launches), 'clocks': clocks,
-        'losses_last': losses, 'setup_s': setup_s, 'parallelism': f'row-partition x{world}',
+    setup_s = time.perf_counter() - t_setup
+    block = {
+        'workload': f'GCNDelete edge unlearning, {shape.name} power-law graph ({n} nodes / {shape.num_edges} directed edges / '
+                    f'{shape.num_deleted} deleted), 128->128->64, 1-D row partition (work-balanced row blocks) over '
+                    f'{world} GPU(s), NCCL all-gather halo exchange of H1 / z / dA2 in {wire} (H0 exchanged once at setup: '
+                    f'frozen, input-constant), layer-1 aggregation still run every epoch',
+        'metric': 'Del-training epochs/s, row-partitioned power-law graph', 'unit': UNIT, 'scaling': 'strong',
+        'n_gpus': world, 'comm_nranks_seen': world, 'steps': steps, 'warmup': warm, 'wire': wire,
+        'dtype': 'bf16-gather (fp32 accumulate), tolerance 2e-2' if wire == 'bf16' else 'f32',
+        'value': res['value'], 'ms_per_step': res['ms_per_step'], 'nnz_message_passing': nnz,
+        'launches_per_epoch': res['launches_per_epoch'], 'comm_ms_per_epoch': res['comm_ms_per_epoch'],
+        'halo_bytes_per_epoch_per_rank_received': res['halo_bytes_per_epoch_per_rank_received'],
+        'rows_per_rank': res['rows_per_rank'], 'losses_last': res['losses_last'], 'parity': parity, 'clocks': clocks,
+        'setup_s': setup_s,
     }
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
+    if res['comm_ms_per_epoch']:
+        lim = max(res['comm_ms_per_epoch'].items(), key=lambda kv: kv[1])
+        block['limiting_collective'] = {'name': lim[0], 'ms_per_epoch': lim[1],
+                                        'note': 'device time on rank 0 between the events bracketing the call; includes waiting for the slowest rank'}
+    if world > 1 and one_gpu_point:
+        # the one-GPU point of the same engine (same kernels, same arithmetic), on rank 0's GPU, same invocation
+        if rank == 0:
+            one = measure(1, 0, 1)
+            t = torch.tensor([one['value']], dtype=torch.float64, device=dev)
+        else:
+            t = torch.zeros(1, dtype=torch.float64, device=dev)
         import torch.distributed as dist
-        dist.destroy_process_group()
+        dist.broadcast(t, 0)
+        block['one_gpu_value'] = float(t.item())
+        block['efficiency'] = block['value'] / (world * block['one_gpu_value'])
+        block['speedup_vs_one_gpu'] = block['value'] / block['one_gpu_value']
+    return block
 
 
 # --------------------------------------------------------------------------- main
@@ -367,6 +469,11 @@ def main():
     ap.add_argument('--cpu-epochs', type=int, default=4, help='bounded CPU-baseline sample (epochs)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-budget-s', type=float, default=150.0, help='time cap of the --impl reference loop')
+    ap.add_argument('--wire', default='bf16', choices=['bf16', 'fp32'], help='halo format of the row-partitioned epoch')
+    ap.add_argument('--partition-steps', type=int, default=10, help='timed epochs of the row-partitioned block')
+    ap.add_argument('--partition-workload', default='powerlaw10m')
+    ap.add_argument('--partition-scale', type=float, default=1.0)
+    ap.add_argument('--no-partitioned', action='store_true', help='N > 1: skip the row-partitioned config-5 block')
     args = ap.parse_args()
     from gnndelete_b200 import synthetic as S
     shape = S.SHAPES[args.workload].scaled(args.scale)
@@ -388,7 +495,19 @@ def main():
     lib = _lib.load()
     from gnndelete_b200.engine import GCNDeleteEngine
     if args.workload.startswith('powerlaw'):
-        return run_partitioned(args, shape, rank, local, world, dev, lib)
+        # the partitioned config on its own (any N, incl. 1): prints the block as the line
+        block = run_partitioned(args, shape, rank, local, world, dev, lib, wire=args.wire, one_gpu_point=False)
+        if rank == 0:
+            line = {'metric': block['metric'], 'value': block['value'], 'unit': UNIT, 'n_gpus': world, 'steps': block['steps'],
+                    'warmup': block['warmup'], 'ms_per_step': block['ms_per_step'], 'higher_is_better': True,
+                    'scaling': 'strong', 'vs_baseline': None, 'dtype': block['dtype'], 'data': 'synthetic',
+                    'config': {'workload': block['workload'], 'arith': ARITH, 'l2': 'feature matrices (>= 0.25 GB each) exceed the 126 MB L2, no flush'},
+                    'gpu_launches': block['launches_per_epoch'] * block['steps'], 'partitioned': block, 'clocks': block['clocks']}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
 
     data, neg, model, z_ori = build_case(shape, 42 + rank, dev)
     n = shape.num_nodes
@@ -419,43 +538,64 @@ def main():
     for _ in range(args.warmup):
         eng_h.epoch()
     ms_h = max_over_ranks(timed_epochs(eng_h, args.steps, world), world, dev)
+    del eng_h
 
     # ---- per-kernel durations (eager launches, events on the launch stream) -> roofline
     peak, peak_src = load_peaks()
     eng_k = GCNDeleteEngine(model, data, neg, z_ori=z_ori, hoist_layer1=False, static_negatives=True)
-    time_kernels(eng_k, 3)
-    kt = time_kernels(eng_k, min(args.steps, 50))
-    b64 = spmm_algo_bytes(n, nnz, shape.out_dim)
-    b128 = spmm_algo_bytes(n, nnz, shape.hidden_dim)
-    achieved = b64 / (kt['spmm_l2_f64'] * 1e-3) / 1e9
-    roofline = {
-        'kernel': 'gd::spmm_batched_kernel<16,false> (GCN layer-2 aggregation, F=64)', 'bound': 'hbm',
-        'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one
-        # `ncu --set full` capture (profiles/r1_spmm_batched_ncu_full.md); only meaningful for the Collab shape
-        'traffic': NCU_DRAM_BYTES_SPMM_L2 if shape.name == 'collab' else None,
-        'gather_ceiling_tbs': 18.0, 'gathered_tbs': (4 * nnz * shape.out_dim) / (kt['spmm_l2_f64'] * 1e-3) / 1e12,
-        'peak_source': peak_src, 'algorithmic_bytes_per_launch': b64, 'kernel_ms': kt['spmm_l2_f64'],
-        'bytes_gather_per_launch': b64 - 4 * n * shape.out_dim + 4 * nnz * shape.out_dim,
-        'other_kernels': {
-            'spmm_l1_f128': {'ms': kt['spmm_l1_f128'], 'algo_bytes': b128,
-                             'frac': b128 / (kt['spmm_l1_f128'] * 1e-3) / 1e9 / peak},
-            'spmm_bwd_f64': {'ms': kt['spmm_bwd_f64'], 'algo_bytes': b64,
-                             'frac': b64 / (kt['spmm_bwd_f64'] * 1e-3) / 1e9 / peak},
-            'edge_loss_fwd': {'ms': kt['edge_loss_fwd']}, 'edge_loss_bwd_spmm': {'ms': kt['edge_loss_bwd_spmm']},
-        },
+    time_kernels(eng_k, data, 3)
+    kt = time_kernels(eng_k, data, min(args.steps, 50))
+    hid, out = shape.hidden_dim, shape.out_dim
+    n1, n2 = int(eng_k.rows1.numel()), int(eng_k.rows2.numel())
+    n_df, n_ni = eng_k.loss.n_df, eng_k.loss.n_ni
+    algo = {
+        'spmm_l1_f128': spmm_algo_bytes(n, nnz, hid), 'spmm_l2_f64': spmm_algo_bytes(n, nnz, out),
+        'spmm_bwd_f64': spmm_algo_bytes(n, nnz, out),
+        'gemm_xw1': gemm_algo_bytes(n, shape.in_dim, hid, False), 'gemm_xw2': gemm_algo_bytes(n, hid, out, False),
+        'gemm_del1': gemm_algo_bytes(n1, hid, hid, True), 'gemm_del2': gemm_algo_bytes(n2, out, out, True),
+        'gemm_da2': gemm_algo_bytes(n2, out, out, True), 'gemm_dx1': gemm_algo_bytes(n1, out, hid, True),
+        'gemm_dw1': gemm_algo_bytes(n1, hid, hid, True), 'gemm_dw2': gemm_algo_bytes(n2, out, out, True),
+        'loss_fwd_bwd': loss_algo_bytes(n_df, n_ni, n, out),
+        'khop_masks_2hop_1hop': khop_algo_bytes(shape.num_edges, n),
     }
+    kernels = {k: {'ms': kt[k], 'algo_bytes': algo[k], 'gbs': algo[k] / (kt[k] * 1e-3) / 1e9,
+                   'frac': algo[k] / (kt[k] * 1e-3) / 1e9 / peak} for k in algo}
+    agg = ['spmm_l1_f128', 'spmm_l2_f64', 'spmm_bwd_f64']
+    agg_bytes, agg_ms = sum(algo[k] for k in agg), sum(kt[k] for k in agg)
+    dom = max(agg, key=lambda k: kt[k])               # the time-dominant aggregation of the epoch
+    traffic, traffic_src = measured_traffic(dom) if shape.name == 'collab' else (None, None)
+    gather_bytes = algo[dom] - 4 * n * (hid if dom == 'spmm_l1_f128' else out) + 4 * nnz * (hid if dom == 'spmm_l1_f128' else out)
+    roofline = {
+        'kernel': {'spmm_l1_f128': 'gd::spmm_batched_kernel<16,false,SCALE|BIAS> x2 (GCN layer-1 aggregation, F=128 as two 64-wide column passes)',
+                   'spmm_l2_f64': 'gd::spmm_batched_kernel<16,false,SCALE|BIAS> (GCN layer-2 aggregation, F=64)',
+                   'spmm_bwd_f64': 'gd::spmm_batched_kernel<16,true,0> (transpose-backward aggregation, F=64)'}[dom],
+        'bound': 'hbm', 'achieved': kernels[dom]['gbs'], 'peak': peak, 'unit': 'GB/s', 'frac': kernels[dom]['frac'],
+        'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
+        'algorithmic_bytes_per_launch': algo[dom], 'kernel_ms': kt[dom], 'bytes_gather_per_launch': gather_bytes,
+        'gathered_tbs': gather_bytes / (kt[dom] * 1e-3) / 1e12, 'gather_ceiling_tbs': 18.0,
+        'aggregations_per_epoch': {'algo_bytes': agg_bytes, 'ms': agg_ms, 'frac': agg_bytes / (agg_ms * 1e-3) / 1e9 / peak},
+        'gemm_share_of_epoch': sum(kt[k] for k in kt if k.startswith('gemm_')) / (ms / args.steps),
+        'other_kernels': {k: v for k, v in kernels.items() if k != dom},
+    }
+    del eng_k
 
-    # ---- e2e: public API with host buffers — per step: pinned negatives -> device, plan
-    #      refresh, epoch, losses -> host
-    eng_e = GCNDeleteEngine(model, data, neg, z_ori=z_ori, hoist_layer1=False)
-    eng_e.capture(warmup=2, dynamic_negatives=True)      # the graph rebuilds the negative incidence from a staging buffer
+    # ---- e2e: through the drop-in trainer (framework.get_trainer(args).start(...)): per step pinned-host negatives -> device,
+    #      epoch (one CUDA-graph launch incl. the negative-pair gradient), losses -> pinned host
+    import tempfile
+    import framework
+    targs = types.SimpleNamespace(unlearning_model='gnndelete', gnn='gcn', dataset='ogbl-collab-shaped', epochs=0, valid_freq=10 ** 9,
+                                  checkpoint_dir=tempfile.mkdtemp(prefix='gd_bench_'), in_dim=shape.in_dim, hidden_dim=hid,
+                                  out_dim=out, lr=1e-3, random_seed=42, hoist_layer1=False, device=str(dev))
+    trainer = framework.get_trainer(targs)
+    d_e2e = data.clone()
+    d_e2e.z_ori = z_ori
+    opt = torch.optim.Adam([model.deletion1.deletion_weight, model.deletion2.deletion_weight], lr=1e-3)
+    sess = trainer.start(model, d_e2e, opt, targs)
     neg_host = neg.cpu().pin_memory()
     out_host = torch.empty(3, dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        eng_e.set_negatives(neg_host)                     # pinned host -> device staging buffer (async H2D)
-        out_host.copy_(eng_e.epoch(), non_blocking=True)  # one graph launch, then losses -> pinned host
+        out_host.copy_(sess.step(neg_host), non_blocking=True)     # H2D negatives, one graph launch, losses -> pinned host
         torch.cuda.current_stream().synchronize()
 
     for _ in range(3):
@@ -467,33 +607,32 @@ def main():
         e2e_step()
     barrier_sync(world)
     e2e_sync_s = max_over_ranks(time.perf_counter() - t0, world, dev)
-
-    # the same steps with the transfers overlapped (EpochPipeline): H2D of step k and D2H of step k-1 ride a copy
-    # stream while the graph of the neighbouring step runs; the host reads every step's losses, one step late
-    from gnndelete_b200.engine import EpochPipeline
-    pipe = EpochPipeline(eng_e)
+    # the same steps with the transfers overlapped: H2D of step k and D2H of step k-1 ride copy streams while the graph of
+    # the neighbouring step runs; the host reads every step's losses, one step late
     for i in range(3):
-        pipe.result(pipe.submit(neg_host))
+        sess.result(sess.submit(neg_host))
     barrier_sync(world)
     t0 = time.perf_counter()
     last = None
     for _ in range(e2e_steps):
-        k = pipe.submit(neg_host)
+        k = sess.submit(neg_host)
         if last is not None:
-            pipe.result(last)
+            sess.result(last)
         last = k
-    pipe.result(last)
+    sess.result(last)
     barrier_sync(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world, dev)
     e2e = {'value': world * e2e_steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': neg_host.numel() * 8,
            'd2h_bytes_per_step': 12, 'steps': e2e_steps, 'value_step_synchronous': world * e2e_steps / e2e_sync_s,
-           'what': 'per step through GCNDeleteEngine / EpochPipeline: new negatives pinned-host -> device, in-graph rebuild '
-                   'of the negative-pair incidence (radix sort), epoch (one CUDA-graph launch), losses -> pinned host and '
-                   'read by the host; transfers of neighbouring steps overlap compute (value_step_synchronous: same steps '
-                   'with a full host sync after every step)'}
+           'captured_step': bool(trainer.trainer_log.get('captured_step')),
+           'what': 'through framework.get_trainer(args).start(model, data, optimizer, args) -> EdgeFormSession (the object '
+                   'GNNDeleteTrainer.train loops over): per step new negatives pinned-host -> device, epoch with both convs '
+                   'recomputed (one CUDA-graph launch; the negative pairs\' gradient is added with vector float reductions, '
+                   'no per-step sort), losses -> pinned host and read by the host; transfers of neighbouring steps overlap '
+                   'compute (value_step_synchronous: same steps with a full host sync after every step)'}
 
     line = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'metric': metric_name(shape), 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(shape), 'where': 'B200',
         'value_hoisted': world * args.steps / (ms_h / 1e3), 'ms_per_step_hoisted': ms_h / args.steps,
@@ -501,6 +640,49 @@ def main():
         'launches_per_epoch': int(launches_per_epoch), 'clocks': clocks,
         'losses_last': losses, 'parallelism': 'replicas' if world > 1 else 'single',
     }
+    del sess, trainer, eng
+
+    # ---- bf16-gather mode (opt-in, separate number: never the headline): gathered operands stored in bf16, fp32 accumulate
+    if world == 1 and shape.name == 'collab':
+        from gnndelete_b200.dist import PartitionedGCNDeleteEngine
+        from gnndelete_b200 import graph as G
+        G._GLOBAL_CACHE = G.PlanCache()
+        torch.cuda.empty_cache()
+        try:
+            e16 = PartitionedGCNDeleteEngine(model, data, neg, z_ori, wire='bf16', world=1, rank=0, hoist_gather=False)
+            for _ in range(max(3, args.warmup)):
+                e16.epoch()
+            ms16 = timed_epochs(e16, args.steps, 1)
+            st = torch.cuda.current_stream()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+            from gnndelete_b200 import ops
+            for a, b in ev:
+                a.record(st); ops.spmm(e16.csr, e16.h1, out=e16.a2, row_scale=e16.dinv, bias=model.conv2.bias.detach()); b.record(st)
+            torch.cuda.synchronize()
+            t16 = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+            b16 = spmm_algo_bytes(n, nnz, out, src_elt=2)
+            line['bf16_gather'] = {'dtype': 'bf16-gather', 'tolerance': 2e-2, 'value': args.steps / (ms16 / 1e3), 'unit': UNIT,
+                                   'ms_per_step': ms16 / args.steps, 'captured': False,
+                                   'spmm_l2_f64': {'ms': t16, 'algo_bytes': b16, 'gbs': b16 / (t16 * 1e-3) / 1e9,
+                                                   'frac': b16 / (t16 * 1e-3) / 1e9 / peak},
+                                   'what': 'same epoch with H0 / H1 / z / dA2 rounded to bf16 before they are gathered (fp32 '
+                                           'accumulation and outputs); eager launches (not graph-captured), so compare its '
+                                           'spmm line, not its epochs/s, with the fp32 path'}
+            del e16
+        except Exception as exc:                       # the opt-in mode must never take the headline down
+            line['bf16_gather'] = {'error': repr(exc)}
+
+    if world > 1 and not args.no_partitioned:
+        del data, model, z_ori, neg
+        from gnndelete_b200 import graph as G
+        G._GLOBAL_CACHE = G.PlanCache()
+        torch.cuda.empty_cache()
+        pshape = S.SHAPES[args.partition_workload].scaled(args.partition_scale)
+        try:
+            line['partitioned'] = run_partitioned(args, pshape, rank, local, world, dev, lib, wire=args.wire)
+        except Exception as exc:
+            line['partitioned'] = {'error': repr(exc)}
+            raise
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         epoch, cores = cpu_epoch_runner(shape)
         epoch()

@@ -85,6 +85,17 @@ SIGNATURES = {
     'gd_edge_loss_fwd': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'gd_edge_loss_fwd_part': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _i64,
                                         _i64, _i64, _vp, _sz, _vp]),
+    'gd_node_loss_workers': (_i32, [_i32, _i32]),
+    'gd_node_loss_workspace_bytes': (_sz, [_i32]),
+    'gd_spmm_batched_bf16_workers': (_i32, [_i32, _i32]),
+    'gd_spmm_batched_bf16': (C.c_int, [_bplan_p, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _i32, _vp]),
+    'gd_cast_bf16': (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _vp]),
+    'gd_move_f32': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    'gd_node_loss_fwd_bwd': (C.c_int, [_bplan_p, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _i32, _i64, _f32,
+                                       _vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'gd_pair_scatter_add': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
+    'gd_dec_items_workspace_bytes': (_sz, []),
+    'gd_dec_items_fwd': (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'gd_dense_ni_workspace_bytes': (_sz, [_i64]),
     'gd_dense_ni_fwd_bwd': (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i64, _vp, _f32, _vp, _i64, _vp, _vp, _sz, _vp]),
     'gd_row_mse_workspace_bytes': (_sz, [_i64]),

@@ -115,7 +115,7 @@ class GCNDeleteEngine:
         ops.spmm(p.fwd, self.h1, out=self.a2, row_scale=p.dinv, bias=m.conv2.bias.detach())
         self._del_rows(self.a2, self.z, self.comp2, lambda: ops.gemm_rows(                    # Del2 on S2
             self.a2, w2, False, out=self.z, rows=self.rows2))
-        return self.loss.forward(self.z)
+        return self.loss.forward(self.z, dz_out=self.dz)       # node mode: dz comes out of the same pass
 
     # ----------------------------------------------------------------- backward
     def backward(self):

@@ -55,13 +55,17 @@ class CSR:
     def num_seg(self):
         return self.plan.get('num_seg', 0)
 
-    def bplan(self, feat, weighted=False):
+    def bplan(self, feat, weighted=False, bf16=False):
         """Batch plan balanced for the sub-warps resident at this width (built on first use);
-        ``None`` when the batched kernel does not cover the width."""
-        if feat not in (32, 64, 128) or self.num_rows == 0 or self.num_rows >= (1 << 30) or not BATCHED or self.dynamic \
-                or self.nnz == 0:
+        ``None`` when the batched kernel does not cover the width.  ``bf16``: the plan of the bf16-source kernel
+        (``gd_spmm_batched_bf16``: feat / 8 lanes per sub-warp, widths 64 / 128)."""
+        if feat not in ((64, 128) if bf16 else (32, 64, 128)) or self.num_rows == 0 or self.num_rows >= (1 << 30) \
+                or not BATCHED or self.dynamic or self.nnz == 0:
             return None
-        workers = L.load().gd_spmm_batched_workers(int(feat), int(bool(weighted))) * OVERSUB
+        if bf16:
+            workers = L.load().gd_spmm_batched_bf16_workers(int(feat), int(bool(weighted))) * OVERSUB
+        else:
+            workers = L.load().gd_spmm_batched_workers(int(feat), int(bool(weighted))) * OVERSUB
         bp = self._bplans.get(workers)
         if bp is None:
             bp = BatchPlan(self.rowptr, self.col, self.num_rows, self.nnz, workers)

@@ -50,23 +50,43 @@ class EdgeLossPlan:
     (``(z_ori[row] * z_ori[col]).sum(-1)``, gnndelete.py:383); they are constant over
     the run, so they are computed once (with the decode kernel) instead of per step.
 
-    The incidence structure is split in two: a FIXED CSR over the Df + NI pairs (built once)
+    Two execution modes, chosen by the embedding width at the first :meth:`forward`:
+
+    ``node`` (widths 32 / 64 / 128, the hot path): losses and ``dz`` come out of ONE pass over the
+    node -> incident-pair lists (``gd_node_loss_fwd_bwd``, csrc/node_loss.cu).  A node keeps its own
+    row in registers, gathers one partner row per incident pair, recomputes the NI logit from its
+    side (``g = c_l (<z_w, z_x> - target)``) and accumulates ``g z_x``; the DEC pairs (Df pair i and
+    its negative share one residual) get their coefficient from a small pre-pass over the ``2 n_df``
+    DEC pairs (``gd_edge_loss_fwd`` with no NI pairs).  One row gather per incidence entry in total,
+    instead of two per pair in the forward plus one per entry in the backward.
+
+    ``pair`` (any other width): ``gd_edge_loss_fwd`` over all pairs writes d loss / d logit into the
+    incidence slots and ``dz`` is a weighted CSR gather.
+
+    In both modes the incidence is split in two: a FIXED part over the Df + NI pairs (built once)
     and a small CSR over the negative pairs that :meth:`update_negatives` rebuilds in place —
     the reference draws new negatives every epoch (gnndelete.py:221-225).  The update is a
     radix sort of ``2 n_df`` keys into preallocated buffers with no host synchronisation, so it
-    can live inside the epoch's CUDA graph; ``dz`` is the fixed gather plus the accumulated
-    negative gather."""
+    can live inside the epoch's CUDA graph."""
+
+    NODE_ROW_LIMIT = 1 << 24          # gd_node_loss_fwd_bwd packs the row id of a batch into 24 bits
 
     def __init__(self, df_edges, neg_edges, ni_edges, num_nodes, z_ori=None, target=None, alpha=0.5,
-                 static_negatives=False):
+                 static_negatives=False, deterministic=False):
         """``static_negatives``: the supplied negatives never change (SURVEY.md §8(d)'s epoch definition), so
-        they join the fixed incidence and ``dz`` is ONE gather; :meth:`update_negatives` then rebuilds the
-        whole incidence (slow path).  Default: negatives are replaceable every step without a rebuild."""
+        they join the fixed incidence; :meth:`update_negatives` then rebuilds the whole incidence (slow path).
+        Default: negatives are replaceable every step without a rebuild.  In ``node`` mode the gradient of the
+        replaceable negative pairs is then ADDED onto ``dz`` with vector float reductions (``gd_pair_scatter_add``):
+        no per-step sort, but the order of a row's few negative contributions is not fixed (like the reference's
+        ``index_add``); ``deterministic=True`` keeps the sorted per-step incidence (tail CSR) instead - bitwise
+        reproducible, ~0.2 ms slower per Collab-sized epoch."""
         dev = df_edges.device
         n_df, n_ni, n = df_edges.shape[1], ni_edges.shape[1], int(num_nodes)
         assert neg_edges.shape[1] == n_df, 'one negative per Df entry (gnndelete.py:221-228)'
         self.n_df, self.n_ni, self.num_nodes = n_df, n_ni, n
         self.static = bool(static_negatives)
+        self.deterministic = bool(deterministic)
+        self.neg_atomic = False
         P = 2 * n_df + n_ni
         self.num_pairs = P
         self.pu = torch.cat([df_edges[0], neg_edges[0], ni_edges[0]]).to(torch.int32).contiguous()
@@ -92,10 +112,6 @@ class EdgeLossPlan:
         self.inc_neg = CSR(self.neg_rowptr, self.neg_col, self.neg_eid, None, n, m)
         self.inc_neg.dynamic = True                  # rebuilt in place every step: no cached batch plan
         self.neg_buf = neg_edges.clone()             # staging buffer a caller may overwrite (H2D) before a graph replay
-        self._feat = None
-        self._build_fixed()
-        self._layout(z_ori.shape[1] if z_ori is not None else 0)
-        self.update_negatives()
         if target is None:
             if n_ni > 0:
                 target = ops.pair_decode(z_ori, self.pu[2 * n_df:P].contiguous(), self.pv[2 * n_df:P].contiguous())
@@ -105,13 +121,29 @@ class EdgeLossPlan:
         self.alpha = float(alpha)
         self.logits = torch.empty(max(P, 1), dtype=torch.float32, device=dev)
         self.losses = torch.zeros(3, dtype=torch.float32, device=dev)
+        self.dec_losses = torch.zeros(3, dtype=torch.float32, device=dev)
+        self.ni_sq_sum = torch.zeros(1, dtype=torch.float32, device=dev)
         self.ws_bytes = L.load().gd_edge_loss_workspace_bytes(P)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self._feat = None
+        self._dz = None
+        self.mode = None
+        self._layout(z_ori.shape[1] if z_ori is not None else 0)
 
-    def _build_fixed(self):
-        """Fixed incidence CSR (node -> (partner, pair side)) over the pairs that never change:
-        Df + NI, plus the negatives in static mode.  Entry e < Pf is the u side of fixed pair e,
-        entry Pf + e its v side."""
+    # ------------------------------------------------------------------ plan construction
+    def _mode_for(self, feat):
+        from .graph import BATCHED
+        ok = BATCHED and feat in (32, 64, 128) and 0 < self.num_nodes < self.NODE_ROW_LIMIT and self.num_pairs > 0
+        return 'node' if ok else 'pair'
+
+    def _fixed_pairs(self):
+        """Indices (into ``pu`` / ``pv``) of the DEC pairs that never change: Df, plus the negatives in static mode."""
+        dev, n_df = self.pu.device, self.n_df
+        return torch.arange(2 * n_df if self.static else n_df, device=dev)
+
+    def _build_fixed_pair(self):
+        """``pair`` mode: fixed incidence CSR (node -> (partner, pair side)) over the pairs that never change:
+        Df + NI, plus the negatives in static mode.  Entry e < Pf is the u side of fixed pair e, entry Pf + e its v side."""
         dev, n_df, P = self.pu.device, self.n_df, self.num_pairs
         if self.static:
             self.fixed_idx = torch.arange(P, device=dev)
@@ -123,15 +155,13 @@ class EdgeLossPlan:
         self._posf = invert_perm(self.inc_fixed.eid, max(2 * Pf, 1))
         self.nnz_fixed = 2 * Pf
 
-    def _layout(self, feat):
-        """Lay out the per-entry gradient buffer ``inc_val`` = [fixed incidence | negative incidence].
+    def _layout_pair(self, feat):
+        """``pair`` mode: per-entry gradient buffer ``inc_val`` = [fixed incidence | negative incidence].
         When the batched aggregation covers ``feat`` the fixed part is in the padded slot layout of its
         batch plan (the loss kernel scatters d loss / d logit through ``pos_u`` / ``pos_v``, so the
         remap is free); otherwise it is in CSR order for the row-walking kernel."""
-        if self._feat == feat:
-            return
-        self._feat = feat
-        n_df, P, Pf = self.n_df, self.num_pairs, int(self.fixed_idx.numel())
+        self._build_fixed_pair()
+        n_df, Pf = self.n_df, int(self.fixed_idx.numel())
         bp = self.inc_fixed.bplan(feat, True) if (feat and self.nnz_fixed) else None
         self.bplan_fixed = bp
         posf = self._posf
@@ -143,9 +173,65 @@ class EdgeLossPlan:
         self.pos_u[self.fixed_idx] = posf[:Pf]
         self.pos_v[self.fixed_idx] = posf[Pf:2 * Pf]
         self.inc_val = torch.zeros(self.val_off + max(self.neg_m, 1), dtype=torch.float32, device=self.pos_u.device)
-        if self.neg_m:
-            torch.add(self.neg_pos[:n_df], self.val_off, out=self.pos_u[n_df:2 * n_df])
-            torch.add(self.neg_pos[n_df:2 * n_df], self.val_off, out=self.pos_v[n_df:2 * n_df])
+
+    def _layout_node(self, feat):
+        """``node`` mode: batch plan over the node -> incident-pair lists (NI pairs from both endpoints, fixed DEC
+        pairs from both endpoints), per-slot values (NI target | DEC coefficient slot), per-batch meta words."""
+        from .graph import BatchPlan
+        dev, n, n_df, n_ni = self.pu.device, self.num_nodes, self.n_df, self.n_ni
+        P = self.num_pairs
+        nu, nv = self.pu[2 * n_df:P].long(), self.pv[2 * n_df:P].long()
+        fidx = self._fixed_pairs()
+        fu, fv = self.pu[:P][fidx].long(), self.pv[:P][fidx].long()
+        Pf = int(fidx.numel())
+        dst = torch.cat([nu, nv, fu, fv])
+        src = torch.cat([nv, nu, fv, fu])
+        inc = build_csr(src, dst, n, self_loops=False)
+        self.inc_fixed = inc
+        self.nnz_fixed = inc.nnz
+        posf = invert_perm(inc.eid, max(inc.nnz, 1)).long()
+        workers = L.load().gd_node_loss_workers(int(feat), 0)
+        bp = BatchPlan(inc.rowptr, inc.col, n, inc.nnz, workers)
+        bp.colp.clamp_(min=0)       # padding slots gather a valid row (coefficient 0): the kernel's loads are unpredicated
+        self.bplan_fixed = bp
+        slot = bp.slot_of_entry[posf[:inc.nnz]] if inc.nnz else posf[:0]
+        self.val_off = bp.num_slots
+        self.inc_val = torch.zeros(self.val_off + max(self.neg_m, 1), dtype=torch.float32, device=dev)
+        if self.neg_atomic:          # negative pair i: both "slots" are element val_off + i (its coefficient, read by the scatter)
+            ar = torch.arange(n_df, dtype=torch.int32, device=dev) + self.val_off
+            self.pos_u[n_df:2 * n_df] = ar
+            self.pos_v[n_df:2 * n_df] = ar
+        flag = torch.zeros(bp.num_slots, dtype=torch.bool, device=dev)
+        if n_ni:
+            s_ni = slot[:2 * n_ni]
+            self.inc_val[s_ni] = torch.cat([self.target[:n_ni], self.target[:n_ni]])
+            flag[s_ni] = True
+        self._ni_slots = slot[:2 * n_ni]
+        self.pos_u[fidx] = slot[2 * n_ni:2 * n_ni + Pf].to(torch.int32)
+        self.pos_v[fidx] = slot[2 * n_ni + Pf:].to(torch.int32)
+        # meta word of every batch: row (low 24 bits) | NI flag of each of its 8 slots (high 8 bits)
+        deg = (inc.rowptr[1:] - inc.rowptr[:-1]).long()
+        nbr = torch.clamp((deg + 7) // 8, min=1)
+        brow = torch.repeat_interleave(torch.arange(n, device=dev), nbr)
+        assert brow.numel() == bp.num_batches
+        bits = (flag.view(-1, 8).long() << torch.arange(8, device=dev)).sum(1)          # [num_batches + 2]
+        meta = bits << 24
+        meta[:bp.num_batches] |= brow
+        self.bmeta = torch.where(meta >= (1 << 31), meta - (1 << 32), meta).to(torch.int32).contiguous()
+        self.nl_ws_bytes = L.load().gd_node_loss_workspace_bytes(bp.num_workers)
+        self.nl_ws = torch.empty(self.nl_ws_bytes, dtype=torch.uint8, device=dev)
+
+    def _layout(self, feat):
+        if self._feat == feat:
+            return
+        self._feat = feat
+        self.mode = self._mode_for(feat)
+        self.neg_atomic = self.mode == 'node' and not self.static and not self.deterministic and self.n_df > 0
+        if self.mode == 'node':
+            self._layout_node(feat)
+        else:
+            self._layout_pair(feat)
+        self.update_negatives()
 
     def update_negatives(self, neg_edges=None):
         """Install new negatives (default: whatever is in ``self.neg_buf``).  Dynamic mode: no allocation,
@@ -164,10 +250,10 @@ class EdgeLossPlan:
                 self.neg_status[1] = bad
                 if bad:
                     return
-                feat = self._feat
-                self._build_fixed()
-                self._feat = None
+                feat, self._feat = self._feat, None
                 self._layout(feat)
+            return
+        if self.neg_atomic:
             return
         self.neg_dst[:n_df].copy_(nu); self.neg_dst[n_df:].copy_(nv)
         self.neg_src[:n_df].copy_(nv); self.neg_src[n_df:].copy_(nu)
@@ -185,18 +271,52 @@ class EdgeLossPlan:
         if bad:
             raise ValueError(f'negative edges hold {bad} endpoints outside [0, {self.num_nodes})')
 
-    def forward(self, z):
-        """Fills ``self.losses`` = (loss, loss_r, loss_l), ``self.logits`` and the incidence
-        values; returns ``self.losses`` (a persistent device tensor, no host sync)."""
+    # ------------------------------------------------------------------------- execution
+    def forward(self, z, dz_out=None):
+        """Fills ``self.losses`` = (loss, loss_r, loss_l) and returns it (a persistent device tensor, no host sync).
+        ``node`` mode also produces ``dz`` here (into ``dz_out`` when given); ``self.logits`` then holds the DEC
+        logits only (``[:2 n_df]``)."""
         self._layout(z.shape[1])
-        L.call('gd_edge_loss_fwd', L.ptr(z, 'f32'), z.stride(0), z.shape[1], L.ptr(self.pu), L.ptr(self.pv),
-               self.n_df, self.n_ni, L.ptr(self.target), self.alpha, L.ptr(self.pos_u), L.ptr(self.pos_v),
-               L.ptr(self.logits), L.ptr(self.inc_val), L.ptr(self.losses), L.ptr(self.ws), self.ws_bytes,
-               L.stream())
+        if self.mode == 'pair':
+            L.call('gd_edge_loss_fwd', L.ptr(z, 'f32'), z.stride(0), z.shape[1], L.ptr(self.pu), L.ptr(self.pv),
+                   self.n_df, self.n_ni, L.ptr(self.target), self.alpha, L.ptr(self.pos_u), L.ptr(self.pos_v),
+                   L.ptr(self.logits), L.ptr(self.inc_val), L.ptr(self.losses), L.ptr(self.ws), self.ws_bytes,
+                   L.stream())
+            return self.losses
+        if self.n_df:            # DEC pre-pass: logits of the Df pairs and their negatives -> coefficient slots, loss_r
+            L.call('gd_edge_loss_fwd', L.ptr(z, 'f32'), z.stride(0), z.shape[1], L.ptr(self.pu), L.ptr(self.pv),
+                   self.n_df, 0, None, self.alpha, L.ptr(self.pos_u), L.ptr(self.pos_v), L.ptr(self.logits),
+                   L.ptr(self.inc_val), L.ptr(self.dec_losses), L.ptr(self.ws), self.ws_bytes, L.stream())
+        dz = dz_out
+        if dz is None:
+            if self._dz is None or self._dz.shape != z.shape:
+                self._dz = torch.empty_like(z)
+            dz = self._dz
+        self._dz_last = dz
+        bp = self.bplan_fixed
+        tail = self.neg_m > 0 and not self.neg_atomic
+        L.call('gd_node_loss_fwd_bwd', bp.ref, L.ptr(self.bmeta), L.ptr(self.inc_val),
+               L.ptr(self.neg_rowptr) if tail else None, L.ptr(self.neg_col) if tail else None,
+               L.ptr(self.inc_val[self.val_off:]) if tail else None,
+               L.ptr(z, 'f32'), z.stride(0), L.ptr(z, 'f32'), z.stride(0), 0, None, z.shape[1], self.n_ni, self.alpha,
+               L.ptr(self.dec_losses), L.ptr(dz), dz.stride(0), L.ptr(bp.scratch(z.shape[1])), L.ptr(self.losses),
+               L.ptr(self.ni_sq_sum), L.ptr(self.nl_ws), self.nl_ws_bytes, L.stream())
+        if self.neg_atomic:
+            n_df = self.n_df
+            L.call('gd_pair_scatter_add', L.ptr(z, 'f32'), z.stride(0), z.shape[1], L.ptr(self.pu[n_df:2 * n_df]),
+                   L.ptr(self.pv[n_df:2 * n_df]), L.ptr(self.inc_val[self.val_off:]), n_df, L.ptr(dz), dz.stride(0),
+                   L.stream())
         return self.losses
 
     def backward(self, z, out=None):
         """dz = d loss / d z for the ``z`` last given to :meth:`forward`."""
+        if self.mode == 'node':
+            dz = self._dz_last
+            if out is None:
+                return dz.clone() if dz is self._dz else dz
+            if out.data_ptr() != dz.data_ptr():
+                out.copy_(dz)
+            return out
         if self.bplan_fixed is not None:
             # one gather: the fixed incidence through its batch plan, this step's negative incidence as the tail CSR
             tail = (self.neg_rowptr, self.neg_col, self.inc_val[self.val_off:]) if self.neg_m > 0 else None

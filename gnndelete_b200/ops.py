@@ -46,6 +46,8 @@ def spmm(csr: CSR, x, out=None, val=None, col_scale=None, row_scale=None, self_c
     constant ``col_scale`` is folded into cached padded weights once.  Per-entry ``val`` in CSR order
     (or a CSR without a plan-able width) goes through the row-walking kernel ``gd_spmm_acc``.  ``tail`` =
     ``(rowptr, col, val)`` of a second plain CSR whose entries are added row by row (batched path only)."""
+    if x.dtype == torch.bfloat16:
+        return _spmm_bf16(csr, x, out, val, col_scale, row_scale, self_coef, bias, accumulate, valp, tail)
     x = _f32(x)
     n, f = csr.num_rows, x.shape[1]
     if out is None:
@@ -74,6 +76,39 @@ def spmm(csr: CSR, x, out=None, val=None, col_scale=None, row_scale=None, self_c
     assert valp is None and tail is None, 'padded weights / a tail CSR need a batch plan'
     L.call('gd_spmm_acc', csr.ref, L.ptr(val), L.ptr(col_scale), L.ptr(row_scale), L.ptr(x), x.stride(0), f,
            float(self_coef), L.ptr(bias), L.ptr(out), out.stride(0), L.ptr(csr.scratch(f)), int(bool(accumulate)),
+           L.stream())
+    return out
+
+
+def _spmm_bf16(csr, x, out, val, col_scale, row_scale, self_coef, bias, accumulate, valp, tail):
+    """The bf16-gather mode of :func:`spmm`: bf16 source rows, fp32 accumulation and output (``gd_spmm_batched_bf16``).
+    There is no row-walking fallback for bf16 sources: the width must be 64 or 128."""
+    x = x.contiguous() if x.stride(1) != 1 else x
+    n, f = csr.num_rows, x.shape[1]
+    if val is not None:
+        raise RuntimeError('per-entry values in CSR order are not supported with a bf16 source (use valp)')
+    weighted = valp is not None or col_scale is not None
+    bp = csr.bplan(f, weighted, bf16=True)
+    if bp is None:
+        raise RuntimeError(f'gd_spmm_batched_bf16 covers widths 64 / 128 on a non-empty static CSR; got width {f}')
+    if out is None:
+        assert not accumulate, 'accumulate needs an output buffer'
+        out = torch.empty(n, f, dtype=torch.float32, device=x.device)
+    if valp is None and col_scale is not None:
+        valp = bp.col_scale_weights(col_scale)
+    t_rp, t_col, t_val = tail if tail is not None else (None, None, None)
+    L.call('gd_spmm_batched_bf16', bp.ref, L.ptr(valp), L.ptr(t_rp), L.ptr(t_col), L.ptr(t_val), L.ptr(row_scale),
+           x.data_ptr(), x.stride(0), f, float(self_coef), L.ptr(bias), L.ptr(out), out.stride(0), L.ptr(bp.scratch(f)),
+           int(bool(accumulate)), L.stream())
+    return out
+
+
+def cast_bf16(x, out=None, row_scale=None):
+    """``out = bf16(row_scale[:, None] * x)`` (round to nearest even) - the wire / gather format of the bf16-gather mode."""
+    x = _f32(x)
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    L.call('gd_cast_bf16', L.ptr(x), x.stride(0), x.shape[0], x.shape[1], L.ptr(row_scale), out.data_ptr(), out.stride(0),
            L.stream())
     return out
 

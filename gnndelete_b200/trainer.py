@@ -396,7 +396,10 @@ class GNNDeleteTrainer(Trainer):
         needs parity supplies ``data.neg_edge_index``."""
         return torch.randint(0, data.num_nodes, (2, count), generator=generator, device=data.x.device)
 
-    def train_edge_form(self, model, data, optimizer, args, logits_ori=None):
+    def start(self, model, data, optimizer, args, logits_ori=None):
+        """Set up the GCNDelete unlearning run and return its :class:`EdgeFormSession` - the object :meth:`train`
+        loops over (one ``session.step()`` per epoch).  Public so that a caller can drive the epochs itself, e.g.
+        feed each epoch's negatives from host memory (``bench.py``'s end-to-end leg does)."""
         dev = self._cuda_device(args)
         model = model.to(dev)
         data = data.to(dev)
@@ -419,8 +422,8 @@ class GNNDeleteTrainer(Trainer):
             if (g['lr'], g['betas'], g['eps']) != (group['lr'], group['betas'], group['eps']):
                 raise ValueError('per-group Adam hyper-parameters are not supported by the fused GCNDelete epoch')
         eng = GCNDeleteEngine(model, data, neg, z_ori=z_ori, lr=group['lr'], betas=group['betas'], eps=group['eps'],
-                              hoist_layer1=True, logits_ori=logits_ori, static_negatives=fixed_neg is not None,
-                              alpha=self._loss_mix())
+                              hoist_layer1=getattr(args, 'hoist_layer1', True), logits_ori=logits_ori,
+                              static_negatives=fixed_neg is not None, alpha=self._loss_mix())
         self.engine = eng
         if getattr(args, 'capture_step', True) and logits_ori is None:
             # one cudaGraphLaunch per epoch; resampled negatives are written into the graph's staging buffer
@@ -431,14 +434,17 @@ class GNNDeleteTrainer(Trainer):
                 eng.graph = None
                 torch.cuda.synchronize()
         self.trainer_log['captured_step'] = eng.graph is not None
+        return EdgeFormSession(self, model, data, eng, gen, n_df, resample=fixed_neg is None)
+
+    def train_edge_form(self, model, data, optimizer, args, logits_ori=None):
+        sess = self.start(model, data, optimizer, args, logits_ori)
+        model, data, eng = sess.model, sess.data, sess.engine
         best_metric = 0
         ring = []
         t0 = time.time()
         for epoch in range(args.epochs):
             model.train()
-            if fixed_neg is None and epoch > 0:
-                eng.set_negatives(self._negatives(data, n_df, gen))
-            losses = eng.epoch()
+            losses = sess.step()
             ring.append(losses.clone())
             last = epoch + 1 == args.epochs
             if (epoch + 1) % self.log_every == 0 or last or (epoch + 1) % args.valid_freq == 0:
@@ -601,6 +607,43 @@ class GNNDeleteTrainer(Trainer):
                     optimizer.state[q] = {'step': st['step'].detach().cpu().reshape(()).clone(),
                                           'exp_avg': st['m'], 'exp_avg_sq': st['v']}
         return optimizer.state_dict()
+
+
+class EdgeFormSession:
+    """One GCNDelete unlearning run in progress (``GNNDeleteTrainer.start``): the fused epoch engine, captured into
+    a CUDA graph when possible, plus the negative-sampling state.  ``step()`` = one epoch of ``train`` (gnndelete.py:
+    215-259 with the edge-form NI of :379-386): new negatives -> forward -> losses -> backward -> Adam."""
+
+    def __init__(self, trainer, model, data, engine, generator, n_df, resample):
+        self.trainer, self.model, self.data, self.engine = trainer, model, data, engine
+        self.gen, self.n_df, self.resample = generator, n_df, resample
+        self.epochs_done = 0
+        self._pipe = None
+
+    def step(self, negatives=None):
+        """One epoch; returns the persistent device tensor (loss, loss_r, loss_l) - no host sync.  ``negatives``:
+        this epoch's ``[2, n_df]`` negative edges (host or device; a pinned host tensor is copied asynchronously);
+        default: resampled on the device like the reference does every epoch (gnndelete.py:221-225), or the fixed
+        ``data.neg_edge_index`` when one was supplied."""
+        if negatives is not None:
+            self.engine.set_negatives(negatives)
+        elif self.resample and self.epochs_done > 0:
+            self.engine.set_negatives(self.trainer._negatives(self.data, self.n_df, self.gen))
+        self.epochs_done += 1
+        return self.engine.epoch()
+
+    # pipelined host feeding: epoch k's negatives upload and epoch k-1's losses download while a neighbour computes
+    def submit(self, neg_host):
+        """Queue one epoch on pinned host negatives; returns its index for :meth:`result`."""
+        if self._pipe is None:
+            from .engine import EpochPipeline
+            self._pipe = EpochPipeline(self.engine)
+        self.epochs_done += 1
+        return self._pipe.submit(neg_host)
+
+    def result(self, k):
+        """Host (loss, loss_r, loss_l) of epoch ``k`` (one of the last two submitted); blocks until it has arrived."""
+        return self._pipe.result(k)
 
 
 class KGTrainer(Trainer):

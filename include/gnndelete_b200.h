@@ -189,6 +189,27 @@ int gd_spmm_batched_tail(const gd_spmm_bplan_t* plan, const float* valp, const i
                          int64_t ldx, int32_t feat, float self_coef, const float* bias, float* out, int64_t ldo,
                          float* scratch, int32_t accumulate, gd_stream_t stream);
 
+/* gd_spmm_batched_tail with a bf16 SOURCE matrix x (fp32 accumulation and output) - the "bf16-gather" mode
+ * (gnndelete_b200/csrc/spmm_batched_bf16.cu): halves the bytes every non-zero gathers; it is the wire format of the
+ * row-partitioned epoch's halo blocks.  ldx in bf16 elements (multiple of 8); feat in {64, 128}; the plan must be
+ * balanced for gd_spmm_batched_bf16_workers(feat, weighted) workers.  Results differ from the fp32 kernel by the
+ * bf16 rounding of the source rows (tolerance 2e-2, stated in the tests). */
+int32_t gd_spmm_batched_bf16_workers(int32_t feat, int32_t weighted);
+int gd_spmm_batched_bf16(const gd_spmm_bplan_t* plan, const float* valp, const int32_t* tail_rowptr,
+                         const int32_t* tail_col, const float* tail_val, const float* row_scale,
+                         const void* x_bf16, int64_t ldx, int32_t feat, float self_coef, const float* bias,
+                         float* out, int64_t ldo, float* scratch, int32_t accumulate, gd_stream_t stream);
+
+/* out_bf16[r, :feat] = bf16(row_scale[r] * x[r, :feat]), round to nearest even; row_scale nullable; feat multiple of
+ * 8, ldo multiple of 8 elements. */
+int gd_cast_bf16(const float* x, int64_t ldx, int64_t rows, int32_t feat, const float* row_scale, void* out_bf16,
+                 int64_t ldo, gd_stream_t stream);
+
+/* dst[dst_idx[i]] = src[src_idx[i]] for i < n (either index list nullable = identity).  The row-partitioned epoch
+ * uses it to drop the all-gathered DEC coefficients into the slots of its incidence plan. */
+int gd_move_f32(const float* src, const int32_t* src_idx, float* dst, const int32_t* dst_idx, int64_t n,
+                gd_stream_t stream);
+
 /* GATConv(heads=1) edge-softmax aggregation (gat.py:11-12; defaults negative_slope=0.2,
  * add_self_loops=True — the CSR must be built with self_loops=1):
  *   a_src[k] = <h_k, att_src>, a_dst[i] = <h_i, att_dst>                 (gd_gat_scores)
@@ -319,6 +340,48 @@ int gd_edge_loss_fwd(const float* z, int64_t ldz, int32_t dim, const int32_t* pa
                      const int32_t* pair_v, int64_t n_df, int64_t n_ni, const float* target,
                      float alpha, const int32_t* pos_u, const int32_t* pos_v, float* logits,
                      float* inc_val, float* losses, void* workspace, size_t workspace_bytes,
+                     gd_stream_t stream);
+
+/* Node-side fusion of the same losses with their gradient (gnndelete_b200/csrc/node_loss.cu): ONE pass over the
+ * node -> incident-pair lists produces dz and loss_l.  `plan` is a batch plan (gd_spmm_bplan_t) over the incidence
+ * rows: NI pairs listed from both endpoints, DEC pairs (Df / negatives) from both endpoints; colp = partner node.
+ *   bmeta[b] : row of batch b in the low 24 bits (num_rows < 2^24), bit 24 + s set when slot s of the batch is an
+ *              NI entry; readable for two batches past num_batches like desc / colp;
+ *   valp[s]  : NI entry: the pair's target logit; DEC entry: d loss / d logit of the pair, as written by
+ *              gd_edge_loss_fwd (n_ni = 0) through pos_u / pos_v; padding slots must hold 0;
+ *   tail_*   : optional plain CSR of further given-coefficient entries (this step's negative pairs).
+ * For plan row r:  dz[r,:] = sum_NI c_l (<zself[r'], z[x]> - target) z[x,:] + sum_DEC valp z[x,:] with
+ * r' = row_slot[r] (or r), c_l = (1 - alpha) * 2 / norm_ni.  losses[3] = {alpha loss_r + (1 - alpha) loss_l, loss_r,
+ * loss_l} with loss_r = dec_losses[1] (nullable = 0) and loss_l = (sum over NI entries of residual^2) / (2 norm_ni)
+ * (every NI pair is listed twice); ni_sq_sum (nullable) receives the raw sum for callers that reduce it over ranks.
+ * `bf16` != 0: z / zself hold bf16 rows (ld in elements; the wire format of the row-partitioned epoch), feat in
+ * {64, 128}; otherwise fp32 rows, feat in {32, 64, 128}.  No float atomics: bitwise reproducible. */
+int32_t gd_node_loss_workers(int32_t feat, int32_t bf16);
+size_t gd_node_loss_workspace_bytes(int32_t num_workers);
+int gd_node_loss_fwd_bwd(const gd_spmm_bplan_t* plan, const int32_t* bmeta, const float* valp,
+                         const int32_t* tail_rowptr, const int32_t* tail_col, const float* tail_val,
+                         const void* z, int64_t ldz, const void* zself, int64_t ldself, int32_t bf16,
+                         const int32_t* row_slot, int32_t feat, int64_t norm_ni, float alpha,
+                         const float* dec_losses, float* dz, int64_t ldo, float* scratch, float* losses,
+                         float* ni_sq_sum, void* workspace, size_t workspace_bytes, gd_stream_t stream);
+
+/* dz[u_i,:] += coef[i] * z[v_i,:] and dz[v_i,:] += coef[i] * z[u_i,:] for num_pairs given-coefficient pairs: the
+ * gradient of this step's NEGATIVE pairs (resampled every epoch, gnndelete.py:221-225), added onto the dz of
+ * gd_node_loss_fwd_bwd with vector float reductions - no per-step sort / incidence rebuild.  The order in which a
+ * row's few contributions are added is not fixed (as in the reference's index_add scatter). */
+int gd_pair_scatter_add(const float* z, int64_t ldz, int32_t feat, const int32_t* pair_u, const int32_t* pair_v,
+                        const float* coef, int64_t num_pairs, float* dz, int64_t ldo, gd_stream_t stream);
+
+/* DEC residuals of a SHARE of the Df items (row-partitioned epoch, gnndelete_b200/dist.py): item i = Df pair
+ * (pair_u[i], pair_v[i]) with its negative (pair_u[n_items + i], pair_v[n_items + i]);
+ *   r_i = <z_u, z_v> - <z_nu, z_nv>  (gcn.py:26-35, gnndelete.py:227-228);  coef_pos[i] = alpha * 2 / norm_df * r_i,
+ *   coef_neg[i] = -coef_pos[i]  (d loss / d logit of the two pairs);  loss_r_part[0] = sum_i r_i^2 / norm_df (this
+ *   caller's share of loss_r; the shares add up over ranks);  logits (nullable) [2 n_items].
+ * z rows fp32 or bf16 (`bf16`), ldz in elements. */
+size_t gd_dec_items_workspace_bytes(void);
+int gd_dec_items_fwd(const void* z, int64_t ldz, int32_t bf16, int32_t feat, const int32_t* pair_u,
+                     const int32_t* pair_v, int64_t n_items, int64_t norm_df, float alpha, float* coef_pos,
+                     float* coef_neg, float* logits, float* loss_r_part, void* workspace, size_t workspace_bytes,
                      gd_stream_t stream);
 
 /* Row-partitioned variant: this caller holds a SUBSET of the Df items / NI pairs (those touching

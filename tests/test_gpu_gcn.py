@@ -277,14 +277,19 @@ def test_delete_model_forward_and_grads(lib, case, gnn):
     U.assert_close(m.deletion1.deletion_weight.grad, om.deletion1.deletion_weight.grad, what='dW_del1')
 
 
-def test_fused_edge_loss(lib, case):
-    """gd_edge_loss_fwd + incidence gather == autograd of the oracle's loss w.r.t. z."""
+@pytest.mark.parametrize('dim,static,det', [(64, False, False), (64, False, True), (64, True, False), (128, False, False),
+                                            (128, False, True), (32, True, False), (48, False, False)])
+def test_fused_edge_loss(lib, case, dim, static, det):
+    """Fused decoder + DEC / NI losses + dz == autograd of the oracle's loss w.r.t. z: the node-side one-pass kernel
+    (gd_node_loss_fwd_bwd, widths 32 / 64 / 128) and the pair-side kernel + incidence gather (any other width), with
+    the negatives in the fixed incidence (static), in the per-step tail CSR (deterministic) or added with vector float
+    reductions (the default for replaceable negatives)."""
     from gnndelete_b200.losses import EdgeLossPlan
     shape, raw, df, data, neg = case
     g = torch.Generator().manual_seed(5)
     n = data.num_nodes
-    z = torch.randn(n, 64, generator=g, dtype=torch.float64, requires_grad=True)
-    zo = torch.randn(n, 64, generator=g, dtype=torch.float64)
+    z = torch.randn(n, dim, generator=g, dtype=torch.float64, requires_grad=True)
+    zo = torch.randn(n, dim, generator=g, dtype=torch.float64)
     ei = data.train_pos_edge_index
     dfe = ei[:, data.df_mask]
     sdf = ei[:, data.sdf_mask]
@@ -296,16 +301,35 @@ def test_fused_edge_loss(lib, case):
     loss = 0.5 * loss_r + 0.5 * loss_l
     loss.backward()
     zg = z.detach().float().to(DEV)
-    plan = EdgeLossPlan(dfe.to(DEV), neg.to(DEV), ni.to(DEV), n, z_ori=zo.float().to(DEV))
-    losses = plan.forward(zg)
-    dz = plan.backward(zg)
+    plan = EdgeLossPlan(dfe.to(DEV), neg.to(DEV), ni.to(DEV), n, z_ori=zo.float().to(DEV), static_negatives=static,
+                        deterministic=det)
+    assert plan.mode == ('node' if dim in (32, 64, 128) else 'pair')
+    assert plan.neg_atomic == (plan.mode == 'node' and not static and not det)
+    losses = plan.forward(zg).clone()
+    dz = plan.backward(zg).clone()
     U.assert_close(losses, torch.stack([loss, loss_r, loss_l]), what='losses')
     U.assert_close(dz, z.grad, what='dz')
     U.assert_close(plan.logits[:2 * nd], lg, what='logits')
     # deterministic: bitwise identical on repeat
     l2 = plan.forward(zg).clone()
     dz2 = plan.backward(zg)
-    assert torch.equal(l2, losses) and torch.equal(dz, dz2)
+    assert torch.equal(l2, losses)
+    if plan.neg_atomic:          # float reductions: the order of a row's few negative contributions is not fixed
+        U.assert_close(dz2, dz, tol=1e-6, what='dz on repeat')
+    else:
+        assert torch.equal(dz, dz2)
+    # replaced negatives (gnndelete.py:221-225): same check against the oracle on the new set
+    neg2 = torch.randint(0, n, neg.shape, generator=g)
+    z.grad = None
+    lg2 = (z[torch.cat([dfe[0], neg2[0]])] * z[torch.cat([dfe[1], neg2[1]])]).sum(-1)
+    loss_r2 = torch.nn.functional.mse_loss(lg2[:nd], lg2[nd:])
+    loss_l2 = torch.nn.functional.mse_loss((z[ni[0]] * z[ni[1]]).sum(-1), (zo[ni[0]] * zo[ni[1]]).sum(-1))
+    (0.5 * loss_r2 + 0.5 * loss_l2).backward()
+    plan.update_negatives(neg2.to(DEV))
+    plan.check_negatives()
+    losses2 = plan.forward(zg).clone()
+    U.assert_close(losses2, torch.stack([0.5 * loss_r2 + 0.5 * loss_l2, loss_r2, loss_l2]).detach(), what='losses (new negatives)')
+    U.assert_close(plan.backward(zg), z.grad, what='dz (new negatives)')
 
 
 def test_deletion_layer_semantics(lib):
