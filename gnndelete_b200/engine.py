@@ -29,12 +29,14 @@ from .losses import DenseNIPlan, EdgeLossPlan
 
 class GCNDeleteEngine:
     def __init__(self, model, data, neg_edge_index, z_ori=None, ni_target=None, hoist_layer1=True,
-                 lr=1e-3, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, logits_ori=None, static_negatives=False):
+                 lr=1e-3, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, logits_ori=None, static_negatives=False,
+                 deterministic=False):
         """``logits_ori`` (dense ``[N, N]``, the original model's ``z z^T`` as saved in
         ``pred_proba.pt``) selects ``train_fullbatch``'s dense-block NI loss instead of the edge form.
         ``static_negatives``: the supplied negatives are fixed for the run, so the loss
         gradient is one gather over one incidence; leave False when negatives are replaced every epoch
-        (``set_negatives`` / ``capture(dynamic_negatives=True)``)."""
+        (``set_negatives`` / ``capture(dynamic_negatives=True)``).  ``deterministic``: replaceable negatives go through a
+        sorted per-step incidence instead of float reductions (bitwise reproducible epochs, see ``EdgeLossPlan``)."""
         self.model = model
         dev = data.x.device
         self.x = data.x.contiguous()
@@ -52,7 +54,8 @@ class GCNDeleteEngine:
             self.dense = DenseNIPlan(data.sdf_node_2hop_mask, ei[:, data.df_mask], logits_ori, n, out, weight=1.0 - alpha)
             ni = ni[:, :0]
         self.loss = EdgeLossPlan(ei[:, data.df_mask], neg_edge_index, ni, n, z_ori=z_ori,
-                                 target=ni_target, alpha=alpha, static_negatives=static_negatives)
+                                 target=ni_target, alpha=alpha, static_negatives=static_negatives,
+                                 deterministic=deterministic)
         self.losses_total = torch.zeros(3, dtype=torch.float32, device=dev)
         self.alpha = float(alpha)
         f32 = dict(dtype=torch.float32, device=dev)

@@ -86,7 +86,7 @@ def test_engine_new_negatives_every_epoch(lib, static):
         U.assert_close(eng2.epoch(), want, what='losses through the in-graph negative rebuild')
         # the double-buffered pipeline returns every step's losses, one step late, and matches the synchronous path
         from gnndelete_b200.engine import EpochPipeline
-        eng3, eng4 = fresh(neg), fresh(neg)
+        eng3, eng4 = fresh(neg, deterministic=True), fresh(neg, deterministic=True)      # sorted per-step incidence: bitwise
         eng3.capture(dynamic_negatives=True)
         eng4.capture(dynamic_negatives=True)
         pipe = EpochPipeline(eng3)
@@ -101,6 +101,16 @@ def test_engine_new_negatives_every_epoch(lib, static):
         for h, g_ in zip(hosts, got):
             eng4.set_negatives(h.to(DEV))
             assert torch.equal(eng4.epoch().cpu(), g_), 'pipelined step == synchronous step, bitwise'
+        # default mode (negative-pair gradient added with float reductions): same steps within fp32 rounding
+        eng5, eng6 = fresh(neg), fresh(neg)
+        assert eng5.loss.neg_atomic
+        eng5.capture(dynamic_negatives=True)
+        eng6.capture(dynamic_negatives=True)
+        pipe = EpochPipeline(eng5)
+        for h in hosts:
+            g_ = pipe.result(pipe.submit(h)).clone()
+            eng6.set_negatives(h.to(DEV))
+            U.assert_close(eng6.epoch().cpu(), g_, tol=1e-5, what='pipelined vs synchronous step (float reductions)')
 
 
 def test_engine_first_step_tight(lib):
@@ -112,10 +122,14 @@ def test_engine_first_step_tight(lib):
 def test_dense_block_ni_matches_fullbatch_oracle(lib):
     """train_fullbatch's dense NI (gnndelete.py:163-193, 239-241): losses and Del gradients against the
     oracle's N x N formulation; the CUDA path only ever touches the S2 x S2 block."""
+    dense_ni_case(0.03)
+
+
+def dense_ni_case(scale):
     from gnndelete_b200 import models as M
     from gnndelete_b200.engine import GCNDeleteEngine
     from oracle import unlearn as OU
-    shape, raw, df, data, neg = U.make_case('cora', 0.03)
+    shape, raw, df, data, neg = U.make_case('cora', scale)
     om = U.oracle_model('gcn', shape, data, dtype=torch.float64)
     d64 = data.clone(); d64.x = data.x.double()
     with torch.no_grad():

@@ -11,9 +11,13 @@ DEV = 'cuda'
 
 @pytest.mark.parametrize('in_dim', [128, 500])
 def test_gat_delete_forward_and_grads(lib, in_dim):
+    gat_delete_case(in_dim, 0.1)
+
+
+def gat_delete_case(in_dim, scale):
     from gnndelete_b200 import models as M
     from oracle import unlearn as OU
-    shape, raw, df, data, neg = U.make_case('pubmed', 0.1, in_dim=in_dim)
+    shape, raw, df, data, neg = U.make_case('pubmed', scale, in_dim=in_dim)
     om = U.oracle_model('gat', shape, data, dtype=torch.float64)
     d64 = data.clone()
     d64.x = data.x.double()
@@ -75,11 +79,15 @@ def test_gat_isolated_and_hub_rows(lib):
 @pytest.mark.parametrize('num_edge_type', [51, 9])
 def test_rgcn_delete_forward_and_grads(lib, num_edge_type):
     """num_edge_type 51 -> block-diagonal weights (num_blocks=4), 9 -> dense relation weights."""
+    rgcn_delete_case(num_edge_type, 0.002)
+
+
+def rgcn_delete_case(num_edge_type, scale):
     import dataclasses
     from gnndelete_b200 import models as M
     from gnndelete_b200 import synthetic as S
     from oracle import unlearn as OU
-    shape = dataclasses.replace(S.SHAPES['biokg'].scaled(0.002), num_edge_type=num_edge_type)
+    shape = dataclasses.replace(S.SHAPES['biokg'].scaled(scale), num_edge_type=num_edge_type)
     raw = S.make_graph(shape, seed=42)
     df = S.sample_df_mask(shape.num_edges, shape.num_deleted, seed=42)
     data = OU.build_unlearning_data(raw, df, num_edge_type=num_edge_type)
