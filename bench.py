@@ -397,7 +397,9 @@ def run_partitioned(args, shape, rank, local, world, dev, lib, wire='bf16', one_
     def measure(w, r, group_world):
         """epochs/s of the partitioned engine over ``w`` ranks (w == 1: no process group, this rank alone)."""
         model.load_state_dict(init)
-        eng = PartitionedGCNDeleteEngine(model, data, neg, z_ori, wire=wire, world=w, rank=r)
+        eng = PartitionedGCNDeleteEngine(model, data, neg, z_ori, wire=wire, world=w, rank=r,
+                                         overlap_layer1=None if args.partition_overlap == 'auto' else False)
+        overlap = eng.overlap
         torch.cuda.synchronize()
         eng.epoch()                                       # first epoch: also builds the batch plans (one-time launches)
         c0 = lib.gd_launch_count()
@@ -413,7 +415,7 @@ def run_partitioned(args, shape, rank, local, world, dev, lib, wire='bf16', one_
         out = {'ms_per_step': ms / steps, 'value': steps / (ms / 1e3), 'launches_per_epoch': int(launches),
                'comm_ms_per_epoch': {k: v / steps for k, v in comm.items()}, 'losses_last': eng.losses.tolist(),
                'halo_bytes_per_epoch_per_rank_received': int(eng.halo_bytes_per_epoch * (w - 1) / w) if w > 1 else 0,
-               'rows_per_rank': [b[1] - b[0] for b in eng.plan.bounds]}
+               'rows_per_rank': [b[1] - b[0] for b in eng.plan.bounds], 'overlap_layer1': overlap}
         del eng
         torch.cuda.empty_cache()
         return out
@@ -436,6 +438,7 @@ def run_partitioned(args, shape, rank, local, world, dev, lib, wire='bf16', one_
         'launches_per_epoch': res['launches_per_epoch'], 'comm_ms_per_epoch': res['comm_ms_per_epoch'],
         'halo_bytes_per_epoch_per_rank_received': res['halo_bytes_per_epoch_per_rank_received'],
         'rows_per_rank': res['rows_per_rank'], 'losses_last': res['losses_last'], 'parity': parity, 'clocks': clocks,
+        'overlap_layer1_with_collectives': res['overlap_layer1'],
         'setup_s': setup_s,
     }
     if res['comm_ms_per_epoch']:
@@ -474,6 +477,8 @@ def main():
     ap.add_argument('--partition-workload', default='powerlaw10m')
     ap.add_argument('--partition-scale', type=float, default=1.0)
     ap.add_argument('--no-partitioned', action='store_true', help='N > 1: skip the row-partitioned config-5 block')
+    ap.add_argument('--partition-overlap', default='auto', choices=['auto', 'off'],
+                    help="'off': do not run the next epoch's layer-1 aggregation under the collectives (A/B measurements)")
     args = ap.parse_args()
     from gnndelete_b200 import synthetic as S
     shape = S.SHAPES[args.workload].scaled(args.scale)

@@ -67,6 +67,9 @@ SIGNATURES = {
     'gd_gat_bwd_src': (C.c_int, [_csr_p, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     'gd_rgcn_norm': (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     'gd_rgcn_conv': (C.c_int, [_csr_p, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
+    'gd_rgcn_edge_tile_rows': (_i32, [_i32, _i32]),
+    'gd_rgcn_edge_conv': (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp]),
+    'gd_rgcn_edge_reduce': (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp]),
     'gd_permute_f32': (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     'gd_gather_rows': (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i32, _vp, _i64, _vp, _vp]),
     'gd_gemm_rows': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),

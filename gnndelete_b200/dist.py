@@ -147,11 +147,15 @@ class PartitionedGCNDeleteEngine:
     """The epoch of ``engine.GCNDeleteEngine`` on one rank of the row partition."""
 
     def __init__(self, model, data, neg_edge_index, z_ori_full, group=None, hoist_gather=True, wire='bf16',
-                 lr=1e-3, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, balance=True, world=None, rank=None):
+                 lr=1e-3, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, balance=True, world=None, rank=None,
+                 overlap_layer1=None):
         """``wire``: 'bf16' (halo blocks travel and are gathered in bf16, fp32 accumulation; tolerance 2e-2) or
         'fp32' (1e-5).  ``hoist_gather``: the layer-1 block ``H0 = D^-1/2 X W1^T`` is frozen and input-constant, so
         it is transformed and exchanged once at setup; the layer-1 aggregation itself is still run every epoch (the
-        reference recomputes conv1 every epoch).  ``world`` / ``rank`` default to the process group's."""
+        reference recomputes conv1 every epoch).  ``world`` / ``rank`` default to the process group's.
+        ``overlap_layer1`` (default: on when ``world > 1`` and the H0 exchange is hoisted): the layer-1 aggregation of
+        epoch k + 1 depends on nothing epoch k produces, so it is issued on a side stream when epoch k enters its first
+        halo exchange and runs while the collectives of epoch k are on the wire (double-buffered ``a1``)."""
         if wire not in ('bf16', 'fp32'):
             raise ValueError(wire)
         if world is None:
@@ -191,7 +195,20 @@ class PartitionedGCNDeleteEngine:
         self.h1_loc = torch.empty(nl, out, **f32) if wire == 'bf16' else self.h1_send[:nl]
         self.z_loc = torch.empty(nl, out, **f32) if wire == 'bf16' else self.z_send[:nl]
         self.da2_loc = torch.empty(nl, out, **f32)
-        self.a1 = torch.empty(nl, hid, **f32); self.x1 = torch.empty(nl, hid, **f32)
+        self.overlap = bool(hoist_gather and self.world > 1) if overlap_layer1 is None else bool(overlap_layer1 and hoist_gather)
+        self.a1_bufs = [torch.empty(nl, hid, **f32) for _ in range(2 if self.overlap else 1)]
+        self.a1 = self.a1_bufs[0]
+        self.x1 = torch.empty(nl, hid, **f32)
+        if self.overlap:
+            # its own CSR object (same arrays): separate batch plans, i.e. separate split-row scratch / ticket state from
+            # the aggregations running concurrently on the main stream
+            self.csr1 = CSR(self.csr.rowptr, self.csr.col, self.csr.eid, None, nl, self.csr.nnz)
+            self.side = torch.cuda.Stream()
+            self.a1_ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self.epoch_done = torch.cuda.Event()
+            self._k, self._a1_pending = 0, False
+        else:
+            self.csr1 = self.csr
         self.a2 = torch.empty(nl, out, **f32)
         self.dz = torch.empty(nl, out, **f32)
         self.dh1 = torch.empty(nl, out, **f32)
@@ -303,16 +320,39 @@ class PartitionedGCNDeleteEngine:
         self._gather(self.h0_send, self.h0, 'allgather_h0')
         self._h0_done = True
 
+    def _layer1_aggregate(self, out):
+        ops.spmm(self.csr1, self.h0, out=out, row_scale=self.dinv, bias=self.model.conv1.bias.detach())
+
     def forward(self):
         m, nl = self.model, self.nl
         if not (self.hoist_gather and self._h0_done):
             self.gather_h0()
-        ops.spmm(self.csr, self.h0, out=self.a1, row_scale=self.dinv, bias=m.conv1.bias.detach())
+        main = torch.cuda.current_stream()
+        if self.overlap:
+            cur = self._k & 1
+            self.a1 = self.a1_bufs[cur]
+            if self._a1_pending:
+                main.wait_event(self.a1_ready[cur])               # issued during the previous epoch's collectives
+            else:
+                self._layer1_aggregate(self.a1)
+        else:
+            self._layer1_aggregate(self.a1)
         w1, w2 = m.deletion1.deletion_weight.detach(), m.deletion2.deletion_weight.detach()
         ops.gemm_rows(self.a1, w1, False, out=self.x1, rows=self.rows1)
         ops.copy_rows(self.a1, self.x1, self.comp1)
         ops.gemm_rows(self.x1, m.conv2.lin.weight.detach(), True, out=self.h1_loc, out_scale=self.dinv, relu_in=True)
         self._publish(self.h1_loc, self.h1_send)
+        if self.overlap:
+            # next epoch's layer-1 aggregation: its output buffer was last read by the PREVIOUS epoch's dW_del1 GEMM
+            nxt = 1 - (self._k & 1)
+            if self._k > 0:
+                self.side.wait_event(self.epoch_done)
+            else:
+                self.side.wait_stream(main)                       # H0 (exchanged at setup on the main stream) and the plans
+            with torch.cuda.stream(self.side):
+                self._layer1_aggregate(self.a1_bufs[nxt])
+                self.a1_ready[nxt].record(self.side)
+            self._a1_pending = True
         self._gather(self.h1_send, self.h1, 'allgather_h1')
         ops.spmm(self.csr, self.h1, out=self.a2, row_scale=self.dinv, bias=m.conv2.bias.detach())
         ops.gemm_rows(self.a2, w2, False, out=self.z_loc, rows=self.rows2)
@@ -369,6 +409,9 @@ class PartitionedGCNDeleteEngine:
         loss_r = self.red[n1 + n2]
         loss_l = self.red[n1 + n2 + 1] * (0.5 / self.plan.norm_ni if self.plan.norm_ni else 0.0)
         torch.stack([self.alpha * loss_r + (1.0 - self.alpha) * loss_l, loss_r, loss_l], out=self.losses)
+        if self.overlap:
+            self.epoch_done.record(torch.cuda.current_stream())      # a1 of this epoch is free from here on
+            self._k += 1
 
     def adam_step(self):
         for p, st in zip(self.params, self.state):

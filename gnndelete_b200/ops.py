@@ -322,7 +322,11 @@ class PairDecodeFn(torch.autograd.Function):
         return spmm(pairs.inc, z, val=val), None
 
 
-RGCN_MODE = os.environ.get('GD_RGCN', 'transform')      # 'tile': the one-kernel relation-tile path (gd_rgcn_conv)
+# 'edge' (default): one pass over relation-sorted edge tiles with register-resident weight slices (gd_rgcn_edge_conv,
+# block-diagonal weights); 'transform': transform-then-gather through a [R N, out] intermediate (the path for dense
+# relation weights); 'tile': the generic one-kernel relation-tile path (gd_rgcn_conv, any shape in {32, 64, 128})
+RGCN_MODE = os.environ.get('GD_RGCN', 'edge')
+RGCN_EDGE_CHUNK = 512                                    # edges per work item of the edge path
 RGCN_Y_LIMIT_BYTES = 32 << 30                            # per-call workspace cap of the transform-then-gather path
 
 
@@ -343,10 +347,83 @@ def _rgcn_dense_weights(plan, weight):
     return hit[1]
 
 
+class _RgcnEdgePlan:
+    """Work items of ``gd_rgcn_edge_conv`` for one direction of a relation-typed CSR: the entries of every tile of
+    ``tile_rows`` destination rows sorted by (relation, destination), cut into chunks of ``RGCN_EDGE_CHUNK`` edges."""
+
+    def __init__(self, csr, entry_weight, num_nodes, tile_rows):
+        dev = csr.rowptr.device
+        n, T = int(num_nodes), int(tile_rows)
+        rp = csr.rowptr.long()
+        deg = rp[1:] - rp[:-1]
+        dst = torch.repeat_interleave(torch.arange(n, device=dev), deg)
+        rel = csr.rel.long()
+        num_rel = int(rel.max().item()) + 1 if csr.nnz else 1
+        if num_rel >= (1 << 26):
+            raise ValueError('relation ids do not fit the packed edge word')
+        key = torch.div(dst, T, rounding_mode='floor') * (num_rel * T) + rel * T + dst % T
+        order = torch.argsort(key, stable=True)
+        self.ent_src = csr.col[order].to(torch.int32).contiguous()
+        self.ent_meta = ((rel[order] << 5) | (dst[order] % T)).to(torch.int32).contiguous()
+        self.ent_w = entry_weight[:csr.nnz][order].contiguous()
+        tiles = -(-n // T)
+        starts = torch.arange(0, tiles + 1, device=dev) * T
+        tile_ptr = rp[starts.clamp(max=n)]
+        ne = tile_ptr[1:] - tile_ptr[:-1]
+        nchunk = torch.clamp((ne + RGCN_EDGE_CHUNK - 1) // RGCN_EDGE_CHUNK, min=1)
+        tip = torch.zeros(tiles + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(nchunk, 0, out=tip[1:])
+        self.num_items = int(tip[-1].item())
+        item_tile = torch.repeat_interleave(torch.arange(tiles, device=dev), nchunk)
+        k_in = torch.arange(self.num_items, device=dev) - tip[item_tile]
+        beg = tile_ptr[item_tile] + k_in * RGCN_EDGE_CHUNK
+        end = torch.minimum(beg + RGCN_EDGE_CHUNK, tile_ptr[item_tile + 1])
+        i32 = lambda t: t.to(torch.int32).contiguous()                           # noqa: E731
+        self.item_tile, self.item_beg, self.item_end = i32(item_tile), i32(beg), i32(end)
+        self.tile_item_ptr = i32(tip)
+        self.tile_rows, self.num_rows = T, n
+        self._scratch = {}
+
+    def scratch(self, out_dim):
+        buf = self._scratch.get(out_dim)
+        if buf is None:
+            buf = torch.empty(max(self.num_items, 1) * self.tile_rows * out_dim, dtype=torch.float32, device=self.ent_w.device)
+            self._scratch[out_dim] = buf
+        return buf
+
+
+def _rgcn_edge_plan(plan, transposed, tile_rows):
+    cache = plan.__dict__.setdefault('_rgcn_edge', {})
+    key = (bool(transposed), int(tile_rows))
+    if key not in cache:
+        w_fwd, w_bwd = plan.rgcn_weights
+        csr = plan.bwd if transposed else plan.fwd
+        cache[key] = _RgcnEdgePlan(csr, w_bwd if transposed else w_fwd, plan.num_nodes, tile_rows)
+    return cache[key]
+
+
+def _rgcn_block_weights(plan, weight, transposed):
+    """Block weights in the layout the edge kernel reads: ``[R, B, in_block, out_block]`` of the direction being
+    computed (the transposed direction needs ``W_r^T`` blocks), cached until the parameter changes."""
+    if not transposed:
+        return weight
+    cache = plan.__dict__.setdefault('_rgcn_wt', {})
+    hit = cache.get(weight.data_ptr())
+    if hit is None or hit[0] is not weight or hit[1] != weight._version:
+        if len(cache) > 8:
+            cache.clear()
+        cache[weight.data_ptr()] = hit = (weight, weight._version, weight.transpose(2, 3).contiguous())
+    return hit[2]
+
+
 def rgcn_conv(plan, x, weight, root, bias, transposed=False, out=None):
     """RGCNConv forward (``transposed``: gradient w.r.t. the layer input).
 
-    Default path, transform-then-gather: ``Y_r = x . W_r`` for every relation on the tensor cores
+    Block-diagonal weights (``num_blocks = 4``, rgcn.py:17-22) take the edge path: ``x . root + bias`` on the tensor
+    cores, then ONE pass over relation-sorted edge tiles (``gd_rgcn_edge_conv`` / ``_reduce``) that keeps a relation's
+    weight slice in registers - no ``[R N, out]`` intermediate, no dense expansion of the blocks.
+
+    Dense relation weights (``GD_RGCN=transform`` forces it for blocks too), transform-then-gather: ``Y_r = x . W_r`` for every relation on the tensor cores
     (``gd_gemm_rows_tc``, one call per relation into one ``[R N, out]`` buffer), then ONE batched weighted
     aggregation over the virtual source index ``rel * N + col`` with the per-(destination, relation) mean
     weights (``gd_spmm_batched`` accumulating onto ``x . root + bias``).  With degree ~ R per node (BioKG:
@@ -364,7 +441,22 @@ def rgcn_conv(plan, x, weight, root, bias, transposed=False, out=None):
     fout = in_dim if transposed else out_dim
     n = x.shape[0]
     b = None if (bias is None or transposed) else bias.detach().contiguous()
-    vcsr = plan.rgcn_virtual(transposed) if RGCN_MODE == 'transform' else None
+    if RGCN_MODE == 'edge' and weight.dim() == 4 and blocks == 4 and n == plan.num_nodes and plan.fwd.rel is not None \
+            and x.stride(0) % 4 == 0:
+        ibe, obe = (ob, ib) if transposed else (ib, ob)
+        tile_rows = L.load().gd_rgcn_edge_tile_rows(int(ibe), int(obe))
+        if tile_rows:
+            ep = _rgcn_edge_plan(plan, transposed, tile_rows)
+            wb = _rgcn_block_weights(plan, weight, transposed)
+            out = gemm_rows(x, root, transposed, out=out, bias=b)        # x . root + bias   (g . root^T)
+            scratch = ep.scratch(fout)
+            L.call('gd_rgcn_edge_conv', L.ptr(ep.item_tile), L.ptr(ep.item_beg), L.ptr(ep.item_end), ep.num_items,
+                   L.ptr(ep.ent_src), L.ptr(ep.ent_meta), L.ptr(ep.ent_w), L.ptr(x), x.stride(0), L.ptr(wb), int(ibe), int(obe),
+                   L.ptr(scratch), L.stream())
+            L.call('gd_rgcn_edge_reduce', L.ptr(ep.tile_item_ptr), n, ep.tile_rows, fout, L.ptr(scratch), L.ptr(out),
+                   out.stride(0), L.stream())
+            return out
+    vcsr = plan.rgcn_virtual(transposed) if RGCN_MODE != 'tile' else None
     bp = vcsr.bplan(fout, True) if vcsr is not None and num_rel * n * fout * 4 <= RGCN_Y_LIMIT_BYTES else None
     if bp is not None and n == plan.num_nodes:
         wd = _rgcn_dense_weights(plan, weight)

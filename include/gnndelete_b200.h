@@ -254,6 +254,24 @@ int gd_rgcn_conv(const gd_csr_t* csr, const int32_t* rel, const float* entry_wei
                  int64_t ldx, const float* weight, const float* root, const float* bias,
                  int32_t num_rel, int32_t num_blocks, int32_t in_dim, int32_t out_dim,
                  int32_t transposed, float* out, int64_t ldo, gd_stream_t stream);
+/* RGCNConv with 4 block-diagonal relation weights as ONE pass over relation-sorted edge tiles
+ * (gnndelete_b200/csrc/rgcn_edge.cu; rgcn.py:17-22 with num_blocks = 4): no [R N, out] intermediate, no dense
+ * expansion of the blocks.  The host plan (gnndelete_b200/ops.py::_RgcnEdgePlan) sorts the entries of every tile of
+ * `tile_rows` destination rows by (relation, destination) and cuts them into work items [item_beg, item_end):
+ *   ent_src[e]  source row,  ent_meta[e] = relation << 5 | destination row inside its tile,
+ *   ent_w[e]    the mean weight 1 / |N_r(i)| of the entry (gd_rgcn_norm).
+ * gd_rgcn_edge_conv writes scratch[item, row in tile, :] = sum_e ent_w[e] * (x[ent_src[e], block] . W_rel[block]) for
+ * the edges of the item; gd_rgcn_edge_reduce adds the items of every tile, in order, ONTO out (which the caller has
+ * filled with x . root + bias).  weight: [R, 4, in_block, out_block] of the direction computed (pass W^T blocks and
+ * the transposed edge list for the gradient w.r.t. x).  (in_block, out_block) in {(32,16), (16,32), (32,32)};
+ * gd_rgcn_edge_tile_rows returns the tile height the kernel uses for a shape (0: not covered). */
+int32_t gd_rgcn_edge_tile_rows(int32_t in_block, int32_t out_block);
+int gd_rgcn_edge_conv(const int32_t* item_tile, const int32_t* item_beg, const int32_t* item_end, int64_t num_items,
+                      const int32_t* ent_src, const int32_t* ent_meta, const float* ent_w, const float* x,
+                      int64_t ldx, const float* weight, int32_t in_block, int32_t out_block, float* scratch,
+                      gd_stream_t stream);
+int gd_rgcn_edge_reduce(const int32_t* tile_item_ptr, int64_t num_rows, int32_t tile_rows, int32_t out_dim,
+                        const float* scratch, float* out, int64_t ldo, gd_stream_t stream);
 /* dst[perm[i]] = src[i] */
 int gd_permute_f32(const float* src, const int32_t* perm, int64_t n, float* dst, gd_stream_t stream);
 /* dst[i,:] = src[idx[i],:]  — nn.Embedding lookup `node_emb(x)` (rgcn.py:30); `status`

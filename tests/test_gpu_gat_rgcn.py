@@ -76,10 +76,47 @@ def test_gat_isolated_and_hub_rows(lib):
     U.assert_close(z2, ref2, what='gat hub z2')
 
 
-@pytest.mark.parametrize('num_edge_type', [51, 9])
-def test_rgcn_delete_forward_and_grads(lib, num_edge_type):
-    """num_edge_type 51 -> block-diagonal weights (num_blocks=4), 9 -> dense relation weights."""
+@pytest.mark.parametrize('num_edge_type,mode', [(51, 'edge'), (51, 'transform'), (51, 'tile'), (9, 'edge'), (9, 'tile')])
+def test_rgcn_delete_forward_and_grads(lib, num_edge_type, mode, monkeypatch):
+    """num_edge_type 51 -> block-diagonal weights (num_blocks=4), 9 -> dense relation weights; every RGCN execution
+    path (GD_RGCN): 'edge' (relation-sorted edge tiles, the default for block weights; dense weights fall through to
+    transform-then-gather), 'transform', 'tile' (generic relation-tile kernel)."""
+    from gnndelete_b200 import ops
+    monkeypatch.setattr(ops, 'RGCN_MODE', mode)
     rgcn_delete_case(num_edge_type, 0.002)
+
+
+def test_rgcn_edge_path_hub_rows_and_chunks(lib, monkeypatch):
+    """Edge path with work items much shorter than a tile's edge list (hub rows spread over several chunks) against
+    the generic tile kernel, forward and transposed, both layer shapes."""
+    import dataclasses
+    from gnndelete_b200 import graph as G
+    from gnndelete_b200 import ops
+    from gnndelete_b200 import synthetic as S
+    shape = dataclasses.replace(S.SHAPES['biokg'].scaled(0.004), num_edge_type=51)
+    raw = S.make_graph(shape, seed=1)
+    ei = torch.cat([raw.train_pos_edge_index, raw.train_pos_edge_index.flip(0)], 1).to(DEV)
+    et = torch.cat([raw.train_edge_type, raw.train_edge_type + 51]).to(DEV)
+    n = shape.num_nodes
+    g = torch.Generator().manual_seed(2)
+    for (fin, fout) in ((128, 64), (128, 128)):
+        w = (torch.randn(102, 4, fin // 4, fout // 4, generator=g) * 0.2).to(DEV)
+        root = (torch.randn(fin, fout, generator=g) * 0.1).to(DEV)
+        bias = torch.randn(fout, generator=g).to(DEV)
+        x = torch.randn(n, fin, generator=g).to(DEV)
+        gout = torch.randn(n, fout, generator=g).to(DEV)
+        plan = G.GraphPlan(ei, n, False, et, 102)
+        monkeypatch.setattr(ops, 'RGCN_MODE', 'tile')
+        ref = ops.rgcn_conv(plan, x, w, root, bias)
+        ref_t = ops.rgcn_conv(plan, gout, w, root, None, transposed=True)
+        monkeypatch.setattr(ops, 'RGCN_MODE', 'edge')
+        monkeypatch.setattr(ops, 'RGCN_EDGE_CHUNK', 64)
+        got = ops.rgcn_conv(plan, x, w, root, bias)
+        got_t = ops.rgcn_conv(plan, gout, w, root, None, transposed=True)
+        assert '_rgcn_edge' in plan.__dict__, 'the edge path must have been taken'
+        U.assert_close(got, ref, what=f'edge vs tile {fin}->{fout}')
+        U.assert_close(got_t, ref_t, what=f'edge vs tile transposed {fin}->{fout}')
+        assert torch.equal(ops.rgcn_conv(plan, x, w, root, bias), got), 'bitwise reproducible'
 
 
 def rgcn_delete_case(num_edge_type, scale):
