@@ -460,6 +460,132 @@ def run_partitioned(args, shape, rank, local, world, dev, lib, wire='bf16', one_
     return block
 
 
+# ------------------------------------------------------------------ KG config (4)
+def rgcn_algo_bytes(n, nnz, num_rel, fin, fout):
+    """SURVEY.md §8(d) RGCN row: rowptr + col + relation id (uint8) + read N*in + write N*out + block weights."""
+    return 4 * (n + 1) + 4 * nnz + nnz + 4 * n * fin + 4 * n * fout + 4 * num_rel * fin * fout // 4
+
+
+def run_kg(args, shape, rank, local, dev, lib):
+    """BASELINE config 4: RGCNDelete on the BioKG shape, the KG node-embedding step (gnndelete_nodeemb.py:744-798)
+    through framework.get_trainer(args).start(...): forward, two backward passes, two Adam steps per step."""
+    import tempfile
+    import framework
+    from gnndelete_b200 import masks as MK
+    from gnndelete_b200 import ops
+    from gnndelete_b200 import synthetic as S
+    from gnndelete_b200.graph import plan_for
+    from gnndelete_b200.kg import negative_sampling_kg
+    net = shape.num_edge_type
+    raw = S.make_graph(shape, seed=42, device='cpu').to(dev)
+    df = S.sample_df_mask(shape.num_edges, shape.num_deleted, seed=42, device='cpu').to(dev)
+    data = MK.build_unlearning_data(raw, df, num_edge_type=net)
+    pos_ei, pos_et = data.edge_index[:, data.df_mask], data.edge_type[data.df_mask]
+    dec = pos_et < net
+    neg = negative_sampling_kg(pos_ei[:, dec], pos_et[dec], torch.Generator(device=dev).manual_seed(43))   # supplied (§8(d))
+
+    def session(capture, with_neg):
+        targs = types.SimpleNamespace(unlearning_model='gnndelete', gnn='rgcn', dataset='ogbl-biokg-shaped', epochs=0,
+                                      valid_freq=10 ** 9, checkpoint_dir=tempfile.mkdtemp(prefix='gd_bench_kg_'), in_dim=shape.in_dim,
+                                      hidden_dim=shape.hidden_dim, out_dim=shape.out_dim, lr=1e-3, alpha=0.5, random_seed=42,
+                                      num_edge_type=net, capture_step=capture, device=str(dev), loss_fct='mse_mean',
+                                      loss_type='both_layerwise', eval_on_cpu=False)
+        torch.manual_seed(42)
+        model = framework.get_model(targs, data.sdf_node_1hop_mask, data.sdf_node_2hop_mask, num_nodes=data.num_nodes,
+                                    num_edge_type=net).to(dev)
+        opt = [torch.optim.Adam([model.deletion1.deletion_weight], lr=1e-3), torch.optim.Adam([model.deletion2.deletion_weight], lr=1e-3)]
+        d = data.clone()
+        if with_neg:
+            d.neg_edge_index = neg
+        trainer = framework.get_trainer(targs)
+        return trainer, trainer.start(model, d, opt, targs), model
+
+    trainer, sess, model = session(True, True)
+    sess.step()
+    c0 = lib.gd_launch_count()
+    if sess.graph is None:
+        sess.step()
+    launches = lib.gd_launch_count() - c0
+    for _ in range(args.warmup):
+        sess.step()
+    st = torch.cuda.current_stream()
+    sampler = ClockSampler(local)
+    sampler.start()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record(st)
+    for _ in range(args.steps):
+        sess.step()
+    b.record(st)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = a.elapsed_time(b)
+    losses = sess.out.tolist()
+    # the relation aggregation kernels on their own (layer-2 forward and its transpose): CUDA events, eager
+    peak, peak_src = load_peaks()
+    ei, et = sess.edge_index, sess.edge_type
+    plan = plan_for(ei, shape.num_nodes, 'rgcn', et, 2 * net)
+    n, nnz, R = shape.num_nodes, int(ei.shape[1]), 2 * net
+    g = torch.Generator(device=dev).manual_seed(1)
+    x = torch.randn(n, shape.hidden_dim, generator=g, device=dev)
+    go = torch.randn(n, shape.out_dim, generator=g, device=dev)
+    c2 = model.conv2
+    kt = {}
+    for name, fn in (('rgcn_conv2_fwd_128_64', lambda: ops.rgcn_conv(plan, x, c2.weight, c2.root, c2.bias)),
+                     ('rgcn_conv2_transposed_64_128', lambda: ops.rgcn_conv(plan, go, c2.weight, c2.root, None, transposed=True))):
+        for _ in range(3):
+            fn()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        for e0, e1 in ev:
+            e0.record(st); fn(); e1.record(st)
+        torch.cuda.synchronize()
+        kt[name] = sum(e0.elapsed_time(e1) for e0, e1 in ev) / len(ev)
+    bts = {'rgcn_conv2_fwd_128_64': rgcn_algo_bytes(n, nnz, R, shape.hidden_dim, shape.out_dim),
+           'rgcn_conv2_transposed_64_128': rgcn_algo_bytes(n, nnz, R, shape.out_dim, shape.hidden_dim)}
+    flops = 2.0 * nnz * shape.hidden_dim * shape.out_dim / 4 + 2.0 * n * shape.hidden_dim * shape.out_dim
+    kern = {k: {'ms': kt[k], 'algo_bytes': bts[k], 'gbs': bts[k] / (kt[k] * 1e-3) / 1e9, 'frac': bts[k] / (kt[k] * 1e-3) / 1e9 / peak,
+                'fp32_tflops': flops / (kt[k] * 1e-3) / 1e12} for k in kt}
+    dom = max(kt, key=kt.get)
+    roofline = {'kernel': f'gd::rgcn_edge_kernel + reduce + root GEMM ({dom})', 'bound': 'hbm', 'achieved': kern[dom]['gbs'], 'peak': peak,
+                'unit': 'GB/s', 'frac': kern[dom]['frac'], 'traffic': None, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': bts[dom], 'kernel_ms': kt[dom], 'other_kernels': {k: v for k, v in kern.items() if k != dom},
+                'note': 'per-edge block products (2 nnz in out / 4 flops) on the fp32 FMA pipes: this kernel is FMA / latency bound, '
+                        'far from the HBM roofline of its compulsory bytes (fp32_tflops column)'}
+    # e2e: a session that takes this step's corrupted triples from pinned host memory (eager: the loss incidence is rebuilt)
+    _, sess_e, _ = session(False, False)
+    neg_host = neg.cpu().pin_memory()
+    out_host = torch.empty(3, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        out_host.copy_(sess_e.step(neg_host), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    k = min(args.steps, 30)
+    t0 = time.perf_counter()
+    for _ in range(k):
+        e2e_step()
+    e2e_s = time.perf_counter() - t0
+    line = {'metric': metric_name(shape), 'value': args.steps / (ms / 1e3), 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(shape), 'where': 'B200', 'roofline': roofline,
+            'e2e': {'value': k / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': neg_host.numel() * 8, 'd2h_bytes_per_step': 12, 'steps': k,
+                    'what': 'KGNodeembSession.step(negatives=pinned host triples): H2D, rebuild of the two loss incidences, the step '
+                            '(eager launches), losses -> pinned host'},
+            'gpu_launches': int(launches * args.steps), 'launches_per_epoch': int(launches), 'captured_step': sess.graph is not None,
+            'clocks': clocks, 'losses_last': losses, 'parallelism': 'single'}
+    if not args.no_cpu_baseline:
+        epoch, cores = cpu_epoch_runner(shape)
+        epoch()
+        t0 = time.perf_counter()
+        epoch()
+        dt = time.perf_counter() - t0
+        line['cpu_baseline'] = {'value': 1.0 / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                'sample': '1 full KG step of the same workload (after 1 warm-up)'}
+    print(json.dumps(line), flush=True)
+
+
 # --------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -513,6 +639,11 @@ def main():
             import torch.distributed as dist
             dist.destroy_process_group()
         return
+
+    if shape.gnn == 'rgcn':
+        if world > 1:
+            raise SystemExit('the KG config runs on one GPU')
+        return run_kg(args, shape, rank, local, dev, lib)
 
     data, neg, model, z_ori = build_case(shape, 42 + rank, dev)
     n = shape.num_nodes

@@ -27,82 +27,114 @@ struct RgcnEdgeArgs {
     int32_t num_items;
 };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // IB / OB: rows / columns of one weight block (4 blocks).  CPL: output columns per lane and pass; a pass covers 32 CPL
 // columns, PASSES = 4 OB / (32 CPL).  T: destination rows per tile (meta = relation << 5 | row in tile).
+// The source rows of the next G edges are staged in shared memory with cp.async while the current G edges are
+// multiplied (the first version loaded x_src into registers and used it at once: one edge in flight per warp, 16 warps
+// per SM at 128 registers -> latency bound at ~4 G edges/s).
 template <int IB, int OB, int CPL, int T>
 __global__ void __launch_bounds__(256, 2) rgcn_edge_kernel(const RgcnEdgeArgs a) {
-    constexpr int OUT = 4 * OB, PASSES = OUT / (32 * CPL), NX = IB / 4;
+    constexpr int IN = 4 * IB, OUT = 4 * OB, PASSES = OUT / (32 * CPL), NX = IB / 4, G = 4;
+    constexpr int WARP_FLOATS = T * OUT + 2 * G * IN;
     static_assert(IB * CPL == 64, "a lane keeps 64 weights");
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* tile = smem + warp * (T * OUT);
+    float* tile = smem + warp * WARP_FLOATS;
+    float* xs = tile + T * OUT;                                   // [2][G][IN]
     const int warps_total = (gridDim.x * blockDim.x) >> 5;
     for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < a.num_items; item += warps_total) {
         const int e0 = __ldg(a.item_beg + item), e1 = __ldg(a.item_end + item);
         for (int i = lane; i < T * OUT / 4; i += 32) reinterpret_cast<float4*>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();
+        const int ngroups = (e1 - e0 + G - 1) / G;
+        auto stage_rows = [&](int g) {                            // source rows of edge group g -> xs[g & 1]
+            if (g < ngroups && lane < IN / 4) {
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    const int e = e0 + g * G + j;
+                    if (e < e1) cp_async16(xs + ((g & 1) * G + j) * IN + 4 * lane, a.x + (int64_t)__ldg(a.ent_src + e) * a.ldx + 4 * lane);
+                }
+            }
+            cp_async_commit();
+        };
 #pragma unroll 1
         for (int pass = 0; pass < PASSES; ++pass) {
             const int c0 = pass * 32 * CPL + lane * CPL;          // first output column of this lane
             const int b = c0 / OB;                                // its block
             const float* wl = a.weight + (int64_t)b * IB * OB + (c0 - b * OB);
-            const float* xl = a.x + b * IB;
             unsigned long long wreg[IB / 2][CPL];                 // packed over input pairs: {W[2q][c], W[2q+1][c]}
             int cur_rel = -1;
-            int src = 0, meta = 0; float w = 0.f;
-            if (e0 < e1) { src = __ldg(a.ent_src + e0); meta = __ldg(a.ent_meta + e0); w = __ldg(a.ent_w + e0); }
+            stage_rows(0);
 #pragma unroll 1
-            for (int e = e0; e < e1; ++e) {
-                // this edge's inputs (the 8 lanes of a block read the same 16-byte words)
-                float4 xv[NX];
-                const float4* xp = reinterpret_cast<const float4*>(xl + (int64_t)src * a.ldx);
+            for (int g = 0; g < ngroups; ++g) {
+                stage_rows(g + 1);
+                int metas[G]; float ws[G];
 #pragma unroll
-                for (int q = 0; q < NX; ++q) xv[q] = __ldg(xp + q);
-                const int rel = meta >> 5, dl = meta & 31;
-                const float we = w;
-                if (e + 1 < e1) { src = __ldg(a.ent_src + e + 1); meta = __ldg(a.ent_meta + e + 1); w = __ldg(a.ent_w + e + 1); }
-                if (rel != cur_rel) {                             // warp-uniform: new relation group, reload the weight slice
-                    cur_rel = rel;
-                    const float* wr = wl + (int64_t)rel * 4 * IB * OB;
-#pragma unroll
-                    for (int q = 0; q < IB / 2; ++q) {
-                        float lo[CPL], hi[CPL];
-                        if (CPL == 2) {
-                            const float2 u = __ldg(reinterpret_cast<const float2*>(wr + (2 * q) * OB));
-                            const float2 v = __ldg(reinterpret_cast<const float2*>(wr + (2 * q + 1) * OB));
-                            lo[0] = u.x; lo[1] = u.y; hi[0] = v.x; hi[1] = v.y;
-                        } else {
-                            const float4 u = __ldg(reinterpret_cast<const float4*>(wr + (2 * q) * OB));
-                            const float4 v = __ldg(reinterpret_cast<const float4*>(wr + (2 * q + 1) * OB));
-                            lo[0] = u.x; lo[1] = u.y; lo[2 % CPL] = u.z; lo[3 % CPL] = u.w;
-                            hi[0] = v.x; hi[1] = v.y; hi[2 % CPL] = v.z; hi[3 % CPL] = v.w;
-                        }
-#pragma unroll
-                        for (int c = 0; c < CPL; ++c) asm("mov.b64 %0, {%1, %2};" : "=l"(wreg[q][c]) : "f"(lo[c]), "f"(hi[c]));
-                    }
+                for (int j = 0; j < G; ++j) {
+                    const int e = min(e0 + g * G + j, e1 - 1);
+                    metas[j] = __ldg(a.ent_meta + e); ws[j] = __ldg(a.ent_w + e);
                 }
-                unsigned long long acc[CPL];
+                cp_async_wait<1>();
+                __syncwarp();
 #pragma unroll
-                for (int c = 0; c < CPL; ++c) acc[c] = 0ull;
+                for (int j = 0; j < G; ++j) {
+                    if (e0 + g * G + j >= e1) break;
+                    const int rel = metas[j] >> 5, dl = metas[j] & 31;
+                    if (rel != cur_rel) {                         // warp-uniform: new relation group, reload the weight slice
+                        cur_rel = rel;
+                        const float* wr = wl + (int64_t)rel * 4 * IB * OB;
 #pragma unroll
-                for (int q = 0; q < NX; ++q) {
-                    unsigned long long x01, x23;
-                    asm("mov.b64 %0, {%1, %2};" : "=l"(x01) : "f"(xv[q].x), "f"(xv[q].y));
-                    asm("mov.b64 %0, {%1, %2};" : "=l"(x23) : "f"(xv[q].z), "f"(xv[q].w));
+                        for (int q = 0; q < IB / 2; ++q) {
+                            float lo[CPL], hi[CPL];
+                            if (CPL == 2) {
+                                const float2 u = __ldg(reinterpret_cast<const float2*>(wr + (2 * q) * OB));
+                                const float2 v = __ldg(reinterpret_cast<const float2*>(wr + (2 * q + 1) * OB));
+                                lo[0] = u.x; lo[1] = u.y; hi[0] = v.x; hi[1] = v.y;
+                            } else {
+                                const float4 u = __ldg(reinterpret_cast<const float4*>(wr + (2 * q) * OB));
+                                const float4 v = __ldg(reinterpret_cast<const float4*>(wr + (2 * q + 1) * OB));
+                                lo[0] = u.x; lo[1] = u.y; lo[2 % CPL] = u.z; lo[3 % CPL] = u.w;
+                                hi[0] = v.x; hi[1] = v.y; hi[2 % CPL] = v.z; hi[3 % CPL] = v.w;
+                            }
+#pragma unroll
+                            for (int c = 0; c < CPL; ++c) asm("mov.b64 %0, {%1, %2};" : "=l"(wreg[q][c]) : "f"(lo[c]), "f"(hi[c]));
+                        }
+                    }
+                    // the IB inputs of this lane's block (the 8 lanes of a block read the same words: broadcast)
+                    const float4* xp = reinterpret_cast<const float4*>(xs + ((g & 1) * G + j) * IN + b * IB);
+                    unsigned long long acc[CPL];
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) acc[c] = 0ull;
+#pragma unroll
+                    for (int q = 0; q < NX; ++q) {
+                        const float4 xv = xp[q];
+                        unsigned long long x01, x23;
+                        asm("mov.b64 %0, {%1, %2};" : "=l"(x01) : "f"(xv.x), "f"(xv.y));
+                        asm("mov.b64 %0, {%1, %2};" : "=l"(x23) : "f"(xv.z), "f"(xv.w));
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) {
+                            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[c]) : "l"(x01), "l"(wreg[2 * q][c]));
+                            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[c]) : "l"(x23), "l"(wreg[2 * q + 1][c]));
+                        }
+                    }
+                    float* tp = tile + dl * OUT + c0;
 #pragma unroll
                     for (int c = 0; c < CPL; ++c) {
-                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[c]) : "l"(x01), "l"(wreg[2 * q][c]));
-                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[c]) : "l"(x23), "l"(wreg[2 * q + 1][c]));
+                        float s0, s1;
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(acc[c]));
+                        tp[c] = fmaf(ws[j], s0 + s1, tp[c]);
                     }
                 }
-                float* tp = tile + dl * OUT + c0;
-#pragma unroll
-                for (int c = 0; c < CPL; ++c) {
-                    float s0, s1;
-                    asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(acc[c]));
-                    tp[c] = fmaf(we, s0 + s1, tp[c]);
-                }
+                __syncwarp();                                     // the staging buffer of this group is refilled two groups on
             }
+            cp_async_wait<0>();
         }
         __syncwarp();
         float4* sp = reinterpret_cast<float4*>(a.scratch + (int64_t)item * (T * OUT));
@@ -133,7 +165,7 @@ __global__ void __launch_bounds__(256) rgcn_edge_reduce_kernel(const int32_t* __
 
 template <int IB, int OB, int CPL, int T>
 static int launch_rgcn_edge(const RgcnEdgeArgs& a, cudaStream_t stream) {
-    constexpr int smem = 8 * T * 4 * OB * (int)sizeof(float);
+    constexpr int smem = 8 * (T * 4 * OB + 2 * 4 * 4 * IB) * (int)sizeof(float);
     static bool configured = false;
     if (!configured) {
         GD_CUDA(cudaFuncSetAttribute(rgcn_edge_kernel<IB, OB, CPL, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

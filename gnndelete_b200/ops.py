@@ -409,7 +409,8 @@ def _rgcn_block_weights(plan, weight, transposed):
         return weight
     cache = plan.__dict__.setdefault('_rgcn_wt', {})
     hit = cache.get(weight.data_ptr())
-    if hit is None or hit[0] is not weight or hit[1] != weight._version:
+    # the entry holds a tensor on the same storage (keeps the address from being reused) and the storage's version
+    if hit is None or hit[0].shape != weight.shape or hit[1] != weight._version:
         if len(cache) > 8:
             cache.clear()
         cache[weight.data_ptr()] = hit = (weight, weight._version, weight.transpose(2, 3).contiguous())

@@ -716,13 +716,14 @@ class KGGNNDeleteNodeembTrainer(KGTrainer):
 
     log_every = 10
 
-    def train(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
+    def start(self, model, data, optimizer, args):
+        """Set up the KG unlearning run and return its :class:`KGNodeembSession` (one ``session.step()`` per epoch)."""
         from .kg import negative_sampling_kg
-        from .losses import RowMSEPlan, row_mse
+        from .losses import RowMSEPlan
         if not isinstance(optimizer, (list, tuple)) or len(optimizer) != 2:
             raise ValueError('expects the [optimizer1, optimizer2] pair built for *layerwise loss types '
                              '(delete_gnn.py:221-226)')
-        dev = torch.device('cuda')
+        dev = torch.device(getattr(args, 'device', None) or 'cuda')
         model = model.to(dev)
         data = data.to(dev)
         alpha = args.alpha
@@ -745,39 +746,138 @@ class KGGNNDeleteNodeembTrainer(KGTrainer):
         neg = fixed_neg if fixed_neg is not None else negative_sampling_kg(dec_ei, dec_et, gen)
         plan1 = RowMSEPlan(dec_ei, neg, m1, z1o, mix=(alpha, 1 - alpha))
         plan2 = RowMSEPlan(dec_ei, neg, m2, z2o, mix=(alpha, 1 - alpha))
+        sess = KGNodeembSession(self, model, data, optimizer, edge_index, edge_type, m1, m2, plan1, plan2, dec_ei, dec_et,
+                                gen, resample=fixed_neg is None)
+        if getattr(args, 'capture_step', True) and fixed_neg is not None:
+            sess.capture()
+        self.trainer_log['captured_step'] = sess.graph is not None
+        return sess
+
+    def train(self, model, data, optimizer, args, logits_ori=None, attack_model_all=None, attack_model_sub=None):
+        sess = self.start(model, data, optimizer, args)
+        model, data = sess.model, sess.data
         ring, best_metric = [], 0
         for epoch in range(args.epochs):
             model.train()
-            z1, z2 = model(data.x, edge_index, edge_type, m1, m2, return_all_emb=True)
-            if fixed_neg is None and epoch > 0:                                      # :764-768, new heads every step
-                neg = negative_sampling_kg(dec_ei, dec_et, gen)
-                plan1.set_pairs(dec_ei, neg)
-                plan2.set_pairs(dec_ei, neg)
-            loss1, loss_r1, loss_l1 = row_mse(z1, plan1)                             # :788-796
-            loss2, loss_r2, loss_l2 = row_mse(z2, plan2)
-            loss1.backward(retain_graph=True)
-            optimizer[0].step()
-            optimizer[0].zero_grad()
-            loss2.backward(retain_graph=True)
-            optimizer[1].step()
-            optimizer[1].zero_grad()
-            ring.append(torch.stack([(loss1 + loss2).detach(), loss_r1 + loss_r2, loss_l1 + loss_l2]))
+            ring.append(sess.step().clone())
             if (epoch + 1) % self.log_every == 0 or epoch + 1 == args.epochs:
                 for i, v in enumerate(torch.stack(ring).cpu().tolist()):
                     self.trainer_log['log'].append({'Epoch': epoch + 1 - len(ring) + i, 'train_loss': v[0],
                                                     'loss_r': v[1], 'loss_l': v[2]})
                 ring = []
             if (epoch + 1) % args.valid_freq == 0:                                   # :815-841
-                del z1, z2, loss1, loss2
                 valid_loss, dt_auc, dt_aup, df_auc, df_aup, _, _, valid_log = self.eval(model, data, 'val')
                 valid_log['epoch'] = epoch
                 self.trainer_log['log'].append(valid_log)
                 if dt_auc + df_auc > best_metric:
                     best_metric = dt_auc + df_auc
+                    sess.mirror_optimizers()
                     torch.save({'model_state': model.state_dict()}, os.path.join(args.checkpoint_dir, 'model_best.pt'))
+        sess.mirror_optimizers()
         torch.save({'model_state': {k: v.to('cpu') for k, v in model.state_dict().items()}},
                    os.path.join(args.checkpoint_dir, 'model_final.pt'))
         return model
+
+
+class KGNodeembSession:
+    """One KG unlearning run in progress (``KGGNNDeleteNodeembTrainer.start``).  ``step()`` is the reference's step
+    body (gnndelete_nodeemb.py:744-798) with its literal schedule: ``loss1.backward`` -> Adam on deletion1 ->
+    ``loss2.backward`` -> Adam on deletion2, where ``loss2.backward`` also leaves a deletion1 gradient that stays in
+    ``.grad`` until the next step's first Adam update.  Adam runs through ``gd_adam_step`` on the hyper-parameters of the
+    caller's two optimizers (device-side step counters, so the whole step is capturable into ONE CUDA graph when the
+    negatives are fixed); the moments are mirrored into the optimizers when checkpoints are written."""
+
+    def __init__(self, trainer, model, data, optimizers, edge_index, edge_type, m1, m2, plan1, plan2, dec_ei, dec_et,
+                 generator, resample):
+        self.trainer, self.model, self.data, self.optimizers = trainer, model, data, list(optimizers)
+        self.edge_index, self.edge_type, self.m1, self.m2 = edge_index, edge_type, m1, m2
+        self.plan1, self.plan2, self.dec_ei, self.dec_et = plan1, plan2, dec_ei, dec_et
+        self.gen, self.resample = generator, resample
+        dev = data.x.device
+        self.groups = []
+        for opt in self.optimizers:
+            g = opt.param_groups[0]
+            ps = [p for grp in opt.param_groups for p in grp['params']]
+            st = [dict(m=torch.zeros_like(p), v=torch.zeros_like(p), step=torch.zeros(1, dtype=torch.float32, device=dev)) for p in ps]
+            for p in ps:
+                p.grad = torch.zeros_like(p)          # kept as tensors (zeroed, never None): static addresses for the graph
+            self.groups.append((g, ps, st))
+        self.out = torch.zeros(3, dtype=torch.float32, device=dev)
+        self.graph = None
+        self.epochs_done = 0
+
+    def _adam(self, k):
+        g, ps, st = self.groups[k]
+        for p, s_ in zip(ps, st):
+            ops.adam_step(p.data, p.grad, s_['m'], s_['v'], s_['step'], g['lr'], g['betas'][0], g['betas'][1], g['eps'])
+            p.grad.zero_()                            # optimizer.zero_grad() of the schedule
+
+    def _body(self):
+        from .losses import row_mse
+        z1, z2 = self.model(self.data.x, self.edge_index, self.edge_type, self.m1, self.m2, return_all_emb=True)
+        loss1, loss_r1, loss_l1 = row_mse(z1, self.plan1)                        # :788-796
+        loss2, loss_r2, loss_l2 = row_mse(z2, self.plan2)
+        loss1.backward(retain_graph=True)
+        self._adam(0)
+        loss2.backward(retain_graph=True)
+        self._adam(1)
+        self.out.copy_(torch.stack([(loss1 + loss2).detach(), loss_r1 + loss_r2, loss_l1 + loss_l2]))
+
+    def capture(self, warmup=2):
+        """Capture one step into a CUDA graph (fixed negatives only).  Warm-up steps run first and are undone."""
+        params = [p for _, ps, _ in self.groups for p in ps]
+        snap_p = [p.detach().clone() for p in params]
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self._body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body()
+            self.graph = g
+        except Exception as exc:                      # capture is an optimisation: fall back to eager steps
+            self.trainer.trainer_log['capture_error'] = repr(exc)
+            self.graph = None
+            torch.cuda.synchronize()
+        with torch.no_grad():                         # undo the warm-up / capture steps
+            for p, s0 in zip(params, snap_p):
+                p.copy_(s0)
+                p.grad.zero_()
+            for _, _, st in self.groups:
+                for s_ in st:
+                    for v in s_.values():
+                        v.zero_()
+
+    def step(self, negatives=None):
+        """One step; returns the persistent device tensor (loss1 + loss2, loss_r1 + loss_r2, loss_l1 + loss_l2).
+        ``negatives``: this step's corrupted triples ``[2, n]`` (host or device); rebuilds the loss incidence, so it is
+        only accepted by a session that was not captured."""
+        if negatives is not None:
+            if self.graph is not None:
+                raise RuntimeError('per-step negatives need an uncaptured session (args.capture_step = False)')
+            neg = negatives.to(self.dec_ei.device, non_blocking=True)
+            self.plan1.set_pairs(self.dec_ei, neg)
+            self.plan2.set_pairs(self.dec_ei, neg)
+        elif self.resample and self.epochs_done > 0:                             # :764-768, new heads every step
+            from .kg import negative_sampling_kg
+            neg = negative_sampling_kg(self.dec_ei, self.dec_et, self.gen)
+            self.plan1.set_pairs(self.dec_ei, neg)
+            self.plan2.set_pairs(self.dec_ei, neg)
+        self.epochs_done += 1
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._body()
+        return self.out
+
+    def mirror_optimizers(self):
+        for opt, (_, ps, st) in zip(self.optimizers, self.groups):
+            for p, s_ in zip(ps, st):
+                opt.state[p] = {'step': s_['step'].detach().cpu().reshape(()).clone(), 'exp_avg': s_['m'], 'exp_avg_sq': s_['v']}
 
 
 # ---- node-embedding loss functions of gnndelete_nodeemb.py:19-92 (the non-MSE members run as device tensor ops

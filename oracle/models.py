@@ -77,6 +77,16 @@ class RGCNConv(nn.Module):
 
 
 # ------------------------------------------------------------------ base encoders
+# Test hook: a *Delete model whose attribute ``relu_mask_override`` holds a bool tensor uses it instead of the sign test of
+# the inter-layer ReLU (``relu(x) := x * mask``) in its Delete forward.  A parity test sets it to the mask the
+# implementation under test produced when some pre-activation lies within rounding distance of zero: there the fp64 and
+# fp32 forward passes may disagree on the sign, and d relu / dx jumps by a finite amount.
+def _relu(x, mask=None):
+    if mask is not None:
+        return x * mask.to(x.dtype)
+    return F.relu(x)
+
+
 class _TwoLayer(nn.Module):
     """conv1 -> ReLU -> conv2, no dropout (gcn.py:15-24, gat.py:15-24, gin.py:26-34)."""
     conv_cls = None
@@ -162,7 +172,7 @@ def _delete_variant(base, conv1_no_grad):
             else:                                   # deletion.py:62-63 (GCN: no_grad commented out)
                 x1 = self.conv1(x, edge_index)
             x1 = self.deletion1(x1, mask_1hop)
-            x2 = self.conv2(F.relu(x1), edge_index)
+            x2 = self.conv2(_relu(x1, getattr(self, 'relu_mask_override', None)), edge_index)
             x2 = self.deletion2(x2, mask_2hop)
             return (x1, x2) if return_all_emb else x2
 
@@ -189,7 +199,7 @@ class RGCNDelete(RGCN):                                              # deletion.
             x = self.node_emb(x)
             x1 = self.conv1(x, edge_index, edge_type)
         x1 = self.deletion1(x1, mask_1hop)
-        x2 = self.conv2(F.relu(x1), edge_index, edge_type)
+        x2 = self.conv2(_relu(x1, getattr(self, 'relu_mask_override', None)), edge_index, edge_type)
         x2 = self.deletion2(x2, mask_2hop)
         return (x1, x2) if return_all_emb else x2
 

@@ -52,7 +52,7 @@ def coalesce(edge_index, edge_attrs, num_nodes=None):
     slot = torch.cumsum(first.to(torch.int64), 0) - 1
     out_attrs = []
     for a in edge_attrs:
-        o = torch.zeros((int(first.sum()),) + tuple(a.shape[1:]), dtype=a.dtype)
+        o = torch.zeros((int(first.sum()),) + tuple(a.shape[1:]), dtype=a.dtype, device=a.device)
         o.index_add_(0, slot, a)
         out_attrs.append(o)
     return edge_index[:, first], out_attrs
@@ -77,9 +77,9 @@ def k_hop_subgraph(node_idx, num_hops, edge_index, num_nodes=None):
     that walks only to lower-index neighbours."""
     n = maybe_num_nodes(edge_index, num_nodes)
     col, row = edge_index[0], edge_index[1]
-    node_idx = torch.as_tensor(node_idx, dtype=torch.int64).flatten()
+    node_idx = torch.as_tensor(node_idx, dtype=torch.int64, device=edge_index.device).flatten()
     subsets = [node_idx]
-    node_mask = torch.zeros(n, dtype=torch.bool)
+    node_mask = torch.zeros(n, dtype=torch.bool, device=edge_index.device)
     for _ in range(num_hops):
         node_mask.fill_(False)
         node_mask[subsets[-1]] = True
@@ -95,7 +95,7 @@ def k_hop_subgraph(node_idx, num_hops, edge_index, num_nodes=None):
 
 # ----------------------------------------------------------------- message passing
 def _scatter_add(msg, index, num_nodes):
-    out = torch.zeros((num_nodes,) + tuple(msg.shape[1:]), dtype=msg.dtype)
+    out = torch.zeros((num_nodes,) + tuple(msg.shape[1:]), dtype=msg.dtype, device=msg.device)
     return out.index_add_(0, index, msg)
 
 
@@ -103,9 +103,9 @@ def gcn_norm(edge_index, num_nodes, dtype):
     """``gcn_norm(improved=False, add_self_loops=True)``; recomputed on every
     GCNConv call because the reference leaves ``cached=False`` (gcn.py:11-12)."""
     ei = add_remaining_self_loops(edge_index, num_nodes)
-    w = torch.ones(ei.size(1), dtype=dtype)
+    w = torch.ones(ei.size(1), dtype=dtype, device=ei.device)
     src, dst = ei[0], ei[1]
-    deg = torch.zeros(num_nodes, dtype=dtype).index_add_(0, dst, w)
+    deg = torch.zeros(num_nodes, dtype=dtype, device=ei.device).index_add_(0, dst, w)
     dinv = deg.pow(-0.5)
     dinv.masked_fill_(dinv == float('inf'), 0)
     return ei, dinv[src] * w * dinv[dst]
@@ -125,7 +125,7 @@ def gcn_conv(x, edge_index, weight, bias):
 
 def segment_softmax(e, index, num_nodes):
     """``torch_geometric.utils.softmax`` grouped by target index."""
-    emax = torch.full((num_nodes,) + tuple(e.shape[1:]), float('-inf'), dtype=e.dtype)
+    emax = torch.full((num_nodes,) + tuple(e.shape[1:]), float('-inf'), dtype=e.dtype, device=e.device)
     emax = emax.scatter_reduce(0, index.view(-1, *([1] * (e.dim() - 1))).expand_as(e), e.detach(),
                                reduce='amax', include_self=True)
     out = (e - emax.index_select(0, index)).exp()
@@ -167,12 +167,12 @@ def rgcn_conv(x, edge_index, edge_type, weight, root, bias):
     n = x.size(0)
     num_rel = weight.size(0)
     out_dim = root.size(1)
-    out = torch.zeros(n, out_dim, dtype=x.dtype)
+    out = torch.zeros(n, out_dim, dtype=x.dtype, device=x.device)
     for r in range(num_rel):
         sel = edge_type == r
         src, dst = edge_index[0][sel], edge_index[1][sel]
         s = _scatter_add(x.index_select(0, src), dst, n)
-        cnt = torch.zeros(n, dtype=x.dtype).index_add_(0, dst, torch.ones(dst.numel(), dtype=x.dtype))
+        cnt = torch.zeros(n, dtype=x.dtype, device=x.device).index_add_(0, dst, torch.ones(dst.numel(), dtype=x.dtype, device=x.device))
         m = s / cnt.clamp(min=1).view(-1, 1)
         if weight.dim() == 4:
             m = m.view(n, weight.size(1), weight.size(2))

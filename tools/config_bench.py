@@ -38,6 +38,10 @@ for name in a.configs.split(','):
     dels = [p for n, p in model.named_parameters() if 'del' in n]
     if kg:
         optimizer = [torch.optim.Adam([model.deletion1.deletion_weight], lr=1e-3), torch.optim.Adam([model.deletion2.deletion_weight], lr=1e-3)]
+        from gnndelete_b200.kg import negative_sampling_kg          # supplied negatives: seed 43
+        pe, pt = data.edge_index[:, data.df_mask], data.edge_type[data.df_mask]
+        keep = pt < shape.num_edge_type
+        data.neg_edge_index = negative_sampling_kg(pe[:, keep], pt[keep], torch.Generator(device=dev).manual_seed(43))
     else:
         optimizer = torch.optim.Adam(dels, lr=1e-3)
         data.neg_edge_index = S.supplied_negatives(shape.num_nodes, int(data.df_mask.sum()), seed=43, device='cpu').to(dev)
