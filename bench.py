@@ -109,7 +109,8 @@ def dist_setup(n_gpus):
         import torch.distributed as dist
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         torch.cuda.set_device(local)
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        from gnndelete_b200.dist import nccl_options
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local), pg_options=nccl_options())
     return rank, local, world
 
 

@@ -39,6 +39,15 @@ from . import ops
 from .graph import CSR, BatchPlan, build_csr, invert_perm
 
 
+def nccl_options():
+    """Process-group options for the partitioned epoch: NCCL's internal stream at HIGH priority, so that a collective's
+    CTAs are dispatched ahead of the aggregation kernels that are enqueued to run next to it."""
+    import torch.distributed as dist
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.is_high_priority_stream = True
+    return opts
+
+
 def row_bounds(num_nodes: int, world: int):
     """Equal row blocks (the unbalanced cut; kept for small graphs and tests)."""
     per = -(-num_nodes // world)
@@ -179,6 +188,10 @@ class PartitionedGCNDeleteEngine:
         # ---- local CSR over source slots (rows beyond n_loc are empty -> truncated view)
         full = build_csr(plan.mp_src_slot, plan.mp_dst_loc, slots, self_loops=False)
         self.csr = _truncate(full, nl)
+        # kernels that run next to a collective (or next to the side-stream aggregation) are cut into 4x more, shorter
+        # CTAs: a one-wave persistent grid that does not fit at once would run its left-over CTAs as a second full wave
+        self.oversub = 4 if self.world > 1 else 1
+        self.csr.oversub = self.oversub
         self.dinv = torch.empty(max(nl, 1), **f32)
         L.call('gd_gcn_dinv', L.ptr(self.csr.rowptr), nl, L.ptr(self.dinv), L.stream())
         self.rows1, self.comp1 = i32(plan.rows1_loc), i32(plan.comp1_loc)
@@ -203,9 +216,11 @@ class PartitionedGCNDeleteEngine:
             # its own CSR object (same arrays): separate batch plans, i.e. separate split-row scratch / ticket state from
             # the aggregations running concurrently on the main stream
             self.csr1 = CSR(self.csr.rowptr, self.csr.col, self.csr.eid, None, nl, self.csr.nnz)
+            self.csr1.oversub = self.oversub
             self.side = torch.cuda.Stream()
             self.a1_ready = [torch.cuda.Event(), torch.cuda.Event()]
             self.epoch_done = torch.cuda.Event()
+            self.pre_gather = torch.cuda.Event()
             self._k, self._a1_pending = 0, False
         else:
             self.csr1 = self.csr
@@ -259,7 +274,7 @@ class PartitionedGCNDeleteEngine:
             raise NotImplementedError('more than 2^24 local rows: split the graph over more ranks')
         inc = _truncate(build_csr(src, dst, slots, self_loops=False), nl)
         pos = invert_perm(inc.eid, max(inc.nnz, 1)).long()[:inc.nnz]
-        workers = L.load().gd_node_loss_workers(int(feat), bf16)
+        workers = L.load().gd_node_loss_workers(int(feat), bf16) * self.oversub
         bp = BatchPlan(inc.rowptr, inc.col, nl, inc.nnz, workers)
         bp.colp.clamp_(min=0)       # padding slots gather a valid row (coefficient 0): the kernel's loads are unpredicated
         self.inc, self.inc_bp = inc, bp
@@ -343,17 +358,18 @@ class PartitionedGCNDeleteEngine:
         ops.gemm_rows(self.x1, m.conv2.lin.weight.detach(), True, out=self.h1_loc, out_scale=self.dinv, relu_in=True)
         self._publish(self.h1_loc, self.h1_send)
         if self.overlap:
-            # next epoch's layer-1 aggregation: its output buffer was last read by the PREVIOUS epoch's dW_del1 GEMM
+            self.pre_gather.record(main)
+        self._gather(self.h1_send, self.h1, 'allgather_h1')
+        if self.overlap:
+            # next epoch's layer-1 aggregation, enqueued AFTER the collective (whose high-priority kernel takes its SM slots
+            # first) and released when the collective's inputs are ready: it runs while the halo blocks are on the wire.
+            # Its output buffer was last read by the PREVIOUS epoch's dW_del1 GEMM.
             nxt = 1 - (self._k & 1)
-            if self._k > 0:
-                self.side.wait_event(self.epoch_done)
-            else:
-                self.side.wait_stream(main)                       # H0 (exchanged at setup on the main stream) and the plans
+            self.side.wait_event(self.pre_gather)
             with torch.cuda.stream(self.side):
                 self._layer1_aggregate(self.a1_bufs[nxt])
                 self.a1_ready[nxt].record(self.side)
             self._a1_pending = True
-        self._gather(self.h1_send, self.h1, 'allgather_h1')
         ops.spmm(self.csr, self.h1, out=self.a2, row_scale=self.dinv, bias=m.conv2.bias.detach())
         ops.gemm_rows(self.a2, w2, False, out=self.z_loc, rows=self.rows2)
         ops.copy_rows(self.a2, self.z_loc, self.comp2)

@@ -28,6 +28,8 @@ from .losses import DenseNIPlan, EdgeLossPlan
 
 
 class GCNDeleteEngine:
+    conv_kind = 'gcn'
+
     def __init__(self, model, data, neg_edge_index, z_ori=None, ni_target=None, hoist_layer1=True,
                  lr=1e-3, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, logits_ori=None, static_negatives=False,
                  deterministic=False):
@@ -43,7 +45,7 @@ class GCNDeleteEngine:
         n = self.x.shape[0]
         self.n = n
         ei = data.train_pos_edge_index
-        self.plan = plan_for(ei[:, data.sdf_mask].contiguous(), n, 'gcn')
+        self.plan = plan_for(ei[:, data.sdf_mask].contiguous(), n, self.conv_kind)
         self.rows1, self.comp1 = rows_of(data.sdf_node_1hop_mask.to(dev), n)
         self.rows2, self.comp2 = rows_of(data.sdf_node_2hop_mask.to(dev), n)
         sdf = ei[:, data.sdf_mask]
@@ -215,6 +217,87 @@ class GCNDeleteEngine:
             if self.loss.static:
                 self.graph = None                     # the incidence buffers are rebuilt: a captured graph is stale
             self.loss.update_negatives(neg_edge_index)
+
+
+class GATDeleteEngine(GCNDeleteEngine):
+    """The same fused epoch for ``GATDelete`` (deletion.py:80-105 over gat.py:7-24, BASELINE config 2): the two
+    aggregations are PyG ``GATConv(heads=1)`` edge-softmax aggregations (``gd_gat_scores`` / ``gd_gat_fwd`` and the two
+    backward kernels) instead of normalised sums; everything else - Del GEMMs, fused loss, Adam, CUDA-graph capture,
+    negative handling - is inherited.  The attention vectors and conv weights are frozen on the Del path, so only the
+    gradient w.r.t. the layer-2 input is computed."""
+    conv_kind = 'gat'
+
+    def __init__(self, model, data, neg_edge_index, **kw):
+        super().__init__(model, data, neg_edge_index, **kw)
+        from . import _lib as L
+        self.L = L
+        dev, n = self.x.device, self.n
+        hid, out = model.conv1.out_channels, model.conv2.out_channels
+        f32 = dict(dtype=torch.float32, device=dev)
+        nnz = self.plan.fwd.nnz
+        self.att = {}
+        for name, conv, c in (('c1', model.conv1, hid), ('c2', model.conv2, out)):
+            self.att[name] = dict(src=conv.att_src.detach().reshape(-1).contiguous(), dst=conv.att_dst.detach().reshape(-1).contiguous(),
+                                  a_src=torch.empty(n, **f32), a_dst=torch.empty(n, **f32), rowmax=torch.empty(n, **f32),
+                                  rowden=torch.empty(n, **f32), slope=float(conv.negative_slope))
+        self.alpha_t = torch.empty(max(nnz, 1), **f32)
+        self.dpre_t = torch.empty(max(nnz, 1), **f32)
+        self.da_dst = torch.empty(n, **f32)
+        self.da_src = torch.empty(n, **f32)
+        self.tinv = self.plan.tinv
+
+    def _gat(self, key, h, bias, out):
+        L, a, p = self.L, self.att[key], self.plan
+        c = h.shape[1]
+        L.call('gd_gat_scores', L.ptr(h), h.stride(0), self.n, c, L.ptr(a['src']), L.ptr(a['dst']), L.ptr(a['a_src']),
+               L.ptr(a['a_dst']), L.stream())
+        L.call('gd_gat_fwd', p.fwd.ref, L.ptr(h), h.stride(0), c, L.ptr(a['a_src']), L.ptr(a['a_dst']), L.ptr(bias),
+               a['slope'], L.ptr(out), out.stride(0), L.ptr(a['rowmax']), L.ptr(a['rowden']), L.stream())
+
+    def layer1(self):
+        c1 = self.model.conv1
+        ops.gemm_rows(self.x, c1.lin_src.weight.detach(), True, out=self.h0)
+        self._gat('c1', self.h0, c1.bias.detach(), self.a1)
+        self._layer1_done = True
+
+    def forward(self):
+        m = self.model
+        if not (self.hoist and self._layer1_done):
+            self.layer1()
+        w1 = m.deletion1.deletion_weight.detach()
+        w2 = m.deletion2.deletion_weight.detach()
+        self._del_rows(self.a1, self.x1, self.comp1, lambda: ops.gemm_rows(                   # Del1 on S1
+            self.a1, w1, False, out=self.x1, rows=self.rows1, relu_mask_out=self.x1_bits))
+        ops.gemm_rows(self.x1, m.conv2.lin_src.weight.detach(), True, out=self.h1, relu_in=True)
+        self._gat('c2', self.h1, m.conv2.bias.detach(), self.a2)
+        self._del_rows(self.a2, self.z, self.comp2, lambda: ops.gemm_rows(                    # Del2 on S2
+            self.a2, w2, False, out=self.z, rows=self.rows2))
+        return self.loss.forward(self.z, dz_out=self.dz)
+
+    def backward(self):
+        m, p, L = self.model, self.plan, self.L
+        g1, g2 = self.params[0].grad, self.params[1].grad
+        w2 = m.deletion2.deletion_weight.detach()
+        self.loss.backward(self.z, out=self.dz)
+        if self.dense is not None:
+            loss_l = self.dense.forward_backward(self.z, self.dz)
+            self.losses_total[1:2].copy_(self.loss.losses[1:2])
+            self.losses_total[2:3].copy_(loss_l)
+            torch.add(self.loss.losses[0:1], loss_l, alpha=1.0 - self.alpha, out=self.losses_total[0:1])
+        ops.gemm_tn_rows(self.a2, self.dz, rows=self.rows2, out=g2)                # dW_del2
+        self._del_rows(self.dz, self.da2, self.comp2, lambda: ops.gemm_rows(                  # dz[S2] @ W2^T
+            self.dz, w2, True, out=self.da2, rows=self.rows2))
+        a, c2 = self.att['c2'], m.conv2
+        out = self.h1.shape[1]
+        bias = c2.bias.detach()
+        L.call('gd_gat_bwd_dst', p.fwd.ref, L.ptr(self.tinv), L.ptr(self.h1), self.h1.stride(0), out, L.ptr(a['a_src']),
+               L.ptr(a['a_dst']), L.ptr(a['rowmax']), L.ptr(a['rowden']), L.ptr(self.da2), self.da2.stride(0), L.ptr(self.a2),
+               self.a2.stride(0), L.ptr(bias), a['slope'], L.ptr(self.alpha_t), L.ptr(self.dpre_t), L.ptr(self.da_dst), L.stream())
+        L.call('gd_gat_bwd_src', p.bwd.ref, L.ptr(self.alpha_t), L.ptr(self.dpre_t), L.ptr(self.da2), self.da2.stride(0), out,
+               L.ptr(a['src']), L.ptr(a['dst']), L.ptr(self.da_dst), L.ptr(self.dh1), self.dh1.stride(0), L.ptr(self.da_src), L.stream())
+        ops.gemm_rows(self.dh1, c2.lin_src.weight.detach(), False, out=self.dx1, rows=self.rows1,
+                      gate=None if self.bitmask else self.x1, gate_bits=self.x1_bits)          # ReLU' (dH1 W_2) on S1
+        ops.gemm_tn_rows(self.a1, self.dx1, rows=self.rows1, out=g1)               # dW_del1
 
 
 class EpochPipeline:

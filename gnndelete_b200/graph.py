@@ -36,6 +36,10 @@ class CSR:
         self._scratch = {}
         self._bplans = {}
         self.dynamic = False     # True: the arrays are rewritten in place (no cached batch plan)
+        # batch-plan workers per resident sub-warp.  1: one persistent wave (fastest alone); > 1: more, shorter CTAs, for
+        # kernels that share the GPU with a collective or another kernel (a persistent wave that does not fit at once
+        # runs its left-over CTAs as a second wave of the same length)
+        self.oversub = OVERSUB
         s = L.CsrStruct()
         s.num_rows, s.nnz = self.num_rows, self.nnz
         s.rowptr, s.col = rowptr.data_ptr(), col.data_ptr()
@@ -63,9 +67,9 @@ class CSR:
                 or not BATCHED or self.dynamic or self.nnz == 0:
             return None
         if bf16:
-            workers = L.load().gd_spmm_batched_bf16_workers(int(feat), int(bool(weighted))) * OVERSUB
+            workers = L.load().gd_spmm_batched_bf16_workers(int(feat), int(bool(weighted))) * self.oversub
         else:
-            workers = L.load().gd_spmm_batched_workers(int(feat), int(bool(weighted))) * OVERSUB
+            workers = L.load().gd_spmm_batched_workers(int(feat), int(bool(weighted))) * self.oversub
         bp = self._bplans.get(workers)
         if bp is None:
             bp = BatchPlan(self.rowptr, self.col, self.num_rows, self.nnz, workers)

@@ -15,7 +15,7 @@ import torch
 
 from . import metrics
 from . import ops
-from .engine import GCNDeleteEngine
+from .engine import GATDeleteEngine, GCNDeleteEngine
 
 
 def get_loss_fct(name):
@@ -293,9 +293,9 @@ class GNNDeleteTrainer(Trainer):
         # original model's pair logits (`logits_ori`, pred_proba.pt) - for every architecture.  Without
         # `logits_ori` the edge form is used for every graph.
         dense = logits_ori is not None and 'ogbl' not in self.args.dataset
-        if type(model).__name__ != 'GCNDelete':
-            # GATDelete / GINDelete: the same step body through the autograd modules (every layer is still one
-            # of the CUDA kernels; only the orchestration differs from the fused GCN engine)
+        if type(model).__name__ not in ('GCNDelete', 'GATDelete'):
+            # GINDelete: the same step body through the autograd modules (every layer is still one of the CUDA
+            # kernels; only the orchestration differs from the fused GCN / GAT engines)
             return self.train_autograd(model, data, optimizer, args, logits_ori if dense else None)
         return self.train_edge_form(model, data, optimizer, args, logits_ori if dense else None)
 
@@ -416,12 +416,13 @@ class GNNDeleteTrainer(Trainer):
         want = {id(model.deletion1.deletion_weight), id(model.deletion2.deletion_weight)}
         have = {id(p) for g in optimizer.param_groups for p in g['params']}
         if have != want:
-            raise ValueError('GNNDeleteTrainer(GCNDelete) expects an optimizer over deletion1/deletion2.deletion_weight only')
+            raise ValueError('GNNDeleteTrainer expects an optimizer over deletion1/deletion2.deletion_weight only')
         group = optimizer.param_groups[0]
         for g in optimizer.param_groups[1:]:
             if (g['lr'], g['betas'], g['eps']) != (group['lr'], group['betas'], group['eps']):
                 raise ValueError('per-group Adam hyper-parameters are not supported by the fused GCNDelete epoch')
-        eng = GCNDeleteEngine(model, data, neg, z_ori=z_ori, lr=group['lr'], betas=group['betas'], eps=group['eps'],
+        engine_cls = GATDeleteEngine if type(model).__name__ == 'GATDelete' else GCNDeleteEngine
+        eng = engine_cls(model, data, neg, z_ori=z_ori, lr=group['lr'], betas=group['betas'], eps=group['eps'],
                               hoist_layer1=getattr(args, 'hoist_layer1', True), logits_ori=logits_ori,
                               static_negatives=fixed_neg is not None, alpha=self._loss_mix())
         self.engine = eng

@@ -106,7 +106,8 @@ def _nccl_worker(rank, world, port, wire, ret):
     os.environ['MASTER_PORT'] = str(port)
     torch.cuda.set_device(rank)
     dev = torch.device('cuda', rank)
-    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    from gnndelete_b200.dist import nccl_options
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev, pg_options=nccl_options())
     try:
         ret[rank] = _check_rank(rank, world, wire, dev)
         dist.barrier()
