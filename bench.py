@@ -398,9 +398,9 @@ def run_partitioned(args, shape, rank, local, world, dev, lib, wire='bf16', one_
     def measure(w, r, group_world):
         """epochs/s of the partitioned engine over ``w`` ranks (w == 1: no process group, this rank alone)."""
         model.load_state_dict(init)
-        eng = PartitionedGCNDeleteEngine(model, data, neg, z_ori, wire=wire, world=w, rank=r,
+        eng = PartitionedGCNDeleteEngine(model, data, neg, z_ori, wire=wire, world=w, rank=r, exchange=args.partition_exchange,
                                          overlap_layer1=None if args.partition_overlap == 'auto' else False)
-        overlap = eng.overlap
+        overlap, exchange = eng.overlap, eng.exchange + (f' (symm failed: {eng.exchange_error})' if hasattr(eng, 'exchange_error') else '')
         torch.cuda.synchronize()
         eng.epoch()                                       # first epoch: also builds the batch plans (one-time launches)
         c0 = lib.gd_launch_count()
@@ -416,7 +416,7 @@ def run_partitioned(args, shape, rank, local, world, dev, lib, wire='bf16', one_
         out = {'ms_per_step': ms / steps, 'value': steps / (ms / 1e3), 'launches_per_epoch': int(launches),
                'comm_ms_per_epoch': {k: v / steps for k, v in comm.items()}, 'losses_last': eng.losses.tolist(),
                'halo_bytes_per_epoch_per_rank_received': int(eng.halo_bytes_per_epoch * (w - 1) / w) if w > 1 else 0,
-               'rows_per_rank': [b[1] - b[0] for b in eng.plan.bounds], 'overlap_layer1': overlap}
+               'rows_per_rank': [b[1] - b[0] for b in eng.plan.bounds], 'overlap_layer1': overlap, 'exchange': exchange}
         del eng
         torch.cuda.empty_cache()
         return out
@@ -430,8 +430,9 @@ def run_partitioned(args, shape, rank, local, world, dev, lib, wire='bf16', one_
     block = {
         'workload': f'GCNDelete edge unlearning, {shape.name} power-law graph ({n} nodes / {shape.num_edges} directed edges / '
                     f'{shape.num_deleted} deleted), 128->128->64, 1-D row partition (work-balanced row blocks) over '
-                    f'{world} GPU(s), NCCL all-gather halo exchange of H1 / z / dA2 in {wire} (H0 exchanged once at setup: '
-                    f'frozen, input-constant), layer-1 aggregation still run every epoch',
+                    f'{world} GPU(s), halo exchange of H1 / z / dA2 in {wire} over NVLink (copy-engine pulls from symmetric peer '
+                    f'buffers, or NCCL all-gather: see "exchange"; H0 exchanged once at setup: frozen, input-constant), layer-1 '
+                    f'aggregation still run every epoch',
         'metric': 'Del-training epochs/s, row-partitioned power-law graph', 'unit': UNIT, 'scaling': 'strong',
         'n_gpus': world, 'comm_nranks_seen': world, 'steps': steps, 'warmup': warm, 'wire': wire,
         'dtype': 'bf16-gather (fp32 accumulate), tolerance 2e-2' if wire == 'bf16' else 'f32',
@@ -439,13 +440,14 @@ def run_partitioned(args, shape, rank, local, world, dev, lib, wire='bf16', one_
         'launches_per_epoch': res['launches_per_epoch'], 'comm_ms_per_epoch': res['comm_ms_per_epoch'],
         'halo_bytes_per_epoch_per_rank_received': res['halo_bytes_per_epoch_per_rank_received'],
         'rows_per_rank': res['rows_per_rank'], 'losses_last': res['losses_last'], 'parity': parity, 'clocks': clocks,
-        'overlap_layer1_with_collectives': res['overlap_layer1'],
+        'overlap_layer1_with_exchanges': res['overlap_layer1'], 'exchange': res['exchange'],
         'setup_s': setup_s,
     }
     if res['comm_ms_per_epoch']:
         lim = max(res['comm_ms_per_epoch'].items(), key=lambda kv: kv[1])
         block['limiting_collective'] = {'name': lim[0], 'ms_per_epoch': lim[1],
-                                        'note': 'device time on rank 0 between the events bracketing the call; includes waiting for the slowest rank'}
+                                        'note': 'device time on rank 0 between the events bracketing the transfer (on the copy stream for pulls); '
+                                                'pulls run underneath the next epoch\'s layer-1 aggregation, so this is not all exposed time'}
     if world > 1 and one_gpu_point:
         # the one-GPU point of the same engine (same kernels, same arithmetic), on rank 0's GPU, same invocation
         if rank == 0:
@@ -604,6 +606,7 @@ def main():
     ap.add_argument('--partition-workload', default='powerlaw10m')
     ap.add_argument('--partition-scale', type=float, default=1.0)
     ap.add_argument('--no-partitioned', action='store_true', help='N > 1: skip the row-partitioned config-5 block')
+    ap.add_argument('--partition-exchange', default='symm', choices=['symm', 'nccl'], help='halo exchange of the row-partitioned epoch')
     ap.add_argument('--partition-overlap', default='auto', choices=['auto', 'off'],
                     help="'off': do not run the next epoch's layer-1 aggregation under the collectives (A/B measurements)")
     args = ap.parse_args()

@@ -26,9 +26,15 @@ Per epoch and rank (``wire`` = bf16 or fp32 blocks on NVLink; the gathered block
 Per rank the work is 1/world of the single-GPU epoch (every aggregation entry, every incidence entry and every Df
 item is processed by exactly one rank); the exchanged volume is 3 [N,64] blocks per epoch.
 ``PartitionPlan`` is pure index logic (torch, any device) so it is tested on CPU with gloo;
-``PartitionedGCNDeleteEngine`` runs the plan with the CUDA kernels and NCCL (``torch.distributed``
-all_gather_into_tensor / all_reduce over NVLink); with ``world == 1`` it runs without a process group — that is the
-one-GPU point of the scaling curve, same kernels, same arithmetic.
+``PartitionedGCNDeleteEngine`` runs the plan with the CUDA kernels.  The three per-epoch halo exchanges are PULLS over
+NVLink peer memory (``torch.distributed._symmetric_memory``): every rank publishes its block into a symmetric buffer,
+a device-side barrier, then each rank copies the other ranks' blocks with the COPY ENGINES (cudaMemcpyAsync from the
+mapped peer buffers) - no SM is spent on the transfer, so a third of the NEXT epoch's layer-1 aggregation (which
+depends on nothing this epoch produces) runs underneath each exchange.  (An SM-based NCCL all-gather next to a
+memory-bound aggregation just trades time: measured, profiles/r2_scale_config5.md.)  ``exchange='nccl'`` keeps the
+all_gather_into_tensor path; the small reductions (DEC coefficients, Del gradients, loss sums) are NCCL either way.
+With ``world == 1`` the engine runs without a process group — that is the one-GPU point of the scaling curve, same
+kernels, same arithmetic.
 """
 from __future__ import annotations
 
@@ -157,14 +163,15 @@ class PartitionedGCNDeleteEngine:
 
     def __init__(self, model, data, neg_edge_index, z_ori_full, group=None, hoist_gather=True, wire='bf16',
                  lr=1e-3, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, balance=True, world=None, rank=None,
-                 overlap_layer1=None):
+                 overlap_layer1=None, exchange='symm'):
         """``wire``: 'bf16' (halo blocks travel and are gathered in bf16, fp32 accumulation; tolerance 2e-2) or
         'fp32' (1e-5).  ``hoist_gather``: the layer-1 block ``H0 = D^-1/2 X W1^T`` is frozen and input-constant, so
         it is transformed and exchanged once at setup; the layer-1 aggregation itself is still run every epoch (the
         reference recomputes conv1 every epoch).  ``world`` / ``rank`` default to the process group's.
-        ``overlap_layer1`` (default: on when ``world > 1`` and the H0 exchange is hoisted): the layer-1 aggregation of
-        epoch k + 1 depends on nothing epoch k produces, so it is issued on a side stream when epoch k enters its first
-        halo exchange and runs while the collectives of epoch k are on the wire (double-buffered ``a1``)."""
+        ``exchange``: 'symm' (copy-engine pulls from symmetric peer buffers; falls back to 'nccl' when symmetric memory
+        cannot be set up) or 'nccl'.  ``overlap_layer1`` (default: on when ``world > 1``, the H0 exchange is hoisted and
+        the exchange is 'symm'): the layer-1 aggregation of epoch k + 1 depends on nothing epoch k produces, so it is
+        cut into three row ranges that run underneath the three exchanges of epoch k (double-buffered ``a1``)."""
         if wire not in ('bf16', 'fp32'):
             raise ValueError(wire)
         if world is None:
@@ -188,42 +195,38 @@ class PartitionedGCNDeleteEngine:
         # ---- local CSR over source slots (rows beyond n_loc are empty -> truncated view)
         full = build_csr(plan.mp_src_slot, plan.mp_dst_loc, slots, self_loops=False)
         self.csr = _truncate(full, nl)
-        # kernels that run next to a collective (or next to the side-stream aggregation) are cut into 4x more, shorter
-        # CTAs: a one-wave persistent grid that does not fit at once would run its left-over CTAs as a second full wave
-        self.oversub = 4 if self.world > 1 else 1
-        self.csr.oversub = self.oversub
         self.dinv = torch.empty(max(nl, 1), **f32)
         L.call('gd_gcn_dinv', L.ptr(self.csr.rowptr), nl, L.ptr(self.dinv), L.stream())
         self.rows1, self.comp1 = i32(plan.rows1_loc), i32(plan.comp1_loc)
         self.rows2, self.comp2 = i32(plan.rows2_loc), i32(plan.comp2_loc)
         # ---- buffers: *_send is this rank's [per, F] block in wire format, the gathered matrices are [slots, F]
-        wd = dict(dtype=self.wdtype, device=dev)
-        self.h0 = torch.zeros(slots, hid, **wd)
-        self.h1 = torch.zeros(slots, out, **wd)
-        self.zg = torch.zeros(slots, out, **wd)
-        self.da2g = torch.zeros(slots, out, **wd)
+        self.exchange = exchange if self.world > 1 else 'none'
+        self.sym = {}
+        self.h0 = self._alloc_gathered('h0', slots, hid, symmetric=False)
+        self.h1 = self._alloc_gathered('h1', slots, out)
+        self.zg = self._alloc_gathered('z', slots, out)
+        self.da2g = self._alloc_gathered('da2', slots, out)
         blk = slice(self.rank * per, self.rank * per + per)
+        self.blk = blk
         self.h0_send, self.h1_send, self.z_send, self.da2_send = self.h0[blk], self.h1[blk], self.zg[blk], self.da2g[blk]
         self.h0_loc = torch.empty(nl, hid, **f32) if wire == 'bf16' else self.h0_send[:nl]
         self.h1_loc = torch.empty(nl, out, **f32) if wire == 'bf16' else self.h1_send[:nl]
         self.z_loc = torch.empty(nl, out, **f32) if wire == 'bf16' else self.z_send[:nl]
         self.da2_loc = torch.empty(nl, out, **f32)
-        self.overlap = bool(hoist_gather and self.world > 1) if overlap_layer1 is None else bool(overlap_layer1 and hoist_gather)
+        if self.exchange == 'symm':
+            self.copy_stream = torch.cuda.Stream()
+        want = bool(hoist_gather and self.exchange == 'symm')
+        self.overlap = want if overlap_layer1 is None else bool(overlap_layer1 and want)
         self.a1_bufs = [torch.empty(nl, hid, **f32) for _ in range(2 if self.overlap else 1)]
         self.a1 = self.a1_bufs[0]
         self.x1 = torch.empty(nl, hid, **f32)
+        self._k, self._a1_pending = 0, False
         if self.overlap:
-            # its own CSR object (same arrays): separate batch plans, i.e. separate split-row scratch / ticket state from
-            # the aggregations running concurrently on the main stream
-            self.csr1 = CSR(self.csr.rowptr, self.csr.col, self.csr.eid, None, nl, self.csr.nnz)
-            self.csr1.oversub = self.oversub
-            self.side = torch.cuda.Stream()
-            self.a1_ready = [torch.cuda.Event(), torch.cuda.Event()]
-            self.epoch_done = torch.cuda.Event()
-            self.pre_gather = torch.cuda.Event()
-            self._k, self._a1_pending = 0, False
+            # three row ranges of the local CSR, each with its own batch plan: one per exchange of the epoch
+            cuts = [0, nl // 3, 2 * nl // 3, nl]
+            self.l1_parts = [(cuts[i], cuts[i + 1], _row_range(self.csr, cuts[i], cuts[i + 1])) for i in range(3) if cuts[i + 1] > cuts[i]]
         else:
-            self.csr1 = self.csr
+            self.l1_parts = [(0, nl, self.csr)]
         self.a2 = torch.empty(nl, out, **f32)
         self.dz = torch.empty(nl, out, **f32)
         self.dh1 = torch.empty(nl, out, **f32)
@@ -274,7 +277,7 @@ class PartitionedGCNDeleteEngine:
             raise NotImplementedError('more than 2^24 local rows: split the graph over more ranks')
         inc = _truncate(build_csr(src, dst, slots, self_loops=False), nl)
         pos = invert_perm(inc.eid, max(inc.nnz, 1)).long()[:inc.nnz]
-        workers = L.load().gd_node_loss_workers(int(feat), bf16) * self.oversub
+        workers = L.load().gd_node_loss_workers(int(feat), bf16)
         bp = BatchPlan(inc.rowptr, inc.col, nl, inc.nnz, workers)
         bp.colp.clamp_(min=0)       # padding slots gather a valid row (coefficient 0): the kernel's loads are unpredicated
         self.inc, self.inc_bp = inc, bp
@@ -305,18 +308,67 @@ class PartitionedGCNDeleteEngine:
         r = torch.div(slot, plan.per, rounding_mode='floor')
         return plan._los[r] + (slot - r * plan.per)
 
-    # ---------------------------------------------------------------- collectives
-    def _timed(self, fn, label):
+    # ---------------------------------------------------------------- exchanges
+    def _alloc_gathered(self, name, rows, feat, symmetric=True):
+        """A [slots, feat] matrix in wire format; with the 'symm' exchange it lives in symmetric memory and every rank
+        maps the other ranks' copies (their blocks are pulled from there)."""
+        dev = self.x_loc.device
+        if self.exchange == 'symm' and symmetric:
+            try:
+                import torch.distributed._symmetric_memory as sm
+                t = sm.empty(rows, feat, dtype=self.wdtype, device=dev)
+                hdl = sm.rendezvous(t, self.group if self.group is not None else self.dist.group.WORLD)
+                peers = [hdl.get_buffer(q, (rows, feat), self.wdtype) for q in range(self.world)]
+                t.zero_()
+                self.sym[name] = dict(hdl=hdl, peers=peers, dirty=False)
+                return t
+            except Exception as exc:               # no peer mapping on this box: every rank fails the same way
+                self.exchange = 'nccl'
+                self.exchange_error = repr(exc)
+                self.sym = {}
+        return torch.zeros(rows, feat, dtype=self.wdtype, device=dev)
+
+    def _timed(self, fn, label, stream=None):
         if self.comm_events is None:
             return fn()
-        st = torch.cuda.current_stream()
+        st = stream or torch.cuda.current_stream()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(st); fn(); b.record(st)
         self.comm_events.append((label, a, b))
 
-    def _gather(self, send, full, label):
-        if self.world > 1:
+    def _before_publish(self, name):
+        """The block about to be overwritten may still be being pulled by a slower rank (previous epoch)."""
+        e = self.sym.get(name)
+        if e is not None and e['dirty']:
+            e['hdl'].barrier(channel=1)
+            e['dirty'] = False
+
+    def _exchange_begin(self, name, send, full, label):
+        """Start the halo exchange of ``full`` (this rank's block ``send`` is already in place).  'symm': device
+        barrier, then world - 1 peer pulls on the copy stream (copy engines); the caller may enqueue independent work on
+        the current stream before :meth:`_exchange_end`.  'nccl': the all-gather runs here."""
+        if self.world == 1:
+            return
+        e = self.sym.get(name)
+        if e is None:
             self._timed(lambda: self.dist.all_gather_into_tensor(full, send, group=self.group), label)
+            return
+        main = torch.cuda.current_stream()
+        e['hdl'].barrier(channel=0)                          # every rank's block is published
+        self.copy_stream.wait_stream(main)
+        per, peers = self.plan.per, e['peers']
+
+        def pulls():
+            with torch.cuda.stream(self.copy_stream):
+                for i in range(1, self.world):
+                    q = (self.rank + i) % self.world
+                    full[q * per:(q + 1) * per].copy_(peers[q][q * per:(q + 1) * per], non_blocking=True)
+        self._timed(pulls, label, stream=self.copy_stream)
+        e['dirty'] = True
+
+    def _exchange_end(self, name):
+        if self.world > 1 and name in self.sym:
+            torch.cuda.current_stream().wait_stream(self.copy_stream)
 
     def _publish(self, loc, send, row_scale=None):
         """Local fp32 rows -> this rank's wire-format block of the gathered matrix."""
@@ -332,49 +384,49 @@ class PartitionedGCNDeleteEngine:
         c1 = self.model.conv1
         ops.gemm_rows(self.x_loc, c1.lin.weight.detach(), True, out=self.h0_loc, out_scale=self.dinv)
         self._publish(self.h0_loc, self.h0_send)
-        self._gather(self.h0_send, self.h0, 'allgather_h0')
+        if self.world > 1:
+            self._timed(lambda: self.dist.all_gather_into_tensor(self.h0, self.h0_send, group=self.group), 'allgather_h0')
         self._h0_done = True
 
-    def _layer1_aggregate(self, out):
-        ops.spmm(self.csr1, self.h0, out=out, row_scale=self.dinv, bias=self.model.conv1.bias.detach())
+    def _layer1_part(self, i, out):
+        """Rows [r0, r1) of the layer-1 aggregation A1 = D^-1/2 SpMM(csr_loc, H0) + b1."""
+        if i >= len(self.l1_parts):
+            return
+        r0, r1, csr = self.l1_parts[i]
+        ops.spmm(csr, self.h0, out=out[r0:r1], row_scale=self.dinv[r0:r1], bias=self.model.conv1.bias.detach())
+
+    def _layer1_all(self, out):
+        for i in range(len(self.l1_parts)):
+            self._layer1_part(i, out)
 
     def forward(self):
         m, nl = self.model, self.nl
         if not (self.hoist_gather and self._h0_done):
             self.gather_h0()
-        main = torch.cuda.current_stream()
-        if self.overlap:
-            cur = self._k & 1
-            self.a1 = self.a1_bufs[cur]
-            if self._a1_pending:
-                main.wait_event(self.a1_ready[cur])               # issued during the previous epoch's collectives
-            else:
-                self._layer1_aggregate(self.a1)
-        else:
-            self._layer1_aggregate(self.a1)
+        cur = self._k & 1 if self.overlap else 0
+        self.a1 = self.a1_bufs[cur]
+        nxt = self.a1_bufs[1 - cur] if self.overlap else None
+        if not (self.overlap and self._a1_pending):
+            self._layer1_all(self.a1)                              # otherwise: done underneath the previous epoch's exchanges
         w1, w2 = m.deletion1.deletion_weight.detach(), m.deletion2.deletion_weight.detach()
         ops.gemm_rows(self.a1, w1, False, out=self.x1, rows=self.rows1)
         ops.copy_rows(self.a1, self.x1, self.comp1)
         ops.gemm_rows(self.x1, m.conv2.lin.weight.detach(), True, out=self.h1_loc, out_scale=self.dinv, relu_in=True)
+        self._before_publish('h1')
         self._publish(self.h1_loc, self.h1_send)
+        self._exchange_begin('h1', self.h1_send, self.h1, 'exchange_h1')
         if self.overlap:
-            self.pre_gather.record(main)
-        self._gather(self.h1_send, self.h1, 'allgather_h1')
-        if self.overlap:
-            # next epoch's layer-1 aggregation, enqueued AFTER the collective (whose high-priority kernel takes its SM slots
-            # first) and released when the collective's inputs are ready: it runs while the halo blocks are on the wire.
-            # Its output buffer was last read by the PREVIOUS epoch's dW_del1 GEMM.
-            nxt = 1 - (self._k & 1)
-            self.side.wait_event(self.pre_gather)
-            with torch.cuda.stream(self.side):
-                self._layer1_aggregate(self.a1_bufs[nxt])
-                self.a1_ready[nxt].record(self.side)
-            self._a1_pending = True
+            self._layer1_part(0, nxt)
+        self._exchange_end('h1')
         ops.spmm(self.csr, self.h1, out=self.a2, row_scale=self.dinv, bias=m.conv2.bias.detach())
         ops.gemm_rows(self.a2, w2, False, out=self.z_loc, rows=self.rows2)
         ops.copy_rows(self.a2, self.z_loc, self.comp2)
+        self._before_publish('z')
         self._publish(self.z_loc, self.z_send)
-        self._gather(self.z_send, self.zg, 'allgather_z')
+        self._exchange_begin('z', self.z_send, self.zg, 'exchange_z')
+        if self.overlap:
+            self._layer1_part(1, nxt)
+        self._exchange_end('z')
         self._loss()
 
     def _loss(self):
@@ -405,11 +457,16 @@ class PartitionedGCNDeleteEngine:
         m = self.model
         g1, g2 = self.params[0].grad, self.params[1].grad
         w2 = m.deletion2.deletion_weight.detach()
-        ops.gemm_tn_rows(self.a2, self.dz, rows=self.rows2, out=g2)
         ops.gemm_rows(self.dz, w2, True, out=self.da2_loc, rows=self.rows2)
         ops.copy_rows(self.dz, self.da2_loc, self.comp2)
+        self._before_publish('da2')
         self._publish(self.da2_loc, self.da2_send, row_scale=self.dinv)          # D^-1/2 on the source side of A_hat^T
-        self._gather(self.da2_send, self.da2g, 'allgather_da2')
+        self._exchange_begin('da2', self.da2_send, self.da2g, 'exchange_da2')
+        ops.gemm_tn_rows(self.a2, self.dz, rows=self.rows2, out=g2)             # dW_del2 needs no halo: under the exchange
+        if self.overlap:
+            self._layer1_part(2, self.a1_bufs[1 - (self._k & 1)])
+            self._a1_pending = True
+        self._exchange_end('da2')
         ops.spmm(self.csr, self.da2g, out=self.dh1)                              # A^T = A (symmetric edge set)
         ops.gemm_rows(self.dh1, m.conv2.lin.weight.detach(), False, out=self.dx1, rows=self.rows1,
                       out_scale=self.dinv, gate=self.x1)
@@ -425,9 +482,7 @@ class PartitionedGCNDeleteEngine:
         loss_r = self.red[n1 + n2]
         loss_l = self.red[n1 + n2 + 1] * (0.5 / self.plan.norm_ni if self.plan.norm_ni else 0.0)
         torch.stack([self.alpha * loss_r + (1.0 - self.alpha) * loss_l, loss_r, loss_l], out=self.losses)
-        if self.overlap:
-            self.epoch_done.record(torch.cuda.current_stream())      # a1 of this epoch is free from here on
-            self._k += 1
+        self._k += 1
 
     def adam_step(self):
         for p, st in zip(self.params, self.state):
@@ -447,6 +502,15 @@ class PartitionedGCNDeleteEngine:
         for label, a, b in (self.comm_events or []):
             out[label] = out.get(label, 0.0) + a.elapsed_time(b)
         return out
+
+
+def _row_range(csr: CSR, r0: int, r1: int) -> CSR:
+    """Rows [r0, r1) of a CSR as a CSR of its own (shares the column array)."""
+    rp = csr.rowptr[r0:r1 + 1]
+    base = int(rp[0].item())
+    end = int(rp[-1].item())
+    return CSR((rp - base).contiguous(), csr.col[base:end], csr.eid[base:end] if csr.eid is not None else None, None,
+               r1 - r0, end - base)
 
 
 def _truncate(csr: CSR, num_rows: int) -> CSR:

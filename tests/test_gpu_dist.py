@@ -33,7 +33,7 @@ def _reference(scale):
     return shape, data, neg, zo, init, ref
 
 
-def _check_rank(rank, world, wire, dev, group=None, scale=0.2):
+def _check_rank(rank, world, wire, dev, group=None, scale=0.2, exchange='symm'):
     from gnndelete_b200 import models as M
     from gnndelete_b200.dist import PartitionedGCNDeleteEngine
     from gnndelete_b200.engine import GCNDeleteEngine
@@ -47,7 +47,9 @@ def _check_rank(rank, world, wire, dev, group=None, scale=0.2):
     dd = data.clone().to(dev)
     m_part = fresh()
     eng = PartitionedGCNDeleteEngine(m_part, dd, neg.to(dev), zo.float().to(dev), group=group, wire=wire,
-                                     world=world, rank=rank)
+                                     world=world, rank=rank, exchange=exchange)
+    if world > 1:
+        assert eng.exchange == exchange, getattr(eng, 'exchange_error', None)
     tol = TOL[wire]
     eng.forward(); eng.backward()
     U.assert_close(eng.losses, ref['losses'], tol=tol, what=f'{wire} partitioned losses vs oracle')
@@ -99,7 +101,7 @@ def test_bf16_source_aggregation(lib):
         assert torch.equal(ops.cast_bf16(x, row_scale=sc), (x * sc.view(-1, 1)).to(torch.bfloat16))
 
 
-def _nccl_worker(rank, world, port, wire, ret):
+def _nccl_worker(rank, world, port, wire, exchange, ret):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
@@ -109,21 +111,21 @@ def _nccl_worker(rank, world, port, wire, ret):
     from gnndelete_b200.dist import nccl_options
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev, pg_options=nccl_options())
     try:
-        ret[rank] = _check_rank(rank, world, wire, dev)
+        ret[rank] = _check_rank(rank, world, wire, dev, exchange=exchange)
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('wire', ['fp32', 'bf16'])
-def test_partitioned_engine_nccl_world2(lib, wire):
+@pytest.mark.parametrize('wire,exchange', [('fp32', 'symm'), ('bf16', 'symm'), ('bf16', 'nccl')])
+def test_partitioned_engine_nccl_world2(lib, wire, exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs (run under gpurun --gpus 2)')
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     ret = ctx.Manager().dict()
-    port = 29700 + (os.getpid() % 1000) + (1 if wire == 'bf16' else 0)
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, wire, ret)) for r in range(2)]
+    port = 29700 + (os.getpid() % 1000) + (1 if wire == 'bf16' else 0) + (2 if exchange == 'nccl' else 0)
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, wire, exchange, ret)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:

@@ -76,6 +76,68 @@ def test_gat_isolated_and_hub_rows(lib):
     U.assert_close(z2, ref2, what='gat hub z2')
 
 
+def test_gat_hub_row_10k_neighbours(lib):
+    """One destination with 10,000 in-neighbours (a row 300x longer than a sub-warp batch) next to ordinary rows:
+    edge-softmax aggregation forward and its gradient w.r.t. the input features against the oracle."""
+    from gnndelete_b200 import models as M
+    from oracle import models as OM
+    import types
+    n = 12000
+    g = torch.Generator().manual_seed(11)
+    hub = torch.stack([torch.arange(1, 10001), torch.zeros(10000, dtype=torch.long)])
+    rnd = torch.randint(0, n, (2, 30000), generator=g)
+    ei = torch.unique(torch.cat([hub, rnd[:, rnd[0] != rnd[1]]], 1), dim=1)
+    args = types.SimpleNamespace(in_dim=64, hidden_dim=128, out_dim=64)
+    torch.manual_seed(0)
+    om = OM.GAT(args).double()
+    U.randomize(om)
+    x = torch.randn(n, 64, generator=g)
+    xo = x.double().requires_grad_(True)
+    ref1, ref2 = om(xo, ei, return_all_emb=True)
+    w = torch.randn(n, 64, generator=g)
+    (ref2 * w.double()).sum().backward()
+    m = M.GAT(args)
+    m.load_state_dict({k: v.float() for k, v in om.state_dict().items()})
+    m = m.to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    z1, z2 = m(xg, ei.to(DEV), return_all_emb=True)
+    U.assert_close(z1, ref1, what='gat 10k-hub z1')
+    U.assert_close(z2, ref2, what='gat 10k-hub z2')
+    (z2 * w.to(DEV)).sum().backward()
+    U.assert_close(xg.grad, xo.grad, what='gat 10k-hub dx')
+
+
+def test_gat_delete_engine_first_step(lib):
+    """GATDeleteEngine (fused, capturable GATDelete epoch): losses and both Del gradients of the first step against the
+    fp64 oracle, then the captured graph against eager steps."""
+    from gnndelete_b200 import models as M
+    from gnndelete_b200.engine import GATDeleteEngine
+    from oracle import unlearn as OU
+    shape, raw, df, data, neg = U.make_case('pubmed', 0.2, in_dim=500)
+    om = U.oracle_model('gat', shape, data, dtype=torch.float64)
+    d64 = data.clone(); d64.x = data.x.double()
+    with torch.no_grad():
+        zo = om.get_original_embeddings(d64.x, d64.train_pos_edge_index[:, d64.dr_mask])
+    loss, lr, ll, _ = OU.edge_form_loss(om, d64, neg, zo)
+    loss.backward()
+
+    def fresh(**kw):
+        m = M.GATDelete(U.args_for(shape), data.sdf_node_1hop_mask, data.sdf_node_2hop_mask)
+        m.load_state_dict({k: v.float() for k, v in om.state_dict().items()}, strict=True)
+        return GATDeleteEngine(m.to(DEV), data.clone().to(DEV), neg.to(DEV), z_ori=zo.float().to(DEV), **kw)
+
+    for hoist in (False, True):
+        eng = fresh(hoist_layer1=hoist, static_negatives=True)
+        got = eng.forward_backward().clone()
+        U.assert_close(got, torch.stack([loss, lr, ll]).detach(), what=f'gat engine losses (hoist={hoist})')
+        U.assert_close(eng.params[0].grad, om.deletion1.deletion_weight.grad, what='gat engine dW_del1')
+        U.assert_close(eng.params[1].grad, om.deletion2.deletion_weight.grad, what='gat engine dW_del2')
+    a, b = fresh(), fresh()
+    a.capture(dynamic_negatives=True)
+    for _ in range(3):
+        U.assert_close(a.epoch(), b.epoch(), tol=1e-5, what='captured vs eager GAT epochs')
+
+
 @pytest.mark.parametrize('num_edge_type,mode', [(51, 'edge'), (51, 'transform'), (51, 'tile'), (9, 'edge'), (9, 'tile')])
 def test_rgcn_delete_forward_and_grads(lib, num_edge_type, mode, monkeypatch):
     """num_edge_type 51 -> block-diagonal weights (num_blocks=4), 9 -> dense relation weights; every RGCN execution
