@@ -131,15 +131,26 @@ def max_over_ranks(value, world, dev):
 
 
 # ------------------------------------------------------------------------ workload
-def build_case(shape, seed, dev, gen_device='cpu', with_eval_edges=True):
-    """Synthetic inputs + masks (CUDA mask pipeline) + random-init model + z_ori."""
+def build_case(shape, seed, dev, gen_device='cpu', with_eval_edges=True, same_on_all_ranks=False):
+    """Synthetic inputs + masks (CUDA mask pipeline) + random-init model + z_ori.  ``same_on_all_ranks``: the inputs
+    generated on rank 0 are broadcast - torch's device-side random permutations / samplers are not bitwise
+    reproducible from one process to the next at the 10 M-node size, and the ranks of a partition must hold the SAME
+    graph."""
     from gnndelete_b200 import synthetic as S
     from gnndelete_b200 import masks as MK
     from gnndelete_b200 import models as M
     raw = S.make_graph(shape, seed=seed, device=gen_device, with_eval_edges=with_eval_edges).to(dev)
     df = S.sample_df_mask(shape.num_edges, shape.num_deleted, seed=seed, device=gen_device).to(dev)
+    if same_on_all_ranks:
+        import torch.distributed as dist
+        dfb = df.to(torch.uint8)
+        for t in (raw.train_pos_edge_index, raw.x, dfb):
+            dist.broadcast(t, 0)
+        df = dfb.bool()
     data = MK.build_unlearning_data(raw, df)
     neg = S.supplied_negatives(shape.num_nodes, int(data.df_mask.sum()), seed=seed + 1, device=gen_device).to(dev)
+    if same_on_all_ranks:
+        dist.broadcast(neg, 0)
     args = types.SimpleNamespace(in_dim=shape.in_dim, hidden_dim=shape.hidden_dim, out_dim=shape.out_dim)
     torch.manual_seed(seed)
     model = M.GCNDelete(args, data.sdf_node_1hop_mask, data.sdf_node_2hop_mask).to(dev)
@@ -344,7 +355,7 @@ def _partition_parity(rank, world, dev, wire, scale=1.0 / 16):
     from gnndelete_b200.dist import PartitionedGCNDeleteEngine
     from gnndelete_b200.engine import GCNDeleteEngine
     shape = S.SHAPES['powerlaw10m'].scaled(scale)
-    data, neg, model, z_ori = build_case(shape, 42, dev, gen_device=dev, with_eval_edges=False)
+    data, neg, model, z_ori = build_case(shape, 42, dev, gen_device=dev, with_eval_edges=False, same_on_all_ranks=world > 1)
     init = {k: v.clone() for k, v in model.state_dict().items()}
     margs = types.SimpleNamespace(in_dim=shape.in_dim, hidden_dim=shape.hidden_dim, out_dim=shape.out_dim)
     m2 = M.GCNDelete(margs, data.sdf_node_1hop_mask, data.sdf_node_2hop_mask).to(dev)
@@ -388,7 +399,7 @@ def run_partitioned(args, shape, rank, local, world, dev, lib, wire='bf16', one_
     if parity is not None and not parity['ok']:
         raise RuntimeError(f'partitioned epoch disagrees with the single-GPU engine: {parity}')
     t_setup = time.perf_counter()
-    data, neg, model, z_ori = build_case(shape, 42, dev, gen_device=dev, with_eval_edges=False)
+    data, neg, model, z_ori = build_case(shape, 42, dev, gen_device=dev, with_eval_edges=False, same_on_all_ranks=world > 1)
     G._GLOBAL_CACHE = G.PlanCache()                      # drop the dr-edge plan before the engines allocate
     torch.cuda.empty_cache()
     init = {k: v.clone() for k, v in model.state_dict().items()}

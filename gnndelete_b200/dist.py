@@ -188,6 +188,15 @@ class PartitionedGCNDeleteEngine:
         self.plan = plan
         n, nl, per, slots = plan.n, plan.n_loc, plan.per, plan.num_slots
         self.nl = nl
+        if self.world > 1:
+            # the ranks must have cut the SAME graph: identical block size and pair counts everywhere
+            sig = [plan.per, plan.norm_df, plan.norm_ni, int(data.sdf_mask.sum())]
+            chk = torch.tensor(sig + [-v for v in sig], dtype=torch.int64, device=dev)
+            self.dist.all_reduce(chk, op=self.dist.ReduceOp.MAX, group=group)
+            chk = chk.tolist()
+            if any(chk[i] != -chk[i + len(sig)] for i in range(len(sig))):
+                raise RuntimeError('the ranks of the partition hold different graphs (block size / pair counts differ): '
+                                   'give every rank the same inputs (e.g. broadcast them from rank 0)')
         hid, out = model.conv1.out_channels, model.conv2.out_channels
         self.x_loc = data.x[plan.lo:plan.hi].contiguous()
         f32 = dict(dtype=torch.float32, device=dev)
