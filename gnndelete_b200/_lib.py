@@ -61,10 +61,11 @@ SIGNATURES = {
     'gd_spmm_batched_tail': (C.c_int, [_bplan_p, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _i32, _vp]),
     'gd_gemm_rows_tc_batch': (C.c_int, [_vp, _i64, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _i64, _i64, _i32, _vp]),
     'gd_gat_scores': (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
-    'gd_gat_fwd': (C.c_int, [_csr_p, _vp, _i64, _i32, _vp, _vp, _vp, _f32, _vp, _i64, _vp, _vp, _vp]),
+    'gd_gat_scratch_floats': (_sz, [_csr_p, _i32]),
+    'gd_gat_fwd': (C.c_int, [_csr_p, _vp, _i64, _i32, _vp, _vp, _vp, _f32, _vp, _i64, _vp, _vp, _vp, _vp]),
     'gd_gat_bwd_dst': (C.c_int, [_csr_p, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _f32,
-                                 _vp, _vp, _vp, _vp]),
-    'gd_gat_bwd_src': (C.c_int, [_csr_p, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+                                 _vp, _vp, _vp, _vp, _vp]),
+    'gd_gat_bwd_src': (C.c_int, [_csr_p, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     'gd_rgcn_norm': (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     'gd_rgcn_conv': (C.c_int, [_csr_p, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     'gd_rgcn_edge_tile_rows': (_i32, [_i32, _i32]),

@@ -252,7 +252,7 @@ class GATDeleteEngine(GCNDeleteEngine):
         L.call('gd_gat_scores', L.ptr(h), h.stride(0), self.n, c, L.ptr(a['src']), L.ptr(a['dst']), L.ptr(a['a_src']),
                L.ptr(a['a_dst']), L.stream())
         L.call('gd_gat_fwd', p.fwd.ref, L.ptr(h), h.stride(0), c, L.ptr(a['a_src']), L.ptr(a['a_dst']), L.ptr(bias),
-               a['slope'], L.ptr(out), out.stride(0), L.ptr(a['rowmax']), L.ptr(a['rowden']), L.stream())
+               a['slope'], L.ptr(out), out.stride(0), L.ptr(a['rowmax']), L.ptr(a['rowden']), L.ptr(p.fwd.gat_scratch(c)), L.stream())
 
     def layer1(self):
         c1 = self.model.conv1
@@ -292,9 +292,11 @@ class GATDeleteEngine(GCNDeleteEngine):
         bias = c2.bias.detach()
         L.call('gd_gat_bwd_dst', p.fwd.ref, L.ptr(self.tinv), L.ptr(self.h1), self.h1.stride(0), out, L.ptr(a['a_src']),
                L.ptr(a['a_dst']), L.ptr(a['rowmax']), L.ptr(a['rowden']), L.ptr(self.da2), self.da2.stride(0), L.ptr(self.a2),
-               self.a2.stride(0), L.ptr(bias), a['slope'], L.ptr(self.alpha_t), L.ptr(self.dpre_t), L.ptr(self.da_dst), L.stream())
+               self.a2.stride(0), L.ptr(bias), a['slope'], L.ptr(self.alpha_t), L.ptr(self.dpre_t), L.ptr(self.da_dst),
+               L.ptr(p.fwd.gat_scratch(out)), L.stream())
         L.call('gd_gat_bwd_src', p.bwd.ref, L.ptr(self.alpha_t), L.ptr(self.dpre_t), L.ptr(self.da2), self.da2.stride(0), out,
-               L.ptr(a['src']), L.ptr(a['dst']), L.ptr(self.da_dst), L.ptr(self.dh1), self.dh1.stride(0), L.ptr(self.da_src), L.stream())
+               L.ptr(a['src']), L.ptr(a['dst']), L.ptr(self.da_dst), L.ptr(self.dh1), self.dh1.stride(0), L.ptr(self.da_src),
+               L.ptr(p.bwd.gat_scratch(out)), L.stream())
         ops.gemm_rows(self.dh1, c2.lin_src.weight.detach(), False, out=self.dx1, rows=self.rows1,
                       gate=None if self.bitmask else self.x1, gate_bits=self.x1_bits)          # ReLU' (dH1 W_2) on S1
         ops.gemm_tn_rows(self.a1, self.dx1, rows=self.rows1, out=g1)               # dW_del1

@@ -76,6 +76,17 @@ class CSR:
             self._bplans[workers] = bp
         return bp
 
+    def gat_scratch(self, channels):
+        """Scratch of the GAT kernels' long-row segments (``gd_gat_scratch_floats``); ``None`` without a split plan."""
+        if self.num_seg == 0:
+            return None
+        key = ('gat', channels)
+        buf = self._scratch.get(key)
+        if buf is None:
+            buf = torch.empty(self.num_seg * (channels + 4), dtype=torch.float32, device=self.rowptr.device)   # 16-byte aligned records
+            self._scratch[key] = buf
+        return buf
+
     def scratch(self, feat):
         """Per-width scratch for the split-row partial sums (allocated once)."""
         if self.num_seg == 0:

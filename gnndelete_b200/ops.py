@@ -538,7 +538,7 @@ class GATAggregateFn(torch.autograd.Function):
         rowden = torch.empty(n, dtype=torch.float32, device=dev)
         b = None if bias is None else bias.detach().contiguous()
         L.call('gd_gat_fwd', plan.fwd.ref, L.ptr(h), h.stride(0), c, L.ptr(a_src), L.ptr(a_dst), L.ptr(b),
-               float(slope), L.ptr(out), out.stride(0), L.ptr(rowmax), L.ptr(rowden), L.stream())
+               float(slope), L.ptr(out), out.stride(0), L.ptr(rowmax), L.ptr(rowden), L.ptr(plan.fwd.gat_scratch(c)), L.stream())
         ctx.plan, ctx.slope = plan, float(slope)
         ctx.save_for_backward(h, att_src, att_dst, a_src, a_dst, rowmax, rowden, out, b if b is not None else h.new_empty(0))
         ctx.has_bias = b is not None
@@ -562,9 +562,10 @@ class GATAggregateFn(torch.autograd.Function):
         L.call('gd_gat_bwd_dst', plan.fwd.ref, L.ptr(plan.tinv), L.ptr(h), h.stride(0), c, L.ptr(a_src),
                L.ptr(a_dst), L.ptr(rowmax), L.ptr(rowden), L.ptr(gout), gout.stride(0), L.ptr(out), out.stride(0),
                L.ptr(b) if ctx.has_bias else None, ctx.slope, L.ptr(alpha_t), L.ptr(dpre_t), L.ptr(da_dst),
-               L.stream())
+               L.ptr(plan.fwd.gat_scratch(c)), L.stream())
         L.call('gd_gat_bwd_src', plan.bwd.ref, L.ptr(alpha_t), L.ptr(dpre_t), L.ptr(gout), gout.stride(0), c,
-               L.ptr(att_src), L.ptr(att_dst), L.ptr(da_dst), L.ptr(dh), dh.stride(0), L.ptr(da_src), L.stream())
+               L.ptr(att_src), L.ptr(att_dst), L.ptr(da_dst), L.ptr(dh), dh.stride(0), L.ptr(da_src),
+               L.ptr(plan.bwd.gat_scratch(c)), L.stream())
         g_src = torch.mv(h.t(), da_src).view(1, 1, -1) if ctx.needs_input_grad[1] else None    # a_src = h att_src
         g_dst = torch.mv(h.t(), da_dst).view(1, 1, -1) if ctx.needs_input_grad[2] else None
         g_bias = gout.sum(0) if ctx.needs_input_grad[3] else None

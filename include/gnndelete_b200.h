@@ -221,21 +221,26 @@ int gd_move_f32(const float* src, const int32_t* src_idx, float* dst, const int3
  *                   in the transposed CSR (`tinv[fwd position] = transposed position`),
  *                   and d a_dst[i];
  *   gd_gat_bwd_src: dh_k = sum_i alpha_ik g_i + d a_src[k] att_src + d a_dst[k] att_dst.
- * out_channels must be 32, 64 or 128. */
+ * out_channels must be 32, 64 or 128.
+ * Rows longer than the CSR's split length (gd_spmm_plan_build) are processed as segments by separate sub-warps and
+ * merged in order (online softmax for the forward) through `scratch`: gd_gat_scratch_floats(csr, channels) floats,
+ * nullable when the CSR carries no split plan (whole rows per sub-warp then). */
 int gd_gat_scores(const float* h, int64_t ldh, int64_t num_nodes, int32_t channels,
                   const float* att_src, const float* att_dst, float* a_src, float* a_dst,
                   gd_stream_t stream);
+size_t gd_gat_scratch_floats(const gd_csr_t* csr, int32_t channels);
 int gd_gat_fwd(const gd_csr_t* csr, const float* h, int64_t ldh, int32_t channels, const float* a_src,
                const float* a_dst, const float* bias, float negative_slope, float* out, int64_t ldo,
-               float* rowmax, float* rowden, gd_stream_t stream);
+               float* rowmax, float* rowden, float* scratch, gd_stream_t stream);
 int gd_gat_bwd_dst(const gd_csr_t* csr, const int32_t* tinv, const float* h, int64_t ldh,
                    int32_t channels, const float* a_src, const float* a_dst, const float* rowmax,
                    const float* rowden, const float* gout, int64_t ldg, const float* out, int64_t ldo,
                    const float* bias, float negative_slope, float* alpha_t, float* dpre_t,
-                   float* da_dst, gd_stream_t stream);
+                   float* da_dst, float* scratch, gd_stream_t stream);
 int gd_gat_bwd_src(const gd_csr_t* csr_t, const float* alpha_t, const float* dpre_t, const float* gout,
                    int64_t ldg, int32_t channels, const float* att_src, const float* att_dst,
-                   const float* da_dst, float* dh, int64_t lddh, float* da_src, gd_stream_t stream);
+                   const float* da_dst, float* dh, int64_t lddh, float* da_src, float* scratch,
+                   gd_stream_t stream);
 
 /* RGCNConv(in, out, R, num_blocks=B|None), aggr='mean', root_weight, bias (rgcn.py:17-22):
  *   out_i = sum_r mean_{k in N_r(i)} x_k . W_r + x_i . root + bias

@@ -1,0 +1,39 @@
+"""Per-kernel shares of ONE epoch from an `ncu --metrics gpu__time_duration.sum --csv` launch list of bench.py.
+usage: python tools/launch_summary.py launches.csv [first_kernel_regex] > summary.md
+The epoch is located as the last run of launches that starts with the layer-1 GEMM (gemm_rows_tc_kernel<2>) and ends
+with the second Adam bump."""
+import csv, re, sys
+rows = []
+with open(sys.argv[1]) as f:
+    lines = [l for l in f if l.startswith('"')]
+rd = csv.reader(lines)
+hdr = next(rd)
+ik, iv, iu = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Metric Unit')
+for r in rd:
+    if len(r) <= iv: continue
+    v = float(r[iv].replace(',', ''))
+    u = r[iu]
+    ns = v * {'ns': 1, 'us': 1e3, 'usecond': 1e3, 'nsecond': 1, 'ms': 1e6, 'msecond': 1e6}.get(u, 1)
+    name = re.sub(r'\(.*', '', r[ik]).replace('void ', '').replace('(int)', '').replace('(bool)', '')
+    rows.append((name, ns))
+# an epoch of the fixed-negatives engine: from a gemm_rows_tc_kernel<2> ... to the 2nd adam_bump after it; take the last complete one
+ends = [i for i, (n, _) in enumerate(rows) if 'adam_bump' in n]
+best = None
+for e in reversed(ends):
+    j = e
+    seen_bump = 0
+    while j >= 0:
+        if 'adam_bump' in rows[j][0]: seen_bump += 1
+        if seen_bump > 2: break
+        j -= 1
+    seg = rows[j + 1:e + 1]
+    if any('spmm_batched_kernel' in n for n, _ in seg) and any('node_loss' in n or 'edge_loss' in n for n, _ in seg):
+        best = seg; break
+agg = {}
+for n, ns in best:
+    c, t = agg.get(n, (0, 0.0)); agg[n] = (c + 1, t + ns)
+tot = sum(t for _, t in agg.values())
+print('| kernel | launches/epoch | ns | share |\n|---|---:|---:|---:|')
+for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print(f'| `{n}` | {c} | {t:.0f} | {100 * t / tot:.1f}% |')
+print(f'| **total** | {sum(c for c, _ in agg.values())} | {tot:.0f} | 100% |')
