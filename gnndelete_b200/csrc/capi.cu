@@ -11,11 +11,6 @@ int fail(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
 }
-bool pdl_enabled() {
-    // opt-in: measured SLOWER on the Collab epoch (917 vs 1090 epochs/s)
-    static const bool on = [] { const char* e = getenv("GD_PDL"); return e && e[0] == '1'; }();
-    return on;
-}
 }  // namespace gd
 
 extern "C" int gd_version(void) { return 100; /* 0.1.0 */ }

@@ -42,25 +42,18 @@ __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
-// ---- programmatic dependent launch (PDL) ---------------------------------------
-// The kernels of one epoch run back to back on one stream / in one CUDA graph.  A kernel launched through
-// launch_pdl may become resident while its predecessor drains: every such kernel executes pdl_wait() before it
-// touches global memory (the predecessor grid has then completed and its writes are visible) and pdl_trigger()
-// right after (the NEXT kernel may start launching once all CTAs of this one have started).  Launched with
-// plain <<<>>> the two instructions are no-ops.  The launch attribute is OFF unless GD_PDL=1: with it the Collab
-// epoch ran at 917 instead of 1090 epochs/s (early-resident dependents take slots from the primary's last CTAs).
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-bool pdl_enabled();
+// ---- kernel launch helper ------------------------------------------------------------
+// Programmatic dependent launch across the epoch's kernels was measured in round 1 (917 instead of 1090 epochs/s on the
+// Collab epoch: early-resident dependents take SM slots from the primary's last CTAs) and removed; launch_pdl is a plain
+// stream-ordered launch, pdl_wait / pdl_trigger compile to nothing.
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_trigger() {}
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.attrs = nullptr;
+    cfg.numAttrs = 0;
     return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }
 

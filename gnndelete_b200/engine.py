@@ -89,8 +89,6 @@ class GCNDeleteEngine:
         # the complement-row copies of the Del layers touch rows the gathered-row GEMM does not: they run on a side
         # stream next to it (fork / join; captured as parallel graph branches)
         self.side = torch.cuda.Stream()
-        self.side2 = torch.cuda.Stream()
-        self.overlap_dw2 = os.environ.get('GD_OVERLAP_DW2', '0') == '1'
 
     def _del_rows(self, src, dst, comp, gemm):
         """``dst[rows] = gemm(src[rows])`` on the current stream, ``dst[comp] = src[comp]`` concurrently."""
@@ -133,23 +131,13 @@ class GCNDeleteEngine:
             self.losses_total[1:2].copy_(self.loss.losses[1:2])
             self.losses_total[2:3].copy_(loss_l)
             torch.add(self.loss.losses[0:1], loss_l, alpha=1.0 - self.alpha, out=self.losses_total[0:1])
-        # dW_del2 = A2[S2]^T dZ[S2] is consumed only by Adam: with GD_OVERLAP_DW2=1 it runs as a parallel branch
-        # next to the input-gradient chain (joined before the dW_del1 GEMM, which shares its workspace family)
-        cur = torch.cuda.current_stream()
-        if self.overlap_dw2:
-            self.side2.wait_stream(cur)
-            with torch.cuda.stream(self.side2):
-                ops.gemm_tn_rows(self.a2, self.dz, rows=self.rows2, out=g2)
-        else:
-            ops.gemm_tn_rows(self.a2, self.dz, rows=self.rows2, out=g2)            # dW_del2
+        ops.gemm_tn_rows(self.a2, self.dz, rows=self.rows2, out=g2)            # dW_del2
         self._del_rows(self.dz, self.da2, self.comp2, lambda: ops.gemm_rows(                  # dz[S2] @ W2^T
             self.dz, w2, True, out=self.da2, rows=self.rows2))
         ops.spmm(p.bwd, self.da2, out=self.dh1, col_scale=p.dinv)                  # A^T D^-1/2 dA2
         ops.gemm_rows(self.dh1, m.conv2.lin.weight.detach(), False, out=self.dx1, rows=self.rows1,
                       out_scale=p.dinv, gate=None if self.bitmask else self.x1,
                       gate_bits=self.x1_bits)                                      # ReLU' (D^-1/2 dH1) W_2 on S1
-        if self.overlap_dw2:
-            cur.wait_stream(self.side2)
         ops.gemm_tn_rows(self.a1, self.dx1, rows=self.rows1, out=g1)               # dW_del1
 
     def forward_backward(self):

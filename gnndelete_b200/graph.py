@@ -17,9 +17,8 @@ import torch
 from . import _lib as L
 
 SEG_LEN = 128    # rows longer than this are split into segments (spmm.cu)
-GROUP_NNZ = 128  # target entries per row group of the streaming aggregation kernel
 DEG_SORT_WINDOW = 4096
-# GD_SPMM=pipe|stream selects the older row-walking kernels (A/B measurements); default: batched
+# GD_SPMM=pipe selects the older row-walking kernel (A/B measurements, tests/test_gpu_fullsize.py); default: batched
 BATCHED = os.environ.get('GD_SPMM', 'batched')[0] == 'b'
 OVERSUB = int(os.environ.get('GD_SPMM_OVERSUB', '1'))
 
@@ -270,21 +269,6 @@ def degree_window_perm(rowptr, window=DEG_SORT_WINDOW):
     return torch.argsort(key, stable=True).to(torch.int32)
 
 
-def row_groups(rowptr, seg_len, target=GROUP_NNZ):
-    """``grp_row`` of the streaming aggregation kernel: consecutive rows are grouped until
-    they hold ~``target`` entries; a row longer than ``seg_len`` forms a group of its own."""
-    n = rowptr.numel() - 1
-    deg = (rowptr[1:] - rowptr[:-1]).long()
-    heavy = deg > seg_len if seg_len else torch.zeros_like(deg, dtype=torch.bool)
-    light = torch.where(heavy, torch.zeros_like(deg), deg)
-    bucket = (torch.cumsum(light, 0) - light) // target
-    start = torch.ones(n, dtype=torch.bool, device=rowptr.device)
-    if n > 1:
-        start[1:] = heavy[1:] | heavy[:-1] | (bucket[1:] != bucket[:-1])
-    first = start.nonzero().squeeze(1)
-    return torch.cat([first, first.new_tensor([n])]).to(torch.int32)
-
-
 def build_csr(src, dst, num_nodes, self_loops=False, rel=None, num_rel=1, seg_len=SEG_LEN, deg_sort=False):
     """COO (int64, ``src -> dst``) -> :class:`CSR` via ``gd_csr_from_coo`` +
     ``gd_spmm_plan_build``.  Raises on out-of-range endpoints."""
@@ -325,7 +309,7 @@ def build_csr(src, dst, num_nodes, self_loops=False, rel=None, num_rel=1, seg_le
             bufs['heavy_ticket'] = torch.zeros(nh, dtype=torch.int32, device=dev)
             plan = dict(seg_len=int(seg_len), num_heavy=nh, num_seg=ns, **bufs)
     perm = None      # visiting-order permutation: unused by the row-pipelined kernel (kept in the ABI)
-    groups = row_groups(rowptr, int(seg_len) if seg_len else 0) if N > 0 else None
+    groups = None    # row groups of the (removed) streaming kernel: the ABI field stays reserved
     return CSR(rowptr, col, eid, rel_out, N, nnz, plan, perm, groups)
 
 

@@ -66,9 +66,7 @@ typedef struct gd_csr {
     int32_t* heavy_ticket;        /* [num_heavy] zero-initialised; self re-arming completion counters */
     /* optional visiting order of the rows (e.g. degree-sorted inside windows); NULL = identity */
     const int32_t* row_perm;      /* [num_rows] */
-    /* optional row groups for the streaming aggregation kernel: group g = rows
-     * [grp_row[g], grp_row[g+1]) with ~128 entries in total; a row longer than seg_len is a
-     * group of its own (processed through its segments).  NULL = sub-warp-per-row kernel. */
+    /* reserved (row groups of a removed streaming kernel): NULL / 0 */
     const int32_t* grp_row;       /* [num_grp + 1] */
     int32_t num_grp;
 } gd_csr_t;
