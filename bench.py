@@ -206,9 +206,9 @@ def time_kernels(eng, data, steps):
         ops.copy_rows(eng.a2, eng.z, eng.comp2)
         timed('loss_fwd_bwd', lambda: (eng.loss.forward(eng.z, dz_out=eng.dz), eng.loss.backward(eng.z, out=eng.dz)))
         timed('gemm_dw2', lambda: ops.gemm_tn_rows(eng.a2, eng.dz, rows=eng.rows2, out=eng.params[1].grad))
-        timed('gemm_da2', lambda: ops.gemm_rows(eng.dz, w2, True, out=eng.da2, rows=eng.rows2))
-        ops.copy_rows(eng.dz, eng.da2, eng.comp2)
-        timed('spmm_bwd_f64', lambda: ops.spmm(p.bwd, eng.da2, out=eng.dh1, col_scale=p.dinv))
+        timed('gemm_da2', lambda: ops.gemm_rows(eng.dz, w2, True, out=eng.da2, rows=eng.rows2, out_scale=p.dinv))
+        ops.copy_rows(eng.dz, eng.da2, eng.comp2, row_scale=p.dinv)
+        timed('spmm_bwd_f64', lambda: ops.spmm(p.bwd, eng.da2, out=eng.dh1))
         timed('gemm_dx1', lambda: ops.gemm_rows(eng.dh1, W2, False, out=eng.dx1, rows=eng.rows1, out_scale=p.dinv,
                                                 gate=None if eng.bitmask else eng.x1, gate_bits=eng.x1_bits))
         timed('gemm_dw1', lambda: ops.gemm_tn_rows(eng.a1, eng.dx1, rows=eng.rows1, out=eng.params[0].grad))

@@ -83,6 +83,7 @@ SIGNATURES = {
     'gd_gemm_tn_tc_workspace_bytes': (_sz, [_i32, _i32]),
     'gd_gemm_tn_rows_tc': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     'gd_copy_rows': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
+    'gd_copy_rows_scaled': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _i64, _vp]),
     'gd_relu_fwd': (C.c_int, [_vp, _i64, _vp, _vp]),
     'gd_relu_bwd': (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     'gd_edge_loss_workspace_bytes': (_sz, [_i64]),

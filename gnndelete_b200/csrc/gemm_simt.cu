@@ -191,16 +191,32 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int np
     }
 }
 
+// dst[r, :] = scale[r] * src[r, :] for r in rows (scale optional).  VEC: 128-bit accesses, feat / 4 lanes per row
+// (a warp moves 128 / feat ... rows per step); the scalar variant covers unaligned operands.
+template <bool VEC>
 __global__ void copy_rows_kernel(const float* __restrict__ src, int64_t lds, const int32_t* __restrict__ rows,
-                                 int64_t m, int feat, float* __restrict__ dst, int64_t ldd) {
+                                 int64_t m, int feat, const float* __restrict__ scale, float* __restrict__ dst, int64_t ldd) {
     pdl_wait();
     pdl_trigger();
-    // one warp per row
-    const int lane = threadIdx.x & 31;
-    for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; i < m;
-         i += ((int64_t)gridDim.x * blockDim.x) >> 5) {
-        const int64_t r = rows ? rows[i] : i;
-        for (int f = lane; f < feat; f += 32) dst[r * ldd + f] = src[r * lds + f];
+    if (VEC) {
+        const int f4 = feat >> 2;
+        const int64_t total = m * f4, step = (int64_t)gridDim.x * blockDim.x;
+        for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += step) {
+            const int64_t i = t / f4;
+            const int c = (int)(t - i * f4);
+            const int64_t r = rows ? rows[i] : i;
+            float4 v = __ldg(reinterpret_cast<const float4*>(src + r * lds) + c);
+            if (scale) { const float sc = __ldg(scale + r); v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; }
+            reinterpret_cast<float4*>(dst + r * ldd)[c] = v;
+        }
+    } else {
+        const int lane = threadIdx.x & 31;                  // one warp per row
+        for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; i < m;
+             i += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+            const int64_t r = rows ? rows[i] : i;
+            const float sc = scale ? scale[r] : 1.0f;
+            for (int f = lane; f < feat; f += 32) dst[r * ldd + f] = scale ? sc * src[r * lds + f] : src[r * lds + f];
+        }
     }
 }
 
@@ -294,14 +310,25 @@ extern "C" int gd_gemm_tn_rows(const float* a, int64_t lda, const float* g, int6
     return GD_OK;
 }
 
-extern "C" int gd_copy_rows(const float* src, int64_t lds, const int32_t* rows, int64_t m, int32_t feat,
-                            float* dst, int64_t ldd, gd_stream_t stream) {
+extern "C" int gd_copy_rows_scaled(const float* src, int64_t lds, const int32_t* rows, int64_t m, int32_t feat,
+                                   const float* row_scale, float* dst, int64_t ldd, gd_stream_t stream) {
     if (m == 0) return GD_OK;
     GD_CHECK_ARG(src && dst && feat > 0, "bad argument");
-    int blocks = (int)std::min<int64_t>(ceil_div<int64_t>(m, 8), kNumSMs * 32);
-    GD_CUDA(launch_pdl(copy_rows_kernel, blocks, 256, 0, as_stream(stream), src, lds, rows, m, feat, dst, ldd));
+    const bool vec = feat % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && (((uintptr_t)src | (uintptr_t)dst) % 16) == 0;
+    if (vec) {
+        const int blocks = (int)std::min<int64_t>(ceil_div<int64_t>(m * (feat / 4), 256), kNumSMs * 16);
+        GD_CUDA(launch_pdl(copy_rows_kernel<true>, blocks, 256, 0, as_stream(stream), src, lds, rows, m, feat, row_scale, dst, ldd));
+    } else {
+        const int blocks = (int)std::min<int64_t>(ceil_div<int64_t>(m, 8), kNumSMs * 32);
+        GD_CUDA(launch_pdl(copy_rows_kernel<false>, blocks, 256, 0, as_stream(stream), src, lds, rows, m, feat, row_scale, dst, ldd));
+    }
     GD_LAUNCH_CHECK();
     return GD_OK;
+}
+
+extern "C" int gd_copy_rows(const float* src, int64_t lds, const int32_t* rows, int64_t m, int32_t feat,
+                            float* dst, int64_t ldd, gd_stream_t stream) {
+    return gd_copy_rows_scaled(src, lds, rows, m, feat, nullptr, dst, ldd, stream);
 }
 
 extern "C" int gd_relu_bwd(const float* grad, const float* pre, int64_t count, float* out, gd_stream_t stream) {

@@ -98,6 +98,25 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo, u
     d |= (uint64_t)1 << 61;
     return d;
 }
+// The descriptors of one kernel differ only in their start-address field (bits [0,14) = shared address >> 4; every
+// operand tile lies below 256 KB, so adding (byte offset >> 4) to the low word never carries into another field):
+// the MMA thread builds one descriptor per operand and advances it with integer additions.  Re-deriving every
+// descriptor from its address (shift / mask / or on the uniform datapath, 4 per k-step) made the single issuing
+// thread the slowest stage of the pipeline (profiles/r1_gemm_phase_knobs.md: ~0.45 us per stage).
+__device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t byte_off) { return d + (uint64_t)(byte_off >> 4); }
+// One lane of a converged warp (elect.sync): unlike `lane == 0`, the compiler knows a single thread is active inside
+// and issues the uniform-datapath tcgen05 instructions without an election loop around each of them.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128
 __device__ __forceinline__ uint32_t make_idesc(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -368,8 +387,9 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) gemm_rows_tc_kernel(const Arg
         }
     } else if (warp == ROWS_MMA_WARP) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = make_idesc(g.n);
+            const uint64_t da0 = make_desc(smem_u32(a_ring)), db_hi0 = make_desc(smem_u32(b_hi)), db_lo0 = make_desc(smem_u32(b_lo));
             uint32_t stage = 0, phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
@@ -381,16 +401,16 @@ __global__ void __launch_bounds__(ROWS_THREADS, 1) gemm_rows_tc_kernel(const Arg
                     mbar_wait(&full_bar[stage], phase);
                     fence_proxy_async();                           // the producers' generic stores -> async proxy (see consume())
                     tc_fence_after();
-                    const uint32_t ahi = smem_u32(a_ring + stage * 2 * TILE_BYTES), alo = ahi + TILE_BYTES;
-                    const uint32_t bhi = smem_u32(b_hi + c * b_tile), blo = smem_u32(b_lo + c * b_tile);
+                    const uint64_t da_hi = desc_advance(da0, stage * 2 * TILE_BYTES), da_lo = desc_advance(da_hi, TILE_BYTES);
+                    const uint64_t db_hi = desc_advance(db_hi0, c * b_tile), db_lo = desc_advance(db_lo0, c * b_tile);
+                    if (!(g.debug & 4)) {
 #pragma unroll
-                    for (int ks = 0; ks < KC / 8; ++ks) {
-                        const uint64_t da_hi = make_desc(ahi + ks * 32), da_lo = make_desc(alo + ks * 32);
-                        const uint64_t db_hi = make_desc(bhi + ks * 32), db_lo = make_desc(blo + ks * 32);
-                        if (g.debug & 4) continue;
-                        umma_tf32(dc, da_lo, db_hi, idesc, (c | ks) != 0);
-                        umma_tf32(dc, da_hi, db_lo, idesc, 1);
-                        umma_tf32(d, da_hi, db_hi, idesc, (c | ks) != 0);
+                        for (int ks = 0; ks < KC / 8; ++ks) {       // one k-step = 8 tf32 = 32 bytes along the swizzled row
+                            const uint32_t accum = (ks != 0) || (c != 0);
+                            umma_tf32(dc, da_lo + 2 * ks, db_hi + 2 * ks, idesc, accum);
+                            umma_tf32(dc, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1);
+                            umma_tf32(d, da_hi + 2 * ks, db_hi + 2 * ks, idesc, accum);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);                // frees the smem stage when the MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -658,8 +678,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tn_tc_kernel(const TnArgs
             }
         }
     } else if (warp == MMA_WARP) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = make_idesc_mn(t.n2);
+            // stage layout: A^T hi | A^T lo | G^T hi | G^T lo; rows 8 ks .. 8 ks + 7 of a stage = two 4-row k-atoms (512 B each)
+            // inside every 4 KB feature-atom column, i.e. + 1024 bytes per k-step
+            const uint64_t da0 = make_desc_mn(smem_u32(smem), TN_ATOM_COL, 512);
             uint32_t stage = 0, phase = 0;
             for (int grp = 0; grp < ngroups; ++grp) {
                 const uint32_t acc = grp & 1, acc_phase = (grp >> 1) & 1;
@@ -671,18 +694,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tn_tc_kernel(const TnArgs
                     mbar_wait(&full_bar[stage], phase);
                     fence_proxy_async();                           // the producers' generic stores -> async proxy
                     tc_fence_after();
-                    const uint32_t ahi = smem_u32(smem + stage * stage_bytes), alo = ahi + TILE_BYTES;
-                    const uint32_t ghi = alo + TILE_BYTES, glo = ghi + g_tile;
+                    const uint64_t da_hi = desc_advance(da0, stage * stage_bytes), da_lo = desc_advance(da_hi, TILE_BYTES);
+                    const uint64_t db_hi = desc_advance(da_lo, TILE_BYTES), db_lo = desc_advance(db_hi, g_tile);
                     const bool first = (s == grp * TN_FLUSH);
 #pragma unroll
                     for (int ks = 0; ks < KC / 8; ++ks) {
-                        // rows 8 ks .. 8 ks + 7 of the stage = two 4-row k-atoms (512 B each) inside every 4 KB feature-atom column
-                        const uint64_t da_hi = make_desc_mn(ahi + ks * 1024, TN_ATOM_COL, 512), da_lo = make_desc_mn(alo + ks * 1024, TN_ATOM_COL, 512);
-                        const uint64_t db_hi = make_desc_mn(ghi + ks * 1024, TN_ATOM_COL, 512), db_lo = make_desc_mn(glo + ks * 1024, TN_ATOM_COL, 512);
                         const uint32_t accum = !(first && ks == 0);
-                        umma_tf32(dc, da_lo, db_hi, idesc, accum);
-                        umma_tf32(dc, da_hi, db_lo, idesc, 1);
-                        umma_tf32(d, da_hi, db_hi, idesc, accum);
+                        umma_tf32(dc, da_lo + 64 * ks, db_hi + 64 * ks, idesc, accum);
+                        umma_tf32(dc, da_hi + 64 * ks, db_lo + 64 * ks, idesc, 1);
+                        umma_tf32(d, da_hi + 64 * ks, db_hi + 64 * ks, idesc, accum);
                     }
                     umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -772,8 +792,7 @@ extern "C" int gd_gemm_rows_tc(const float* a, int64_t lda, const int32_t* rows,
     GD_CHECK_ARG(((uintptr_t)a | (uintptr_t)out | (uintptr_t)gate) % 16 == 0 && (!gate || ldgate % 4 == 0), "operands must be 16-byte aligned");
     tc::Args g{a, lda, rows, m, k, b, b_is_nk, n, bias, out_scale, gate, ldgate, relu_in, relu_out, out, ldo,
                relu_mask_out, gate_bits, (int)ceil_div<int64_t>(m, tc::BM), tc::num_stages(k, n), 0};
-    static const int dbg = [] { const char* e = getenv("GD_TC_DEBUG"); return e ? atoi(e) : 0; }();
-    g.debug = dbg;
+    { const char* e = getenv("GD_TC_DEBUG"); g.debug = e ? atoi(e) : 0; }     // measurement only; read per call so one process can sweep it
     const size_t smem = tc::smem_bytes(k, n);
     const int grid = std::min(g.num_tiles, kNumSMs);
     const int need = (bias ? tc::EPI_BIAS : 0) | (out_scale ? tc::EPI_SCALE : 0) | (relu_out ? tc::EPI_RELU : 0) |

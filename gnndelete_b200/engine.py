@@ -90,12 +90,12 @@ class GCNDeleteEngine:
         # stream next to it (fork / join; captured as parallel graph branches)
         self.side = torch.cuda.Stream()
 
-    def _del_rows(self, src, dst, comp, gemm):
-        """``dst[rows] = gemm(src[rows])`` on the current stream, ``dst[comp] = src[comp]`` concurrently."""
+    def _del_rows(self, src, dst, comp, gemm, row_scale=None):
+        """``dst[rows] = gemm(src[rows])`` on the current stream, ``dst[comp] = (row_scale *) src[comp]`` concurrently."""
         cur = torch.cuda.current_stream()
         self.side.wait_stream(cur)
         with torch.cuda.stream(self.side):
-            ops.copy_rows(src, dst, comp)
+            ops.copy_rows(src, dst, comp, row_scale=row_scale)
         gemm()
         cur.wait_stream(self.side)
 
@@ -132,9 +132,11 @@ class GCNDeleteEngine:
             self.losses_total[2:3].copy_(loss_l)
             torch.add(self.loss.losses[0:1], loss_l, alpha=1.0 - self.alpha, out=self.losses_total[0:1])
         ops.gemm_tn_rows(self.a2, self.dz, rows=self.rows2, out=g2)            # dW_del2
-        self._del_rows(self.dz, self.da2, self.comp2, lambda: ops.gemm_rows(                  # dz[S2] @ W2^T
-            self.dz, w2, True, out=self.da2, rows=self.rows2))
-        ops.spmm(p.bwd, self.da2, out=self.dh1, col_scale=p.dinv)                  # A^T D^-1/2 dA2
+        # da2 <- D^-1/2 dA2: the source-side factor of the transpose aggregation is applied where its operand is produced
+        # (GEMM epilogue / complement copy), so the aggregation runs without per-entry weights
+        self._del_rows(self.dz, self.da2, self.comp2, lambda: ops.gemm_rows(                  # D^-1/2 (dz[S2] @ W2^T)
+            self.dz, w2, True, out=self.da2, rows=self.rows2, out_scale=p.dinv), row_scale=p.dinv)
+        ops.spmm(p.bwd, self.da2, out=self.dh1)                                    # A^T (D^-1/2 dA2)
         ops.gemm_rows(self.dh1, m.conv2.lin.weight.detach(), False, out=self.dx1, rows=self.rows1,
                       out_scale=p.dinv, gate=None if self.bitmask else self.x1,
                       gate_bits=self.x1_bits)                                      # ReLU' (D^-1/2 dH1) W_2 on S1

@@ -170,9 +170,10 @@ def gemm_tn_rows(a, g, rows=None, relu_a=False, a_scale=None, out=None):
     return out
 
 
-def copy_rows(src, dst, rows):
-    L.call('gd_copy_rows', L.ptr(src), src.stride(0), L.ptr(rows), rows.numel(), src.shape[1],
-           L.ptr(dst), dst.stride(0), L.stream())
+def copy_rows(src, dst, rows, row_scale=None):
+    """``dst[rows] = src[rows]`` (``* row_scale[rows]`` when given)."""
+    L.call('gd_copy_rows_scaled', L.ptr(src), src.stride(0), L.ptr(rows), rows.numel(), src.shape[1],
+           L.ptr(row_scale), L.ptr(dst), dst.stride(0), L.stream())
     return dst
 
 

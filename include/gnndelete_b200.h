@@ -339,6 +339,12 @@ int gd_gemm_tn_rows_tc(const float* a, int64_t lda, const float* g, int64_t ldg,
 int gd_copy_rows(const float* src, int64_t lds, const int32_t* rows, int64_t m, int32_t feat,
                  float* dst, int64_t ldd, gd_stream_t stream);
 
+/* dst[rows[i], :] = row_scale[rows[i]] * src[rows[i], :]  (row_scale may be NULL).  Backward of the GCN epoch: the
+ * D^-1/2 factor of the transpose aggregation's source rows is applied where dA2 is produced (here for the unmasked
+ * rows, in the Del GEMM's epilogue for the masked ones), so the aggregation itself runs without per-entry weights. */
+int gd_copy_rows_scaled(const float* src, int64_t lds, const int32_t* rows, int64_t m, int32_t feat,
+                        const float* row_scale, float* dst, int64_t ldd, gd_stream_t stream);
+
 /* out = max(x, 0)  (F.relu between the two convs, deletion.py:67; used where the ReLU
  * cannot be folded into the next contraction's prologue: GIN / RGCN aggregate first) */
 int gd_relu_fwd(const float* x, int64_t count, float* out, gd_stream_t stream);
