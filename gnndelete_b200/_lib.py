@@ -105,6 +105,11 @@ SIGNATURES = {
     'gd_dense_ni_fwd_bwd': (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i64, _vp, _f32, _vp, _i64, _vp, _vp, _sz, _vp]),
     'gd_row_mse_workspace_bytes': (_sz, [_i64]),
     'gd_row_mse_fwd_bwd': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i64, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _i64, _vp, _vp, _sz, _vp]),
+    'gd_dense_ni_tc_supported': (C.c_int, [_i32]),
+    'gd_dense_ni_tc_target_bytes': (_sz, [_i64]),
+    'gd_dense_ni_tc_pack_target': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    'gd_dense_ni_tc_workspace_bytes': (_sz, [_i64]),
+    'gd_dense_ni_tc_fwd_bwd': (C.c_int, [_vp, _i64, _i64, _vp, _f32, _vp, _i64, _vp, _vp, _sz, _vp]),
     'gd_add_rows': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     'gd_pair_decode': (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     'gd_adam_step': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp]),

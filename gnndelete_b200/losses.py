@@ -10,6 +10,8 @@ incidence slots; the gradient w.r.t. the embeddings is then a deterministic CSR 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -387,7 +389,18 @@ class DenseNIPlan:
         self.dzs = torch.empty(max(n_s, 1), self.dim, dtype=torch.float32, device=dev)
         self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.ws_bytes = L.load().gd_dense_ni_workspace_bytes(n_s)
+        lib = L.load()
+        # tensor-core kernel (tcgen05, 3xTF32) for the reference's 64-wide embeddings; GD_DENSE_NI=simt keeps the fp32
+        # CUDA-core kernel (the only one for other widths)
+        self.tensor_core = bool(lib.gd_dense_ni_tc_supported(self.dim)) and os.environ.get('GD_DENSE_NI', 'tc') != 'simt' and n_s > 0
+        if self.tensor_core:
+            self.packed = torch.empty(lib.gd_dense_ni_tc_target_bytes(n_s) // 4, dtype=torch.float32, device=dev)
+            L.call('gd_dense_ni_tc_pack_target', L.ptr(self.tgt), self.tgt.stride(0), L.ptr(self.excl), n_s, L.ptr(self.packed), L.stream())
+            torch.cuda.current_stream().synchronize()
+            self.tgt = self.excl = None                  # the packed tiles carry both (sentinel -1 = pair not in M)
+            self.ws_bytes = lib.gd_dense_ni_tc_workspace_bytes(n_s)
+        else:
+            self.ws_bytes = lib.gd_dense_ni_workspace_bytes(n_s)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
 
     def forward_backward(self, z, dz):
@@ -396,9 +409,13 @@ class DenseNIPlan:
             return self.loss_sum * 0.0
         L.call('gd_gather_rows', L.ptr(z, 'f32'), z.stride(0), z.shape[0], L.ptr(self.S, 'i64'), self.n_s, self.dim,
                L.ptr(self.zs), self.zs.stride(0), L.ptr(self.status), L.stream())
-        L.call('gd_dense_ni_fwd_bwd', L.ptr(self.zs), self.zs.stride(0), self.dim, self.n_s, L.ptr(self.tgt),
-               self.tgt.stride(0), L.ptr(self.excl), self.scale, L.ptr(self.dzs), self.dzs.stride(0), L.ptr(self.loss_sum),
-               L.ptr(self.ws), self.ws_bytes, L.stream())
+        if self.tensor_core:
+            L.call('gd_dense_ni_tc_fwd_bwd', L.ptr(self.zs), self.zs.stride(0), self.n_s, L.ptr(self.packed), self.scale,
+                   L.ptr(self.dzs), self.dzs.stride(0), L.ptr(self.loss_sum), L.ptr(self.ws), self.ws_bytes, L.stream())
+        else:
+            L.call('gd_dense_ni_fwd_bwd', L.ptr(self.zs), self.zs.stride(0), self.dim, self.n_s, L.ptr(self.tgt),
+                   self.tgt.stride(0), L.ptr(self.excl), self.scale, L.ptr(self.dzs), self.dzs.stride(0), L.ptr(self.loss_sum),
+                   L.ptr(self.ws), self.ws_bytes, L.stream())
         L.call('gd_add_rows', L.ptr(self.dzs), self.dzs.stride(0), L.ptr(self.S32), self.n_s, self.dim, L.ptr(dz),
                dz.stride(0), L.stream())
         return self.loss_sum / self.num_pairs

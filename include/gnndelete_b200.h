@@ -436,6 +436,21 @@ int gd_dense_ni_fwd_bwd(const float* zs, int64_t ldz, int32_t dim, int64_t n_s, 
                         int64_t ldt, const uint32_t* excl_bits, float coef_scale, float* dzs,
                         int64_t lddz, float* loss_sum, void* workspace, size_t workspace_bytes,
                         gd_stream_t stream);
+/* The same loss on the tensor cores (tcgen05.mma kind::tf32 with the 3xTF32 operand split, accumulators in TMEM): one CTA
+ * per 128 rows of z_S sweeps the 64-row column blocks - logit tile, sigmoid / residual / coefficient epilogue out of
+ * TMEM, gradient contraction accumulated in TMEM; nothing N x N is formed.  The target block is packed once
+ * (gd_dense_ni_tc_pack_target: tile-major, coalesced for the epilogue's row-per-thread reads; excluded pairs, the
+ * diagonal and the padding carry the sentinel -1, so the kernel reads no bitmap).  dim must be 64
+ * (gd_dense_ni_tc_supported); same outputs and the same coef_scale as gd_dense_ni_fwd_bwd. */
+int gd_dense_ni_tc_supported(int32_t dim);
+size_t gd_dense_ni_tc_target_bytes(int64_t n_s);
+int gd_dense_ni_tc_pack_target(const float* tgt_sig, int64_t ldt, const uint32_t* excl_bits, int64_t n_s,
+                               float* packed_target, gd_stream_t stream);
+size_t gd_dense_ni_tc_workspace_bytes(int64_t n_s);
+int gd_dense_ni_tc_fwd_bwd(const float* zs, int64_t ldz, int64_t n_s, const float* packed_target, float coef_scale,
+                           float* dzs, int64_t lddz, float* loss_sum, void* workspace, size_t workspace_bytes,
+                           gd_stream_t stream);
+
 /* dst[rows[i], :] += src[i, :]   (rows unique) */
 int gd_add_rows(const float* src, int64_t lds, const int32_t* rows, int64_t m, int32_t feat, float* dst,
                 int64_t ldd, gd_stream_t stream);

@@ -125,6 +125,47 @@ def test_dense_block_ni_matches_fullbatch_oracle(lib):
     dense_ni_case(0.03)
 
 
+@pytest.mark.parametrize('n_s', [37, 128, 700, 1500])
+def test_dense_ni_tensor_core_kernel_matches_fp64(lib, n_s, monkeypatch):
+    """gd_dense_ni_tc_fwd_bwd (tcgen05, 3xTF32) on its own: loss sum and dz against an fp64 evaluation of
+    gnndelete.py:239-241 on the S x S block, and against the fp32 CUDA-core kernel.  Sizes cover a partial row block,
+    one exact block, a split J sweep (jsplit > 1) and ragged last blocks; excluded (Df) pairs in both orders."""
+    from gnndelete_b200.losses import DenseNIPlan
+    torch.manual_seed(n_s)
+    n = n_s + 50
+    mask = torch.zeros(n, dtype=torch.bool)
+    mask[torch.randperm(n)[:n_s]] = True
+    S = mask.nonzero().squeeze(1)
+    z_ori = torch.randn(n, 64, dtype=torch.float64) * 0.4
+    z = z_ori + 0.1 * torch.randn(n, 64, dtype=torch.float64)
+    logits_ori = z_ori @ z_ori.t()
+    df = torch.stack([S[torch.randint(0, n_s, (3 * n_s,))], S[torch.randint(0, n_s, (3 * n_s,))]])
+    # fp64 reference on the block
+    zs = z[S].clone().requires_grad_(True)
+    keep = torch.ones(n_s, n_s, dtype=torch.bool).tril(-1)
+    pos = torch.full((n,), -1, dtype=torch.long); pos[S] = torch.arange(n_s)
+    pu, pv = pos[df[0]], pos[df[1]]
+    keep[pu, pv] = False; keep[pv, pu] = False
+    res = (torch.sigmoid(zs @ zs.t()) - torch.sigmoid(logits_ori[S][:, S]))[keep]
+    loss_ref = (res ** 2).mean()
+    (0.5 * loss_ref).backward()
+    out = {}
+    for mode in ('tc', 'simt'):
+        monkeypatch.setenv('GD_DENSE_NI', mode)
+        plan = DenseNIPlan(mask.to(DEV), df.to(DEV), logits_ori.float().to(DEV), n, 64, weight=0.5)
+        assert plan.tensor_core == (mode == 'tc')
+        assert plan.num_pairs == int(keep.sum())
+        dz = torch.zeros(n, 64, device=DEV)
+        loss = plan.forward_backward(z.float().to(DEV), dz)
+        loss2 = plan.forward_backward(z.float().to(DEV), torch.zeros_like(dz))      # second call: same result (TMEM / barriers re-armed)
+        assert torch.equal(loss, loss2)
+        U.assert_close(loss.reshape(()), loss_ref.detach(), what=f'dense NI loss ({mode})')
+        U.assert_close(dz[S.to(DEV)], zs.grad, what=f'dense NI dz ({mode})')
+        assert float(dz[~mask.to(DEV)].abs().max()) == 0.0
+        out[mode] = (loss, dz)
+    U.assert_close(out['tc'][1], out['simt'][1], what='tensor-core vs CUDA-core dz')
+
+
 def dense_ni_case(scale):
     from gnndelete_b200 import models as M
     from gnndelete_b200.engine import GCNDeleteEngine
