@@ -224,6 +224,81 @@ def time_kernels(eng, data, steps):
     return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in rec.items()}
 
 
+def load_tensor_peak():
+    """(TF32 dense TFLOP/s, source): half of the measured bf16 figure of MEASURED_PEAKS.json (kind::tf32 runs at half the
+    bf16 rate; the sustained number - the kernel is timed inside a loop), else half of the recipe's fallback."""
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['bf16_tflops_sustained']) / 2, 'measured (MEASURED_PEAKS.json bf16_tflops_sustained / 2: kind::tf32 runs at half the bf16 rate)'
+    except (OSError, KeyError, ValueError):
+        return 1400.0 / 2, 'fallback (B200_PROFILING.md sustained bf16 1.4 PFLOP/s / 2)'
+
+
+def run_dense_ni_block(dev, lib, steps):
+    """BASELINE config 1 as the reference runs it: train_fullbatch's dense S2 x S2 NI loss (gnndelete.py:163-193,
+    239-241) on the Cora shape - the path's one tensor-bound contraction.  Epochs/s of the captured engine with that
+    loss, the kernel alone (CUDA events over graph replays) against the TF32 tensor roofline, and the fp32 CUDA-core
+    kernel for comparison."""
+    from gnndelete_b200 import synthetic as S
+    from gnndelete_b200.engine import GCNDeleteEngine
+    from gnndelete_b200 import graph as G
+    shape = S.SHAPES['cora']
+    data, neg, model, z_ori = build_case(shape, 42, dev)
+    logits_ori = z_ori @ z_ori.t()                                 # what base.py:288 stores in pred_proba.pt
+    st = torch.cuda.current_stream()
+    out = {'workload': f'GCNDelete edge unlearning, cora-shaped synthetic graph ({shape.num_nodes} nodes / {shape.num_edges} directed '
+                       f'edges / {shape.num_deleted} deleted), dense-block NI loss of train_fullbatch, full graph per step'}
+    for mode in ('tc', 'simt'):
+        os.environ['GD_DENSE_NI'] = mode
+        eng = GCNDeleteEngine(model, data, neg, z_ori=z_ori, hoist_layer1=False, static_negatives=True, logits_ori=logits_ori)
+        plan = eng.dense
+        n_s, pairs = plan.n_s, plan.num_pairs
+        eng.capture(warmup=2)
+        for _ in range(3):
+            eng.epoch()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k = max(10, min(steps, 50) if mode == 'tc' else 10)
+        torch.cuda.synchronize()
+        a.record(st)
+        for _ in range(k):
+            eng.epoch()
+        b.record(st)
+        torch.cuda.synchronize()
+        ms_epoch = a.elapsed_time(b) / k
+        # the kernel alone: gather of z[S], the contraction kernel, the scatter-add of dz[S] (graph of 5 calls)
+        z, dz = eng.z, torch.zeros_like(eng.z)
+        g = torch.cuda.CUDAGraph()
+        plan.forward_backward(z, dz)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            for _ in range(5):
+                plan.forward_backward(z, dz)
+        g.replay(); torch.cuda.synchronize()
+        a.record(st); g.replay(); b.record(st); torch.cuda.synchronize()
+        ms_k = a.elapsed_time(b) / 5
+        flops = 2 * 2.0 * n_s * n_s * 64                               # both contractions over the full S x S block (each pair from both sides)
+        rec = {'epochs_per_s': 1e3 / ms_epoch, 'ms_per_epoch': ms_epoch, 'kernel_ms': ms_k,
+               'fp32_equivalent_tflops': flops / (ms_k * 1e-3) / 1e12}
+        if mode == 'tc':
+            peak, src = load_tensor_peak()
+            issued = 3 * flops                                         # 3xTF32: three tensor-core products per fp32-accurate one
+            out.update({'n_s': n_s, 'pairs': pairs, 'epochs_per_s': rec['epochs_per_s'], 'ms_per_epoch': ms_epoch,
+                        'roofline': {'kernel': 'gd::tc::dense_ni_tc_kernel (tcgen05.mma kind::tf32, 3xTF32, accumulators in TMEM)',
+                                     'bound': 'tensor', 'achieved': issued / (ms_k * 1e-3) / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
+                                     'frac': issued / (ms_k * 1e-3) / 1e12 / peak, 'peak_source': src,
+                                     'flops_issued_per_launch': issued, 'fp32_equivalent_tflops': rec['fp32_equivalent_tflops'],
+                                     'kernel_ms': ms_k, 'target_bytes_per_launch': n_s * n_s * 4,
+                                     'traffic': (measured_traffic('dense_ni_tc') or (None, None))[0]},
+                        'dtype': 'tf32x3 (fp32-level accuracy, 1e-5 vs the fp64 oracle)'})
+        else:
+            out['cuda_core_fp32_kernel'] = rec
+        del eng, g
+        G._GLOBAL_CACHE = G.PlanCache()
+        torch.cuda.empty_cache()
+    os.environ.pop('GD_DENSE_NI', None)
+    return out
+
+
 def timed_epochs(eng, steps, world):
     """K epochs between barrier+sync brackets, CUDA events on the launch stream; ms total."""
     st = torch.cuda.current_stream()
@@ -822,6 +897,13 @@ def main():
             del e16
         except Exception as exc:                       # the opt-in mode must never take the headline down
             line['bf16_gather'] = {'error': repr(exc)}
+
+    # ---- config 1 with the reference's dense-block NI loss: the tensor-core contraction of the path (own roofline block)
+    if world == 1 and shape.name == 'collab':
+        try:
+            line['dense_ni'] = run_dense_ni_block(dev, lib, args.steps)
+        except Exception as exc:
+            line['dense_ni'] = {'error': repr(exc)}
 
     if world > 1 and not args.no_partitioned:
         del data, model, z_ori, neg

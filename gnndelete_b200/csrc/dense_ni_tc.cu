@@ -11,6 +11,7 @@
 //            SWIZZLE_128B A operand of the second contraction
 //   MMA2   dZ_I[128 x 64] += C[128 x 64] . Z_J     same instruction shape, accumulated in TMEM over the whole sweep
 // Both contractions keep fp32 accuracy with the 3xTF32 operand split of gemm_tc.cu (main + correction accumulators).
+// The logit tile is double buffered in TMEM: MMA1 of block t + 1 is issued before the epilogue of block t starts.
 // Every operand is K-major (the layout the row GEMM has exercised since round 1): Z_J is staged twice, as [j][d] for
 // MMA1 and transposed as [d][j] for MMA2 (4-byte conflict-free stores, lanes = j).
 //
@@ -20,6 +21,8 @@
 // kernel reads no bitmap.  Every unordered pair is visited from both sides: a CTA writes only its own rows of dz -
 // deterministic, no atomics.  Small S: the J sweep is split over `jsplit` CTAs per row block and a second kernel
 // adds the parts in order.
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace gd {
@@ -28,7 +31,8 @@ namespace tc {
 constexpr int NI_BI = 128;                 // rows of z_S per CTA (UMMA M)
 constexpr int NI_BJ = 64;                  // column block: UMMA N of the logit tile, K of the gradient contraction
 constexpr int NI_D = 64;                   // embedding width (out_dim of the reference's models)
-constexpr int NI_THREADS = 256;
+constexpr int NI_WORKER_WARPS = 16;         // 4 per TMEM lane quarter, 16 logit columns per thread
+constexpr int NI_THREADS = (NI_WORKER_WARPS + 1) * 32;   // + the MMA-issuing warp
 constexpr int NI_TILE = NI_BI * NI_BJ;     // floats of one packed target tile
 // shared-memory map (bytes; every operand tile 1024-aligned; "atom" = 32 k values = one 128-byte swizzle row)
 constexpr int NI_ZI_HI = 0;                        // Z_I   [128 rows i][k = d]   2 atoms x 16 KB
@@ -40,7 +44,8 @@ constexpr int NI_ZT_LO = NI_ZT_HI + 2 * 8192;
 constexpr int NI_C_HI = NI_ZT_LO + 2 * 8192;       // C     [128 rows i][k = j]   2 atoms x 16 KB    A of MMA2
 constexpr int NI_C_LO = NI_C_HI + 2 * 16384;
 constexpr int NI_SMEM = NI_C_LO + 2 * 16384;       // 196608
-constexpr int NI_TMEM_COLS = 256;                  // P main | P corr | dZ main | dZ corr, 64 columns each
+constexpr int NI_TMEM_COLS = 512;                  // P[0] main | corr, P[1] main | corr, dZ main | corr (64 columns each)
+constexpr uint32_t NI_COL_P = 0, NI_COL_DZ = 256;
 
 struct NiArgs {
     const float* zs; int64_t ldz; int64_t n_s;
@@ -51,214 +56,285 @@ struct NiArgs {
     int jsplit;
 };
 
-// sigmoid(p) with two MUFU ops.  ex2.approx is accurate to 2^-22 but the fp32 product p * log2(e) is not (its rounding
-// error grows with |p|), so the product's exact residual and the low part of log2(e) are folded back in.
-__device__ __forceinline__ float sigmoid_mufu(float p) {
-    const float L2E = 1.4426950408889634f;
-    float x = -p * L2E;
-    float err = fmaf(-p, L2E, -x);
-    err = fmaf(-p, 1.925963033500e-8f, err);
-    x = fminf(x, 126.0f);                           // keeps e finite (sigmoid underflows to ~1e-38 there)
-    float e;
+// The coefficient tile is split for the 3xTF32 contraction WITHOUT rounding instructions: kind::tf32 reads the upper 19
+// bits of a 32-bit operand, so the raw fp32 value serves as "hi" (= c truncated to tf32) and lo = c - trunc(c) is exact
+// (<= 13 significant bits, of which the tensor core keeps 11: error 2^-21 relative).  2 ALU operations per element
+// instead of 5 on the kernel's busiest pipe.  NI_TRUNC_SPLIT = false restores the rounded split of gemm_tc.cu.
+constexpr bool NI_TRUNC_SPLIT = true;
+__device__ __forceinline__ void split_coef(float c, float& hi, float& lo) {
+    if (NI_TRUNC_SPLIT) {
+        hi = c;
+        lo = c - __uint_as_float(__float_as_uint(c) & 0xffffe000u);
+    } else {
+        split_tf32(c, hi, lo);
+    }
+}
+
+// The logit tile is computed as P' = (-log2(e) Z_I) . Z_J^T (the factor is folded into the Z_I operand when it is staged),
+// so sigmoid(p) = 1 / (1 + 2^P') costs two MUFU operations and one add (ex2.approx / rcp.approx: 2^-22 relative each).
+// Saturates cleanly: 2^x = inf -> 1 / inf = 0, 2^x = 0 -> 1.
+constexpr float NI_NEG_LOG2E = -1.4426950408889634f;
+__device__ __forceinline__ float sigmoid_from_scaled(float x) {
+    float e, s;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
-    e = fmaf(e, err * 0.6931471805599453f, e);
-    float s;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(1.0f + e));
     return s;
 }
 
+// Software pipeline of one CTA.  Warps 0-15 (workers) stage the operands and run the epilogue; warp 16 issues the MMAs
+// (one elected lane) and prefetches the target tiles into L2.  The issuing warp is separate because the generic->async
+// proxy fence that must precede a tcgen05.mma on freshly written shared memory compiles to MEMBAR.ALL.CTA, which waits
+// for the executing thread's own outstanding global loads - on a worker it exposed the latency of the prefetched target
+// tile and Z_J rows in every block (0.84 ms for the Cora block); warp 16 has no loads in flight.  The tensor pipe
+// executes in issue order:
+//   block t:  workers wait P[t] (also frees the Z_J buffer), stage Z_J(t+1)      | sync A |  warp 16: MMA1(t+1) -> P[(t+1)&1]
+//             workers: TMEM -> coefficients; wait MMA2(t-1); store C(t), Z_J^T(t) | sync B |  warp 16: MMA2(t) -> dZ
 __global__ void __launch_bounds__(NI_THREADS, 1) dense_ni_tc_kernel(const NiArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // by offset: keeps the shared address space
     __shared__ uint64_t bar_p, bar_d;
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float red[NI_THREADS / 32];
+    __shared__ float red[NI_WORKER_WARPS];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ib = blockIdx.x / a.jsplit, split = blockIdx.x - ib * a.jsplit;
     const int per = (a.n_jb + a.jsplit - 1) / a.jsplit;
     const int jb0 = split * per, jb1 = min(a.n_jb, jb0 + per);
+    const int T = max(jb1 - jb0, 0);
+    const bool worker = warp < NI_WORKER_WARPS;
+    const float* tile0 = a.packed + ((int64_t)ib * a.n_jb + jb0) * NI_TILE;       // this CTA's target tiles are contiguous
 
     if (tid == 0) {
         mbar_init(&bar_p, 1);
         mbar_init(&bar_d, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (!worker) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
                      "r"(NI_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    // ---- Z_I once: thread = (row r = 32 (warp % 4) + lane, atom = warp / 4): 128 contiguous bytes of its row
-    {
-        const int r = (warp & 3) * 32 + lane, atom = warp >> 2;
-        const int64_t gi = (int64_t)ib * NI_BI + r;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gi < a.n_s) v = __ldg(reinterpret_cast<const float4*>(a.zs + gi * a.ldz + atom * 32) + c);
-            float4 hi, lo;
-            split4(v, hi, lo);
-            const uint32_t o = atom * 16384 + swz(r, c);
-            *reinterpret_cast<float4*>(smem + NI_ZI_HI + o) = hi;
-            *reinterpret_cast<float4*>(smem + NI_ZI_LO + o) = lo;
-        }
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_base_smem;
-
-    // Z_J staging role: thread = (row j = 32 (warp % 2) + lane, 64 bytes = chunks 4 (warp / 2) .. + 3 of the row)
-    const int sj = (warp & 1) * 32 + lane, sc0 = (warp >> 1) * 4;
-    float4 zj[4];
-    auto load_zj = [&](int jb) {
+    // Z_J staging role: thread = (row j = 32 (warp % 2) + lane, 32 bytes = chunks 2 (warp / 2), + 1 of the row)
+    const int sj = (warp & 1) * 32 + lane, sc0 = ((warp >> 1) & 7) * 2;
+    auto load_zj = [&](int jb, float4 (&z)[2]) {
         const int64_t gj = (int64_t)jb * NI_BJ + sj;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            zj[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (jb < jb1 && gj < a.n_s) zj[e] = __ldg(reinterpret_cast<const float4*>(a.zs + gj * a.ldz) + sc0 + e);
+        for (int e = 0; e < 2; ++e) {
+            z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (jb < jb1 && gj < a.n_s) z[e] = __ldg(reinterpret_cast<const float4*>(a.zs + gj * a.ldz) + sc0 + e);
         }
     };
-    // epilogue role: thread = (row i = 32 (warp % 4) + lane, columns 32 (warp / 4) .. + 31 = atom warp / 4 of the C tile)
-    const int q = warp & 3, h = warp >> 2;
-    const int ei = q * 32 + lane;
-    const int64_t gi = (int64_t)ib * NI_BI + ei;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t idesc = make_idesc(NI_BJ);
-    float loss = 0.f;
-
-    load_zj(jb0);
-    int t = 0;
-    for (int jb = jb0; jb < jb1; ++jb, ++t) {
-        // ---- (1) the previous block's second contraction has read Z_J^T and C
-        if (t > 0) mbar_wait(&bar_d, (uint32_t)((t - 1) & 1));
-        // ---- (2) stage Z_J: K-major [j][d] (128-bit stores) and transposed [d][j] (32-bit stores, lanes = j)
+    auto stage_k = [&](const float4 (&z)[2]) {                       // K-major [j][d]: operand B of the logit tile
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < 2; ++e) {
             float4 hi, lo;
-            split4(zj[e], hi, lo);
-            const int c = sc0 + e;                                    // 16-byte chunk of the row: atom c / 8, chunk c % 8
+            split4(z[e], hi, lo);
+            const int c = sc0 + e;
             const uint32_t o = (c >> 3) * 8192 + swz(sj, c & 7);
             *reinterpret_cast<float4*>(smem + NI_ZJ_HI + o) = hi;
             *reinterpret_cast<float4*>(smem + NI_ZJ_LO + o) = lo;
+        }
+    };
+    const uint32_t zt_base = (sj >> 5) * 8192 + ((sj & 3) << 2);     // transposed tile: k = j -> atom sj / 32, word sj % 32 of row d
+    const uint32_t zt_chunk = (sj & 31) >> 2;
+    auto stage_t = [&](const float4 (&z)[2]) {                       // transposed [d][j]: operand B of the gradient contraction
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            float4 hi, lo;
+            split4(z[e], hi, lo);
             const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int d = 4 * c + u;                              // row of the transposed tile; k = j: atom sj / 32, word sj % 32
-                const uint32_t ot = (sj >> 5) * 8192 + d * 128 + ((((sj & 31) >> 2) ^ (d & 7)) << 4) + ((sj & 3) << 2);
+                const int d = 4 * (sc0 + e) + u;                      // d & 7 == 4 e + u (sc0 is even)
+                const uint32_t ot = zt_base + d * 128 + ((zt_chunk ^ (uint32_t)(4 * e + u)) << 4);
                 *reinterpret_cast<float*>(smem + NI_ZT_HI + ot) = hv[u];
                 *reinterpret_cast<float*>(smem + NI_ZT_LO + ot) = lv[u];
             }
         }
-        fence_proxy_async();
-        __syncthreads();
-        // ---- (3) logit tile
-        if (warp == 0 && elect_one()) {
+    };
+
+    float4 zc[2], zn[2];
+    if (worker) {
+        // ---- Z_I once, scaled by -log2(e): thread = (row r = 32 (warp % 4) + lane, 64 bytes = chunks 4 (warp / 4) .. + 3 of the row)
+        const int r = (warp & 3) * 32 + lane, c0 = (warp >> 2) * 4;
+        const int64_t gr = (int64_t)ib * NI_BI + r;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = c0 + e;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gr < a.n_s) v = __ldg(reinterpret_cast<const float4*>(a.zs + gr * a.ldz) + c);
+            v.x *= NI_NEG_LOG2E; v.y *= NI_NEG_LOG2E; v.z *= NI_NEG_LOG2E; v.w *= NI_NEG_LOG2E;
+            float4 hi, lo;
+            split4(v, hi, lo);
+            const uint32_t o = (c >> 3) * 16384 + swz(r, c & 7);
+            *reinterpret_cast<float4*>(smem + NI_ZI_HI + o) = hi;
+            *reinterpret_cast<float4*>(smem + NI_ZI_LO + o) = lo;
+        }
+        load_zj(jb0, zc);
+        if (T > 0) stage_k(zc);
+    }
+    tc_fence_before();
+    __syncthreads();                                                  // sync 0: Z_I, Z_J(0), barriers, TMEM address
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (!worker) {
+        // ================================ MMA issuer (warp 16) ================================
+        // The whole warp takes part in the named barriers (bar.sync is warp-aligned); elect.sync picks the same lane
+        // every time, so all MMAs and commits come from one thread.
+        const uint32_t idesc = make_idesc(NI_BJ);                     // both contractions: M = 128, N = 64
+        const uint64_t zi_hi = make_desc(smem_u32(smem + NI_ZI_HI)), zi_lo = make_desc(smem_u32(smem + NI_ZI_LO));
+        const uint64_t zj_hi = make_desc(smem_u32(smem + NI_ZJ_HI)), zj_lo = make_desc(smem_u32(smem + NI_ZJ_LO));
+        const uint64_t c_hi = make_desc(smem_u32(smem + NI_C_HI)), c_lo = make_desc(smem_u32(smem + NI_C_LO));
+        const uint64_t zt_hi = make_desc(smem_u32(smem + NI_ZT_HI)), zt_lo = make_desc(smem_u32(smem + NI_ZT_LO));
+        auto contract = [&](uint32_t d_main, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, bool fresh) {
+            const uint32_t d_corr = d_main + 64;                      // 3xTF32: main + correction accumulator
+            fence_proxy_async();                                      // the workers' generic stores -> async proxy
             tc_fence_after();
-            const uint64_t a_hi = make_desc(smem_u32(smem + NI_ZI_HI)), a_lo = make_desc(smem_u32(smem + NI_ZI_LO));
-            const uint64_t b_hi = make_desc(smem_u32(smem + NI_ZJ_HI)), b_lo = make_desc(smem_u32(smem + NI_ZJ_LO));
-            const uint32_t dP = tmem_base, dPc = tmem_base + 64;
 #pragma unroll
             for (int s = 0; s < 8; ++s) {                             // k-step: atom s / 4, 32 bytes per step inside it
                 const uint32_t ao = (s >> 2) * (16384 >> 4) + (s & 3) * 2, bo = (s >> 2) * (8192 >> 4) + (s & 3) * 2;
-                umma_tf32(dPc, a_lo + ao, b_hi + bo, idesc, s != 0);
-                umma_tf32(dPc, a_hi + ao, b_lo + bo, idesc, 1);
-                umma_tf32(dP, a_hi + ao, b_hi + bo, idesc, s != 0);
+                const uint32_t accum = !(fresh && s == 0);
+                umma_tf32(d_corr, a_lo + ao, b_hi + bo, idesc, accum);
+                umma_tf32(d_corr, a_hi + ao, b_lo + bo, idesc, 1);
+                umma_tf32(d_main, a_hi + ao, b_hi + bo, idesc, accum);
             }
-            umma_commit(&bar_p);
+        };
+        auto l2_prefetch_tile = [&](int t) {                          // whole 32 KB target tile of block t -> L2
+            if (t < T) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(tile0 + (int64_t)t * NI_TILE), "r"(NI_TILE * 4) : "memory");
+        };
+        if (elect_one()) {
+            if (T > 0) {
+                contract(tmem_base + NI_COL_P, zi_hi, zi_lo, zj_hi, zj_lo, true);
+                umma_commit(&bar_p);
+            }
+            l2_prefetch_tile(1);
+            l2_prefetch_tile(2);
         }
         __syncwarp();
-        // ---- (4) while the tensor core works: this block's target chunks and the next block's rows
-        const float4* tg_tile = reinterpret_cast<const float4*>(a.packed + ((int64_t)ib * a.n_jb + jb) * NI_TILE);
-        float4 tg[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) tg[c] = __ldg(tg_tile + (8 * h + c) * NI_BI + ei);
-        load_zj(jb + 1);
-        // ---- (5) epilogue: logits -> coefficients
-        mbar_wait(&bar_p, (uint32_t)(t & 1));
-        tc_fence_after();
-        uint32_t pm[32], pc[32];
-        tmem_ld32_nowait(t_lane + 32 * h, pm);
-        tmem_ld32_nowait(t_lane + 64 + 32 * h, pc);
-        tmem_wait_ld();
-        const int64_t gj0 = (int64_t)jb * NI_BJ + 32 * h;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float tv[4] = {tg[c].x, tg[c].y, tg[c].z, tg[c].w};
-            float cv[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float p = __uint_as_float(pm[4 * c + u]) + __uint_as_float(pc[4 * c + u]);
-                const float s = sigmoid_mufu(p);
-                const float r = s - tv[u];
-                const bool on = tv[u] >= 0.f;
-                cv[u] = on ? a.scale2 * r * s * (1.0f - s) : 0.f;
-                if (on && gi > gj0 + 4 * c + u) loss = fmaf(r, r, loss);
+        for (int t = 0; t < T; ++t) {
+            asm volatile("bar.sync 1, %0;" ::"r"(NI_THREADS) : "memory");              // sync A(t): Z_J(t+1) staged, P[(t+1)&1] drained
+            if (elect_one()) {
+                if (t + 1 < T) {
+                    contract(tmem_base + NI_COL_P + 128 * ((t + 1) & 1), zi_hi, zi_lo, zj_hi, zj_lo, true);
+                    umma_commit(&bar_p);
+                }
+                l2_prefetch_tile(t + 3);
             }
-            float4 hi, lo;
-            split4(make_float4(cv[0], cv[1], cv[2], cv[3]), hi, lo);
-            const uint32_t o = h * 16384 + swz(ei, c);
-            *reinterpret_cast<float4*>(smem + NI_C_HI + o) = hi;
-            *reinterpret_cast<float4*>(smem + NI_C_LO + o) = lo;
+            __syncwarp();
+            asm volatile("bar.sync 2, %0;" ::"r"(NI_THREADS) : "memory");              // sync B(t): C(t), Z_J^T(t) stored
+            if (elect_one()) {
+                contract(tmem_base + NI_COL_DZ, c_hi, c_lo, zt_hi, zt_lo, t == 0);
+                umma_commit(&bar_d);
+            }
+            __syncwarp();
         }
-        tc_fence_before();
-        fence_proxy_async();
-        __syncthreads();
-        // ---- (6) gradient contraction, accumulated over the sweep
-        if (warp == 0 && elect_one()) {
+    } else {
+        // ================================ workers (warps 0-15) ================================
+        load_zj(jb0 + 1, zn);
+        // epilogue role: thread = (row i = 32 (warp % 4) + lane, logit columns 16 (warp / 4) .. + 15)
+        const int q = warp & 3, cg = warp >> 2;
+        const int ei = q * 32 + lane;
+        const int64_t gi = (int64_t)ib * NI_BI + ei;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t c_off = (cg >> 1) * 16384;                     // atom of the C tile; chunks 4 (cg & 1) .. + 3 inside it
+        float loss = 0.f;
+
+        for (int t = 0; t < T; ++t) {
+            const int jb = jb0 + t;
+            // this block's target chunks (L2 hits: the tile was prefetched three blocks ago)
+            const float4* tg_tile = reinterpret_cast<const float4*>(tile0 + (int64_t)t * NI_TILE);
+            float4 tg[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tg[c] = __ldg(tg_tile + (4 * cg + c) * NI_BI + ei);
+            // ---- logit tile of block t complete (the tensor pipe is in order: so is everything issued before it)
+            mbar_wait(&bar_p, (uint32_t)(t & 1));
             tc_fence_after();
-            const uint64_t a_hi = make_desc(smem_u32(smem + NI_C_HI)), a_lo = make_desc(smem_u32(smem + NI_C_LO));
-            const uint64_t b_hi = make_desc(smem_u32(smem + NI_ZT_HI)), b_lo = make_desc(smem_u32(smem + NI_ZT_LO));
-            const uint32_t dD = tmem_base + 128, dDc = tmem_base + 192;
+            // ---- next block's Z_J; its logit tile runs under this block's epilogue
+            if (t + 1 < T) stage_k(zn);
+            asm volatile("bar.sync 1, %0;" ::"r"(NI_THREADS) : "memory");              // sync A(t)
+            // ---- epilogue: logits -> coefficients (registers)
+            uint32_t pm[16], pc[16];
+            const uint32_t tP = t_lane + NI_COL_P + 128 * (t & 1) + 16 * cg;
+            tmem_ld16_nowait(tP, pm);
+            tmem_ld16_nowait(tP + 64, pc);
+            tmem_wait_ld();
+            // pairs of this tile that count towards the loss (i > j): all of them, none, or (2 of the sweep's blocks) a band
+            const int64_t j_lo = (int64_t)jb * NI_BJ, i_lo = (int64_t)ib * NI_BI;
+            const int tri = (j_lo + NI_BJ - 1 < i_lo) ? 1 : ((j_lo > i_lo + NI_BI - 1) ? 0 : 2);
+            const int lim = (int)max((int64_t)-1, min((int64_t)NI_BJ, gi - (j_lo + 16 * cg)));   // element k of my 16 counts iff lim > k
+            float cv[16];
+            float sq = 0.f;
+            auto coefficients = [&](auto band) {
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                const uint32_t ao = (s >> 2) * (16384 >> 4) + (s & 3) * 2, bo = (s >> 2) * (8192 >> 4) + (s & 3) * 2;
-                const uint32_t accum = (t != 0) || (s != 0);
-                umma_tf32(dDc, a_lo + ao, b_hi + bo, idesc, accum);
-                umma_tf32(dDc, a_hi + ao, b_lo + bo, idesc, 1);
-                umma_tf32(dD, a_hi + ao, b_hi + bo, idesc, accum);
+                for (int c = 0; c < 4; ++c) {
+                    const float tv[4] = {tg[c].x, tg[c].y, tg[c].z, tg[c].w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float s = sigmoid_from_scaled(__uint_as_float(pm[4 * c + u]) + __uint_as_float(pc[4 * c + u]));
+                        const float r = tv[u] >= 0.f ? s - tv[u] : 0.f;              // sentinel -1: pair not in M
+                        cv[4 * c + u] = r * fmaf(-s, s, s);                          // (s - t) s (1 - s); 2 w / |M| is applied to dz at the end
+                        if (!decltype(band)::value || lim > 4 * c + u) sq = fmaf(r, r, sq);
+                    }
+                }
+            };
+            if (tri == 2) coefficients(std::true_type{}); else coefficients(std::false_type{});
+            if (tri != 0) loss += sq;
+            // ---- the previous gradient contraction has read C and Z_J^T
+            if (t > 0) mbar_wait(&bar_d, (uint32_t)((t - 1) & 1));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float4 hi, lo;
+                split_coef(cv[4 * c], hi.x, lo.x); split_coef(cv[4 * c + 1], hi.y, lo.y);
+                split_coef(cv[4 * c + 2], hi.z, lo.z); split_coef(cv[4 * c + 3], hi.w, lo.w);
+                const uint32_t o = c_off + swz(ei, (cg & 1) * 4 + c);
+                *reinterpret_cast<float4*>(smem + NI_C_HI + o) = hi;
+                *reinterpret_cast<float4*>(smem + NI_C_LO + o) = lo;
             }
-            umma_commit(&bar_d);
+            stage_t(zc);
+            tc_fence_before();
+            asm volatile("bar.sync 2, %0;" ::"r"(NI_THREADS) : "memory");              // sync B(t)
+            zc[0] = zn[0]; zc[1] = zn[1];
+            load_zj(jb + 2, zn);
         }
-        __syncwarp();
-    }
-    // ---- rows of dz owned by this CTA
-    {
-        float* orow = a.jsplit == 1 ? a.dz_out + gi * a.lddz + 32 * h
-                                    : a.dz_out + (((int64_t)split * a.n_ib + ib) * NI_BI + ei) * NI_D + 32 * h;
+        // ---- rows of dz owned by this CTA: thread = (row i, 16 embedding columns), scaled by 2 w / |M|
+        float* orow = a.jsplit == 1 ? a.dz_out + gi * a.lddz + 16 * cg
+                                    : a.dz_out + (((int64_t)split * a.n_ib + ib) * NI_BI + ei) * NI_D + 16 * cg;
         const bool row_ok = a.jsplit == 1 ? gi < a.n_s : true;
-        uint32_t dm[32], dc[32];
-        if (t > 0) {
-            mbar_wait(&bar_d, (uint32_t)((t - 1) & 1));
+        uint32_t dm[16], dc[16];
+        if (T > 0) {
+            mbar_wait(&bar_d, (uint32_t)((T - 1) & 1));
             tc_fence_after();
-            tmem_ld32_nowait(t_lane + 128 + 32 * h, dm);
-            tmem_ld32_nowait(t_lane + 192 + 32 * h, dc);
+            tmem_ld16_nowait(t_lane + NI_COL_DZ + 16 * cg, dm);
+            tmem_ld16_nowait(t_lane + NI_COL_DZ + 64 + 16 * cg, dc);
             tmem_wait_ld();
         } else {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) { dm[e] = 0; dc[e] = 0; }
+            for (int e = 0; e < 16; ++e) { dm[e] = 0; dc[e] = 0; }
         }
         if (row_ok) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                reinterpret_cast<float4*>(orow)[c] =
-                    make_float4(__uint_as_float(dm[4 * c]) + __uint_as_float(dc[4 * c]), __uint_as_float(dm[4 * c + 1]) + __uint_as_float(dc[4 * c + 1]),
-                                __uint_as_float(dm[4 * c + 2]) + __uint_as_float(dc[4 * c + 2]), __uint_as_float(dm[4 * c + 3]) + __uint_as_float(dc[4 * c + 3]));
+            for (int c = 0; c < 4; ++c) {
+                float4 o;
+                o.x = a.scale2 * (__uint_as_float(dm[4 * c]) + __uint_as_float(dc[4 * c]));
+                o.y = a.scale2 * (__uint_as_float(dm[4 * c + 1]) + __uint_as_float(dc[4 * c + 1]));
+                o.z = a.scale2 * (__uint_as_float(dm[4 * c + 2]) + __uint_as_float(dc[4 * c + 2]));
+                o.w = a.scale2 * (__uint_as_float(dm[4 * c + 3]) + __uint_as_float(dc[4 * c + 3]));
+                reinterpret_cast<float4*>(orow)[c] = o;
+            }
         }
+        // ---- deterministic block reduction of the loss
+        loss = warp_sum(loss);
+        if (lane == 0) red[warp] = loss;
     }
-    // ---- deterministic block reduction of the loss
-    loss = warp_sum(loss);
-    if (lane == 0) red[warp] = loss;
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
         float s = 0.f;
-        for (int w = 0; w < NI_THREADS / 32; ++w) s += red[w];
+        for (int w = 0; w < NI_WORKER_WARPS; ++w) s += red[w];
         a.partial[blockIdx.x] = s;
     }
-    if (warp == 0) {
+    if (!worker) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NI_TMEM_COLS));
     }
