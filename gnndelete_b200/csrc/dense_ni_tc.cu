@@ -21,6 +21,8 @@
 // kernel reads no bitmap.  Every unordered pair is visited from both sides: a CTA writes only its own rows of dz -
 // deterministic, no atomics.  Small S: the J sweep is split over `jsplit` CTAs per row block and a second kernel
 // adds the parts in order.
+#include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "tc_common.cuh"
@@ -39,11 +41,12 @@ constexpr int NI_ZI_HI = 0;                        // Z_I   [128 rows i][k = d] 
 constexpr int NI_ZI_LO = NI_ZI_HI + 2 * 16384;
 constexpr int NI_ZJ_HI = NI_ZI_LO + 2 * 16384;     // Z_J   [64 rows j][k = d]    2 atoms x 8 KB     B of MMA1
 constexpr int NI_ZJ_LO = NI_ZJ_HI + 2 * 8192;
-constexpr int NI_ZT_HI = NI_ZJ_LO + 2 * 8192;      // Z_J^T [64 rows d][k = j]    2 atoms x 8 KB     B of MMA2
-constexpr int NI_ZT_LO = NI_ZT_HI + 2 * 8192;
-constexpr int NI_C_HI = NI_ZT_LO + 2 * 8192;       // C     [128 rows i][k = j]   2 atoms x 16 KB    A of MMA2
+constexpr int NI_ZT = NI_ZJ_LO + 2 * 8192;         // Z_J^T [64 rows d][k = j]    hi 16 KB | lo 16 KB   B of MMA2 (two buffers when C lives in TMEM)
+constexpr int NI_ZT_BUF = 2 * 16384;
+constexpr int NI_C_HI = NI_ZT + NI_ZT_BUF;         // C     [128 rows i][k = j]   2 atoms x 16 KB    A of MMA2 (shared-memory variant only)
 constexpr int NI_C_LO = NI_C_HI + 2 * 16384;
-constexpr int NI_SMEM = NI_C_LO + 2 * 16384;       // 196608
+constexpr int NI_SMEM = NI_C_LO + 2 * 16384;       // 196608 (C in shared memory);  163840 with C in TMEM (second Z_J^T buffer instead)
+constexpr int NI_SMEM_CT = NI_ZT + 2 * NI_ZT_BUF;
 constexpr int NI_TMEM_COLS = 512;                  // P[0] main | corr, P[1] main | corr, dZ main | corr (64 columns each)
 constexpr uint32_t NI_COL_P = 0, NI_COL_DZ = 256;
 
@@ -89,10 +92,17 @@ __device__ __forceinline__ float sigmoid_from_scaled(float x) {
 // executes in issue order:
 //   block t:  workers wait P[t] (also frees the Z_J buffer), stage Z_J(t+1)      | sync A |  warp 16: MMA1(t+1) -> P[(t+1)&1]
 //             workers: TMEM -> coefficients; wait MMA2(t-1); store C(t), Z_J^T(t) | sync B |  warp 16: MMA2(t) -> dZ
+//
+// CT = true (default): the coefficient tile never touches shared memory.  The epilogue writes C (hi = the raw fp32 value,
+// lo = c - trunc(c)) with tcgen05.st IN PLACE over the logit tile it has just read (P main -> C hi, P corr -> C lo) and the
+// gradient contraction takes its A operand from tensor memory.  That removes the 64 KB of C stores and the 96 KB of
+// A-operand reads per block from the shared-memory data pipe (the kernel's busiest unit, profiles/r2_dense_ni_tc_ncu_full.md),
+// and with it the wait on the previous contraction: Z_J^T is double buffered in the space the C tile occupied.
+template <bool CT>
 __global__ void __launch_bounds__(NI_THREADS, 1) dense_ni_tc_kernel(const NiArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // by offset: keeps the shared address space
-    __shared__ uint64_t bar_p, bar_d;
+    __shared__ uint64_t bar_p, bar_d, bar_end;
     __shared__ uint32_t tmem_base_smem;
     __shared__ float red[NI_WORKER_WARPS];
 
@@ -107,6 +117,7 @@ __global__ void __launch_bounds__(NI_THREADS, 1) dense_ni_tc_kernel(const NiArgs
     if (tid == 0) {
         mbar_init(&bar_p, 1);
         mbar_init(&bar_d, 1);
+        mbar_init(&bar_end, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (!worker) {
@@ -137,7 +148,7 @@ __global__ void __launch_bounds__(NI_THREADS, 1) dense_ni_tc_kernel(const NiArgs
     };
     const uint32_t zt_base = (sj >> 5) * 8192 + ((sj & 3) << 2);     // transposed tile: k = j -> atom sj / 32, word sj % 32 of row d
     const uint32_t zt_chunk = (sj & 31) >> 2;
-    auto stage_t = [&](const float4 (&z)[2]) {                       // transposed [d][j]: operand B of the gradient contraction
+    auto stage_t = [&](const float4 (&z)[2], int buf) {              // transposed [d][j]: operand B of the gradient contraction
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             float4 hi, lo;
@@ -147,8 +158,8 @@ __global__ void __launch_bounds__(NI_THREADS, 1) dense_ni_tc_kernel(const NiArgs
             for (int u = 0; u < 4; ++u) {
                 const int d = 4 * (sc0 + e) + u;                      // d & 7 == 4 e + u (sc0 is even)
                 const uint32_t ot = zt_base + d * 128 + ((zt_chunk ^ (uint32_t)(4 * e + u)) << 4);
-                *reinterpret_cast<float*>(smem + NI_ZT_HI + ot) = hv[u];
-                *reinterpret_cast<float*>(smem + NI_ZT_LO + ot) = lv[u];
+                *reinterpret_cast<float*>(smem + NI_ZT + buf * NI_ZT_BUF + ot) = hv[u];
+                *reinterpret_cast<float*>(smem + NI_ZT + buf * NI_ZT_BUF + 16384 + ot) = lv[u];
             }
         }
     };
@@ -186,7 +197,7 @@ __global__ void __launch_bounds__(NI_THREADS, 1) dense_ni_tc_kernel(const NiArgs
         const uint64_t zi_hi = make_desc(smem_u32(smem + NI_ZI_HI)), zi_lo = make_desc(smem_u32(smem + NI_ZI_LO));
         const uint64_t zj_hi = make_desc(smem_u32(smem + NI_ZJ_HI)), zj_lo = make_desc(smem_u32(smem + NI_ZJ_LO));
         const uint64_t c_hi = make_desc(smem_u32(smem + NI_C_HI)), c_lo = make_desc(smem_u32(smem + NI_C_LO));
-        const uint64_t zt_hi = make_desc(smem_u32(smem + NI_ZT_HI)), zt_lo = make_desc(smem_u32(smem + NI_ZT_LO));
+        const uint64_t zt_hi = make_desc(smem_u32(smem + NI_ZT)), zt_lo = make_desc(smem_u32(smem + NI_ZT + 16384));
         auto contract = [&](uint32_t d_main, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, bool fresh) {
             const uint32_t d_corr = d_main + 64;                      // 3xTF32: main + correction accumulator
             fence_proxy_async();                                      // the workers' generic stores -> async proxy
@@ -198,6 +209,19 @@ __global__ void __launch_bounds__(NI_THREADS, 1) dense_ni_tc_kernel(const NiArgs
                 umma_tf32(d_corr, a_lo + ao, b_hi + bo, idesc, accum);
                 umma_tf32(d_corr, a_hi + ao, b_lo + bo, idesc, 1);
                 umma_tf32(d_main, a_hi + ao, b_hi + bo, idesc, accum);
+            }
+        };
+        auto contract_tmem_a = [&](uint32_t d_main, uint32_t a_main, uint64_t b_hi, uint64_t b_lo, bool fresh) {
+            const uint32_t d_corr = d_main + 64, a_corr = a_main + 64;  // A = C in tensor memory: hi over P main, lo over P corr
+            fence_proxy_async();
+            tc_fence_after();
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {                             // k-step: 8 columns of A, atom s / 4 (+ 32 bytes per step) of B
+                const uint32_t bo = (s >> 2) * (8192 >> 4) + (s & 3) * 2;
+                const uint32_t accum = !(fresh && s == 0);
+                umma_tf32_tmem_a(d_corr, a_corr + 8 * s, b_hi + bo, idesc, accum);
+                umma_tf32_tmem_a(d_corr, a_main + 8 * s, b_lo + bo, idesc, 1);
+                umma_tf32_tmem_a(d_main, a_main + 8 * s, b_hi + bo, idesc, accum);
             }
         };
         auto l2_prefetch_tile = [&](int t) {                          // whole 32 KB target tile of block t -> L2
@@ -224,8 +248,14 @@ __global__ void __launch_bounds__(NI_THREADS, 1) dense_ni_tc_kernel(const NiArgs
             __syncwarp();
             asm volatile("bar.sync 2, %0;" ::"r"(NI_THREADS) : "memory");              // sync B(t): C(t), Z_J^T(t) stored
             if (elect_one()) {
-                contract(tmem_base + NI_COL_DZ, c_hi, c_lo, zt_hi, zt_lo, t == 0);
-                umma_commit(&bar_d);
+                if (CT) {
+                    const uint32_t zo = (t & 1) * (NI_ZT_BUF >> 4);
+                    contract_tmem_a(tmem_base + NI_COL_DZ, tmem_base + NI_COL_P + 128 * (t & 1), zt_hi + zo, zt_lo + zo, t == 0);
+                } else {
+                    contract(tmem_base + NI_COL_DZ, c_hi, c_lo, zt_hi, zt_lo, t == 0);
+                    umma_commit(&bar_d);
+                }
+                if (t == T - 1) umma_commit(&bar_end);
             }
             __syncwarp();
         }
@@ -280,18 +310,34 @@ __global__ void __launch_bounds__(NI_THREADS, 1) dense_ni_tc_kernel(const NiArgs
             };
             if (tri == 2) coefficients(std::true_type{}); else coefficients(std::false_type{});
             if (tri != 0) loss += sq;
-            // ---- the previous gradient contraction has read C and Z_J^T
-            if (t > 0) mbar_wait(&bar_d, (uint32_t)((t - 1) & 1));
+            if (CT) {
+                // ---- C in place over the logit tile (tensor memory); Z_J^T into the buffer MMA2(t-2) has released
+                //      (it was issued before MMA1(t), whose completion this iteration has already awaited)
+                uint32_t ch[16], cl[16];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float4 hi, lo;
-                split_coef(cv[4 * c], hi.x, lo.x); split_coef(cv[4 * c + 1], hi.y, lo.y);
-                split_coef(cv[4 * c + 2], hi.z, lo.z); split_coef(cv[4 * c + 3], hi.w, lo.w);
-                const uint32_t o = c_off + swz(ei, (cg & 1) * 4 + c);
-                *reinterpret_cast<float4*>(smem + NI_C_HI + o) = hi;
-                *reinterpret_cast<float4*>(smem + NI_C_LO + o) = lo;
+                for (int k = 0; k < 16; ++k) {
+                    float hi, lo;
+                    split_coef(cv[k], hi, lo);
+                    ch[k] = __float_as_uint(hi); cl[k] = __float_as_uint(lo);
+                }
+                tmem_st16(tP, ch);
+                tmem_st16(tP + 64, cl);
+                stage_t(zc, t & 1);
+                tmem_wait_st();
+            } else {
+                // ---- the previous gradient contraction has read C and Z_J^T
+                if (t > 0) mbar_wait(&bar_d, (uint32_t)((t - 1) & 1));
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float4 hi, lo;
+                    split_coef(cv[4 * c], hi.x, lo.x); split_coef(cv[4 * c + 1], hi.y, lo.y);
+                    split_coef(cv[4 * c + 2], hi.z, lo.z); split_coef(cv[4 * c + 3], hi.w, lo.w);
+                    const uint32_t o = c_off + swz(ei, (cg & 1) * 4 + c);
+                    *reinterpret_cast<float4*>(smem + NI_C_HI + o) = hi;
+                    *reinterpret_cast<float4*>(smem + NI_C_LO + o) = lo;
+                }
+                stage_t(zc, 0);
             }
-            stage_t(zc);
             tc_fence_before();
             asm volatile("bar.sync 2, %0;" ::"r"(NI_THREADS) : "memory");              // sync B(t)
             zc[0] = zn[0]; zc[1] = zn[1];
@@ -303,7 +349,7 @@ __global__ void __launch_bounds__(NI_THREADS, 1) dense_ni_tc_kernel(const NiArgs
         const bool row_ok = a.jsplit == 1 ? gi < a.n_s : true;
         uint32_t dm[16], dc[16];
         if (T > 0) {
-            mbar_wait(&bar_d, (uint32_t)((T - 1) & 1));
+            mbar_wait(&bar_end, 0);
             tc_fence_after();
             tmem_ld16_nowait(t_lane + NI_COL_DZ + 16 * cg, dm);
             tmem_ld16_nowait(t_lane + NI_COL_DZ + 64 + 16 * cg, dc);
@@ -438,10 +484,19 @@ extern "C" int gd_dense_ni_tc_fwd_bwd(const float* zs, int64_t ldz, int64_t n_s,
     float* partial = static_cast<float*>(workspace);
     float* parts = js > 1 ? reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + align_up((size_t)(n_ib * js + 1) * sizeof(float))) : nullptr;
     tc::NiArgs a{zs, ldz, n_s, packed_target, (int)n_ib, (int)n_jb, 2.0f * coef_scale, js > 1 ? parts : dzs, lddz, partial, js};
-    const size_t smem = tc::NI_SMEM + 1024;
-    GD_CUDA(cudaFuncSetAttribute(tc::dense_ni_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // GD_DENSE_NI_C=smem keeps the coefficient tile in shared memory (the first version of the kernel; A/B and fallback)
+    const char* cenv = getenv("GD_DENSE_NI_C");
+    const bool c_in_tmem = !(cenv && strcmp(cenv, "smem") == 0);
     const int grid = (int)(n_ib * js);
-    tc::dense_ni_tc_kernel<<<grid, tc::NI_THREADS, smem, stream>>>(a);
+    if (c_in_tmem) {
+        const size_t smem = tc::NI_SMEM_CT + 1024;
+        GD_CUDA(cudaFuncSetAttribute(tc::dense_ni_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::dense_ni_tc_kernel<true><<<grid, tc::NI_THREADS, smem, stream>>>(a);
+    } else {
+        const size_t smem = tc::NI_SMEM + 1024;
+        GD_CUDA(cudaFuncSetAttribute(tc::dense_ni_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::dense_ni_tc_kernel<false><<<grid, tc::NI_THREADS, smem, stream>>>(a);
+    }
     GD_LAUNCH_CHECK();
     const int fblocks = js > 1 ? (int)std::min<int64_t>(ceil_div<int64_t>(n_s * (tc::NI_D / 4), 256), kNumSMs * 8) : 1;
     tc::dense_ni_tc_finish_kernel<<<fblocks, 256, 0, stream>>>(partial, grid, loss_sum, parts, js, n_ib * tc::NI_BI, n_s, dzs, lddz);
