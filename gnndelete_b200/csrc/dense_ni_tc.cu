@@ -6,11 +6,11 @@
 //
 // One CTA owns 128 rows I of z_S and sweeps the 64-row column blocks J (flash-attention shaped, nothing N x N is formed):
 //   MMA1   P[128 x 64]   = Z_I . Z_J^T            tcgen05.mma kind::tf32, M = 128, N = 64, K = 64, accumulators in TMEM
-//   epilogue (thread = row i, 32 columns each): tcgen05.ld P, s = sigmoid(P), residual against the packed target tile,
-//            coefficient c = 2 w/|M| (s - t) s (1 - s), loss partial; c is split hi / lo and stored as the K-major
-//            SWIZZLE_128B A operand of the second contraction
-//   MMA2   dZ_I[128 x 64] += C[128 x 64] . Z_J     same instruction shape, accumulated in TMEM over the whole sweep
-// Both contractions keep fp32 accuracy with the 3xTF32 operand split of gemm_tc.cu (main + correction accumulators).
+//   epilogue (thread = row i, 16 columns): tcgen05.ld P, s = sigmoid(P), residual against the packed target tile,
+//            coefficient c = (s - t) s (1 - s), loss partial; c is split hi / lo and written back over P (tcgen05.st)
+//   MMA2   dZ_I[128 x 64] += C[128 x 64] . Z_J     A operand from tensor memory, accumulated in TMEM over the whole sweep
+// Both contractions keep fp32 accuracy with the 3xTF32 operand split of gemm_tc.cu (main + correction accumulators);
+// hi and lo of the B operand sit next to each other along N, so a k-step is two MMAs (N = 128 and N = 64), not three.
 // The logit tile is double buffered in TMEM: MMA1 of block t + 1 is issued before the epilogue of block t starts.
 // Every operand is K-major (the layout the row GEMM has exercised since round 1): Z_J is staged twice, as [j][d] for
 // MMA1 and transposed as [d][j] for MMA2 (4-byte conflict-free stores, lanes = j).
@@ -21,8 +21,6 @@
 // kernel reads no bitmap.  Every unordered pair is visited from both sides: a CTA writes only its own rows of dz -
 // deterministic, no atomics.  Small S: the J sweep is split over `jsplit` CTAs per row block and a second kernel
 // adds the parts in order.
-#include <cstdlib>
-#include <cstring>
 #include <type_traits>
 
 #include "tc_common.cuh"
@@ -39,14 +37,10 @@ constexpr int NI_TILE = NI_BI * NI_BJ;     // floats of one packed target tile
 // shared-memory map (bytes; every operand tile 1024-aligned; "atom" = 32 k values = one 128-byte swizzle row)
 constexpr int NI_ZI_HI = 0;                        // Z_I   [128 rows i][k = d]   2 atoms x 16 KB
 constexpr int NI_ZI_LO = NI_ZI_HI + 2 * 16384;
-constexpr int NI_ZJ_HI = NI_ZI_LO + 2 * 16384;     // Z_J   [64 rows j][k = d]    2 atoms x 8 KB     B of MMA1
-constexpr int NI_ZJ_LO = NI_ZJ_HI + 2 * 8192;
-constexpr int NI_ZT = NI_ZJ_LO + 2 * 8192;         // Z_J^T [64 rows d][k = j]    hi 16 KB | lo 16 KB   B of MMA2 (two buffers when C lives in TMEM)
+constexpr int NI_ZJ_HI = NI_ZI_LO + 2 * 16384;     // Z_J   2 atoms x [64 rows j hi | 64 rows j lo][k = d] (16 KB each)   B of MMA1
+constexpr int NI_ZT = NI_ZJ_HI + 2 * 16384;        // Z_J^T 2 buffers x 2 atoms x [64 rows d hi | 64 rows d lo][k = j]     B of MMA2
 constexpr int NI_ZT_BUF = 2 * 16384;
-constexpr int NI_C_HI = NI_ZT + NI_ZT_BUF;         // C     [128 rows i][k = j]   2 atoms x 16 KB    A of MMA2 (shared-memory variant only)
-constexpr int NI_C_LO = NI_C_HI + 2 * 16384;
-constexpr int NI_SMEM = NI_C_LO + 2 * 16384;       // 196608 (C in shared memory);  163840 with C in TMEM (second Z_J^T buffer instead)
-constexpr int NI_SMEM_CT = NI_ZT + 2 * NI_ZT_BUF;
+constexpr int NI_SMEM = NI_ZT + 2 * NI_ZT_BUF;     // 163840
 constexpr int NI_TMEM_COLS = 512;                  // P[0] main | corr, P[1] main | corr, dZ main | corr (64 columns each)
 constexpr uint32_t NI_COL_P = 0, NI_COL_DZ = 256;
 
@@ -93,16 +87,15 @@ __device__ __forceinline__ float sigmoid_from_scaled(float x) {
 //   block t:  workers wait P[t] (also frees the Z_J buffer), stage Z_J(t+1)      | sync A |  warp 16: MMA1(t+1) -> P[(t+1)&1]
 //             workers: TMEM -> coefficients; wait MMA2(t-1); store C(t), Z_J^T(t) | sync B |  warp 16: MMA2(t) -> dZ
 //
-// CT = true (default): the coefficient tile never touches shared memory.  The epilogue writes C (hi = the raw fp32 value,
-// lo = c - trunc(c)) with tcgen05.st IN PLACE over the logit tile it has just read (P main -> C hi, P corr -> C lo) and the
-// gradient contraction takes its A operand from tensor memory.  That removes the 64 KB of C stores and the 96 KB of
-// A-operand reads per block from the shared-memory data pipe (the kernel's busiest unit, profiles/r2_dense_ni_tc_ncu_full.md),
-// and with it the wait on the previous contraction: Z_J^T is double buffered in the space the C tile occupied.
-template <bool CT>
+// The coefficient tile never touches shared memory: the epilogue writes C (hi = the raw fp32 value, lo = c - trunc(c)) with
+// tcgen05.st IN PLACE over the logit tile it has just read (P main -> C hi, P corr -> C lo) and the gradient contraction
+// takes its A operand from tensor memory.  Against a C tile in shared memory (the first version, 0.80 ms) that removes
+// 64 KB of stores and 96 KB of A-operand reads per block from the shared-memory data pipe - the kernel's busiest unit,
+// profiles/r2_dense_ni_tc_ncu_full.md - and the wait on the previous contraction: Z_J^T is double buffered instead.
 __global__ void __launch_bounds__(NI_THREADS, 1) dense_ni_tc_kernel(const NiArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // by offset: keeps the shared address space
-    __shared__ uint64_t bar_p, bar_d, bar_end;
+    __shared__ uint64_t bar_p, bar_end;
     __shared__ uint32_t tmem_base_smem;
     __shared__ float red[NI_WORKER_WARPS];
 
@@ -116,7 +109,6 @@ __global__ void __launch_bounds__(NI_THREADS, 1) dense_ni_tc_kernel(const NiArgs
 
     if (tid == 0) {
         mbar_init(&bar_p, 1);
-        mbar_init(&bar_d, 1);
         mbar_init(&bar_end, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -141,12 +133,12 @@ __global__ void __launch_bounds__(NI_THREADS, 1) dense_ni_tc_kernel(const NiArgs
             float4 hi, lo;
             split4(z[e], hi, lo);
             const int c = sc0 + e;
-            const uint32_t o = (c >> 3) * 8192 + swz(sj, c & 7);
+            const uint32_t o = (c >> 3) * 16384 + swz(sj, c & 7);     // atom: [64 rows hi | 64 rows lo], one N = 128 operand
             *reinterpret_cast<float4*>(smem + NI_ZJ_HI + o) = hi;
-            *reinterpret_cast<float4*>(smem + NI_ZJ_LO + o) = lo;
+            *reinterpret_cast<float4*>(smem + NI_ZJ_HI + 8192 + o) = lo;
         }
     };
-    const uint32_t zt_base = (sj >> 5) * 8192 + ((sj & 3) << 2);     // transposed tile: k = j -> atom sj / 32, word sj % 32 of row d
+    const uint32_t zt_base = (sj >> 5) * 16384 + ((sj & 3) << 2);     // transposed tile: k = j -> atom sj / 32, word sj % 32 of row d
     const uint32_t zt_chunk = (sj & 31) >> 2;
     auto stage_t = [&](const float4 (&z)[2], int buf) {              // transposed [d][j]: operand B of the gradient contraction
 #pragma unroll
@@ -159,7 +151,7 @@ __global__ void __launch_bounds__(NI_THREADS, 1) dense_ni_tc_kernel(const NiArgs
                 const int d = 4 * (sc0 + e) + u;                      // d & 7 == 4 e + u (sc0 is even)
                 const uint32_t ot = zt_base + d * 128 + ((zt_chunk ^ (uint32_t)(4 * e + u)) << 4);
                 *reinterpret_cast<float*>(smem + NI_ZT + buf * NI_ZT_BUF + ot) = hv[u];
-                *reinterpret_cast<float*>(smem + NI_ZT + buf * NI_ZT_BUF + 16384 + ot) = lv[u];
+                *reinterpret_cast<float*>(smem + NI_ZT + buf * NI_ZT_BUF + 8192 + ot) = lv[u];
             }
         }
     };
@@ -193,45 +185,40 @@ __global__ void __launch_bounds__(NI_THREADS, 1) dense_ni_tc_kernel(const NiArgs
         // ================================ MMA issuer (warp 16) ================================
         // The whole warp takes part in the named barriers (bar.sync is warp-aligned); elect.sync picks the same lane
         // every time, so all MMAs and commits come from one thread.
-        const uint32_t idesc = make_idesc(NI_BJ);                     // both contractions: M = 128, N = 64
+        // hi and lo of a B operand are adjacent along N ([64 rows hi | 64 rows lo] per k-atom) and so are the main and the
+        // correction accumulator in TMEM: a_hi x [b_hi | b_lo] is ONE N = 128 instruction, a k-step costs two MMAs, not three
+        const uint32_t idesc64 = make_idesc(64), idesc128 = make_idesc(128);
         const uint64_t zi_hi = make_desc(smem_u32(smem + NI_ZI_HI)), zi_lo = make_desc(smem_u32(smem + NI_ZI_LO));
-        const uint64_t zj_hi = make_desc(smem_u32(smem + NI_ZJ_HI)), zj_lo = make_desc(smem_u32(smem + NI_ZJ_LO));
-        const uint64_t c_hi = make_desc(smem_u32(smem + NI_C_HI)), c_lo = make_desc(smem_u32(smem + NI_C_LO));
-        const uint64_t zt_hi = make_desc(smem_u32(smem + NI_ZT)), zt_lo = make_desc(smem_u32(smem + NI_ZT + 16384));
-        auto contract = [&](uint32_t d_main, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, bool fresh) {
-            const uint32_t d_corr = d_main + 64;                      // 3xTF32: main + correction accumulator
+        const uint64_t zj = make_desc(smem_u32(smem + NI_ZJ_HI)), zt = make_desc(smem_u32(smem + NI_ZT));
+        auto logits = [&](int buf) {                                  // P[buf] = (-log2 e Z_I) . Z_J^T
+            const uint32_t d = tmem_base + NI_COL_P + 128 * buf;
             fence_proxy_async();                                      // the workers' generic stores -> async proxy
             tc_fence_after();
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {                             // k-step: atom s / 4, 32 bytes per step inside it
-                const uint32_t ao = (s >> 2) * (16384 >> 4) + (s & 3) * 2, bo = (s >> 2) * (8192 >> 4) + (s & 3) * 2;
-                const uint32_t accum = !(fresh && s == 0);
-                umma_tf32(d_corr, a_lo + ao, b_hi + bo, idesc, accum);
-                umma_tf32(d_corr, a_hi + ao, b_lo + bo, idesc, 1);
-                umma_tf32(d_main, a_hi + ao, b_hi + bo, idesc, accum);
+            for (int s = 0; s < 8; ++s) {                             // k-step: atom s / 4 (16 KB), 32 bytes per step inside it
+                const uint32_t o = (s >> 2) * (16384 >> 4) + (s & 3) * 2;
+                umma_tf32(d, zi_hi + o, zj + o, idesc128, s != 0);    // main | corr (+)= a_hi x [b_hi | b_lo]
+                umma_tf32(d + 64, zi_lo + o, zj + o, idesc64, 1);     // corr += a_lo x b_hi
             }
+            umma_commit(&bar_p);
         };
-        auto contract_tmem_a = [&](uint32_t d_main, uint32_t a_main, uint64_t b_hi, uint64_t b_lo, bool fresh) {
-            const uint32_t d_corr = d_main + 64, a_corr = a_main + 64;  // A = C in tensor memory: hi over P main, lo over P corr
+        auto gradient = [&](int t) {                                  // dZ += C(t) . Z_J(t); A = C in tensor memory over P[t & 1]
+            const uint32_t d = tmem_base + NI_COL_DZ, c_hi = tmem_base + NI_COL_P + 128 * (t & 1), c_lo = c_hi + 64;
+            const uint64_t b = zt + (uint64_t)((t & 1) * (NI_ZT_BUF >> 4));
             fence_proxy_async();
             tc_fence_after();
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {                             // k-step: 8 columns of A, atom s / 4 (+ 32 bytes per step) of B
-                const uint32_t bo = (s >> 2) * (8192 >> 4) + (s & 3) * 2;
-                const uint32_t accum = !(fresh && s == 0);
-                umma_tf32_tmem_a(d_corr, a_corr + 8 * s, b_hi + bo, idesc, accum);
-                umma_tf32_tmem_a(d_corr, a_main + 8 * s, b_lo + bo, idesc, 1);
-                umma_tf32_tmem_a(d_main, a_main + 8 * s, b_hi + bo, idesc, accum);
+            for (int s = 0; s < 8; ++s) {                             // k-step: 8 columns of C, atom s / 4 (+ 32 bytes per step) of Z_J^T
+                const uint32_t o = (s >> 2) * (16384 >> 4) + (s & 3) * 2;
+                umma_tf32_tmem_a(d, c_hi + 8 * s, b + o, idesc128, !(t == 0 && s == 0));
+                umma_tf32_tmem_a(d + 64, c_lo + 8 * s, b + o, idesc64, 1);
             }
         };
         auto l2_prefetch_tile = [&](int t) {                          // whole 32 KB target tile of block t -> L2
             if (t < T) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(tile0 + (int64_t)t * NI_TILE), "r"(NI_TILE * 4) : "memory");
         };
         if (elect_one()) {
-            if (T > 0) {
-                contract(tmem_base + NI_COL_P, zi_hi, zi_lo, zj_hi, zj_lo, true);
-                umma_commit(&bar_p);
-            }
+            if (T > 0) logits(0);
             l2_prefetch_tile(1);
             l2_prefetch_tile(2);
         }
@@ -239,22 +226,13 @@ __global__ void __launch_bounds__(NI_THREADS, 1) dense_ni_tc_kernel(const NiArgs
         for (int t = 0; t < T; ++t) {
             asm volatile("bar.sync 1, %0;" ::"r"(NI_THREADS) : "memory");              // sync A(t): Z_J(t+1) staged, P[(t+1)&1] drained
             if (elect_one()) {
-                if (t + 1 < T) {
-                    contract(tmem_base + NI_COL_P + 128 * ((t + 1) & 1), zi_hi, zi_lo, zj_hi, zj_lo, true);
-                    umma_commit(&bar_p);
-                }
+                if (t + 1 < T) logits((t + 1) & 1);
                 l2_prefetch_tile(t + 3);
             }
             __syncwarp();
             asm volatile("bar.sync 2, %0;" ::"r"(NI_THREADS) : "memory");              // sync B(t): C(t), Z_J^T(t) stored
             if (elect_one()) {
-                if (CT) {
-                    const uint32_t zo = (t & 1) * (NI_ZT_BUF >> 4);
-                    contract_tmem_a(tmem_base + NI_COL_DZ, tmem_base + NI_COL_P + 128 * (t & 1), zt_hi + zo, zt_lo + zo, t == 0);
-                } else {
-                    contract(tmem_base + NI_COL_DZ, c_hi, c_lo, zt_hi, zt_lo, t == 0);
-                    umma_commit(&bar_d);
-                }
+                gradient(t);
                 if (t == T - 1) umma_commit(&bar_end);
             }
             __syncwarp();
@@ -267,7 +245,6 @@ __global__ void __launch_bounds__(NI_THREADS, 1) dense_ni_tc_kernel(const NiArgs
         const int ei = q * 32 + lane;
         const int64_t gi = (int64_t)ib * NI_BI + ei;
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-        const uint32_t c_off = (cg >> 1) * 16384;                     // atom of the C tile; chunks 4 (cg & 1) .. + 3 inside it
         float loss = 0.f;
 
         for (int t = 0; t < T; ++t) {
@@ -310,34 +287,19 @@ __global__ void __launch_bounds__(NI_THREADS, 1) dense_ni_tc_kernel(const NiArgs
             };
             if (tri == 2) coefficients(std::true_type{}); else coefficients(std::false_type{});
             if (tri != 0) loss += sq;
-            if (CT) {
-                // ---- C in place over the logit tile (tensor memory); Z_J^T into the buffer MMA2(t-2) has released
-                //      (it was issued before MMA1(t), whose completion this iteration has already awaited)
-                uint32_t ch[16], cl[16];
+            // ---- C in place over the logit tile (tensor memory); Z_J^T into the buffer MMA2(t-2) has released
+            //      (it was issued before MMA1(t), whose completion this iteration has already awaited)
+            uint32_t ch[16], cl[16];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    float hi, lo;
-                    split_coef(cv[k], hi, lo);
-                    ch[k] = __float_as_uint(hi); cl[k] = __float_as_uint(lo);
-                }
-                tmem_st16(tP, ch);
-                tmem_st16(tP + 64, cl);
-                stage_t(zc, t & 1);
-                tmem_wait_st();
-            } else {
-                // ---- the previous gradient contraction has read C and Z_J^T
-                if (t > 0) mbar_wait(&bar_d, (uint32_t)((t - 1) & 1));
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float4 hi, lo;
-                    split_coef(cv[4 * c], hi.x, lo.x); split_coef(cv[4 * c + 1], hi.y, lo.y);
-                    split_coef(cv[4 * c + 2], hi.z, lo.z); split_coef(cv[4 * c + 3], hi.w, lo.w);
-                    const uint32_t o = c_off + swz(ei, (cg & 1) * 4 + c);
-                    *reinterpret_cast<float4*>(smem + NI_C_HI + o) = hi;
-                    *reinterpret_cast<float4*>(smem + NI_C_LO + o) = lo;
-                }
-                stage_t(zc, 0);
+            for (int k = 0; k < 16; ++k) {
+                float hi, lo;
+                split_coef(cv[k], hi, lo);
+                ch[k] = __float_as_uint(hi); cl[k] = __float_as_uint(lo);
             }
+            tmem_st16(tP, ch);
+            tmem_st16(tP + 64, cl);
+            stage_t(zc, t & 1);
+            tmem_wait_st();
             tc_fence_before();
             asm volatile("bar.sync 2, %0;" ::"r"(NI_THREADS) : "memory");              // sync B(t)
             zc[0] = zn[0]; zc[1] = zn[1];
@@ -484,19 +446,10 @@ extern "C" int gd_dense_ni_tc_fwd_bwd(const float* zs, int64_t ldz, int64_t n_s,
     float* partial = static_cast<float*>(workspace);
     float* parts = js > 1 ? reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + align_up((size_t)(n_ib * js + 1) * sizeof(float))) : nullptr;
     tc::NiArgs a{zs, ldz, n_s, packed_target, (int)n_ib, (int)n_jb, 2.0f * coef_scale, js > 1 ? parts : dzs, lddz, partial, js};
-    // GD_DENSE_NI_C=smem keeps the coefficient tile in shared memory (the first version of the kernel; A/B and fallback)
-    const char* cenv = getenv("GD_DENSE_NI_C");
-    const bool c_in_tmem = !(cenv && strcmp(cenv, "smem") == 0);
     const int grid = (int)(n_ib * js);
-    if (c_in_tmem) {
-        const size_t smem = tc::NI_SMEM_CT + 1024;
-        GD_CUDA(cudaFuncSetAttribute(tc::dense_ni_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc::dense_ni_tc_kernel<true><<<grid, tc::NI_THREADS, smem, stream>>>(a);
-    } else {
-        const size_t smem = tc::NI_SMEM + 1024;
-        GD_CUDA(cudaFuncSetAttribute(tc::dense_ni_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc::dense_ni_tc_kernel<false><<<grid, tc::NI_THREADS, smem, stream>>>(a);
-    }
+    const size_t smem = tc::NI_SMEM + 1024;
+    GD_CUDA(cudaFuncSetAttribute(tc::dense_ni_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc::dense_ni_tc_kernel<<<grid, tc::NI_THREADS, smem, stream>>>(a);
     GD_LAUNCH_CHECK();
     const int fblocks = js > 1 ? (int)std::min<int64_t>(ceil_div<int64_t>(n_s * (tc::NI_D / 4), 256), kNumSMs * 8) : 1;
     tc::dense_ni_tc_finish_kernel<<<fblocks, 256, 0, stream>>>(partial, grid, loss_sum, parts, js, n_ib * tc::NI_BI, n_s, dzs, lddz);

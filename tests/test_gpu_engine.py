@@ -125,11 +125,12 @@ def test_dense_block_ni_matches_fullbatch_oracle(lib):
     dense_ni_case(0.03)
 
 
-@pytest.mark.parametrize('n_s', [37, 128, 700, 1500])
+@pytest.mark.parametrize('n_s', [37, 128, 700, 1500, 2600])
 def test_dense_ni_tensor_core_kernel_matches_fp64(lib, n_s, monkeypatch):
     """gd_dense_ni_tc_fwd_bwd (tcgen05, 3xTF32) on its own: loss sum and dz against an fp64 evaluation of
     gnndelete.py:239-241 on the S x S block, and against the fp32 CUDA-core kernel.  Sizes cover a partial row block,
-    one exact block, a split J sweep (jsplit > 1) and ragged last blocks; excluded (Df) pairs in both orders."""
+    one exact block, a split J sweep (jsplit > 1), ragged last blocks and (2600: six column blocks per CTA) the steady state
+    of the block pipeline; excluded (Df) pairs in both orders."""
     from gnndelete_b200.losses import DenseNIPlan
     torch.manual_seed(n_s)
     n = n_s + 50
