@@ -426,8 +426,9 @@ class GNNDeleteTrainer(Trainer):
                               hoist_layer1=getattr(args, 'hoist_layer1', True), logits_ori=logits_ori,
                               static_negatives=fixed_neg is not None, alpha=self._loss_mix())
         self.engine = eng
-        if getattr(args, 'capture_step', True) and logits_ori is None:
-            # one cudaGraphLaunch per epoch; resampled negatives are written into the graph's staging buffer
+        if getattr(args, 'capture_step', True):
+            # one cudaGraphLaunch per epoch (edge-form and dense-block NI alike); resampled negatives are written into the
+            # graph's staging buffer
             try:
                 eng.capture(warmup=2, dynamic_negatives=fixed_neg is None)
             except Exception as exc:                            # capture is an optimisation: fall back to eager epochs

@@ -8,7 +8,8 @@ import torch
 ap = argparse.ArgumentParser()
 ap.add_argument('--epochs', type=int, default=30)
 ap.add_argument('--scale', type=float, default=1.0)
-ap.add_argument('--configs', default='cora,pubmed,biokg')
+ap.add_argument('--configs', default='cora,cora-dense,pubmed,biokg',
+                help="'cora-dense' = config 1 with train_fullbatch's dense-block NI loss (logits_ori given), 'cora' = edge-form NI")
 a = ap.parse_args()
 import framework
 from gnndelete_b200 import masks as MK, synthetic as S
@@ -25,7 +26,8 @@ def targs(tmp, gnn, shape, **kw):
 
 
 for name in a.configs.split(','):
-    shape = S.SHAPES[name].scaled(a.scale)
+    dense_ni = name.endswith('-dense')
+    shape = S.SHAPES[name.replace('-dense', '')].scaled(a.scale)
     kg = shape.num_edge_type > 0
     raw = S.make_graph(shape, seed=42, device='cpu').to(dev)
     df = S.sample_df_mask(shape.num_edges, shape.num_deleted, seed=42, device='cpu').to(dev)
@@ -47,13 +49,19 @@ for name in a.configs.split(','):
         data.neg_edge_index = S.supplied_negatives(shape.num_nodes, int(data.df_mask.sum()), seed=43, device='cpu').to(dev)
     trainer = framework.get_trainer(args)
     warm = targs(tmp, shape.gnn, shape, epochs=3)
-    trainer.train(model, data, optimizer, warm)                 # plans, workspaces, module loading
+    logits_ori = None
+    if dense_ni:                                                # what base.py:288 stores in pred_proba.pt
+        with torch.no_grad():
+            zo_ = model.get_original_embeddings(data.x, data.train_pos_edge_index[:, data.dr_mask])
+            logits_ori = zo_ @ zo_.t()
+    extra = (logits_ori,) if dense_ni else ()
+    trainer.train(model, data, optimizer, warm, *extra)         # plans, workspaces, module loading
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    trainer.train(model, data, optimizer, args)
+    trainer.train(model, data, optimizer, args, *extra)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    line = {'config': name, 'gnn': shape.gnn, 'nodes': shape.num_nodes, 'directed_edges': shape.num_edges,
+    line = {'config': name, 'ni_loss': 'dense block (train_fullbatch)' if dense_ni else 'edge form', 'gnn': shape.gnn, 'nodes': shape.num_nodes, 'directed_edges': shape.num_edges,
             'deleted': shape.num_deleted, 'dims': [shape.in_dim, shape.hidden_dim, shape.out_dim], 'epochs': a.epochs,
             'epochs_per_s_through_trainer': a.epochs / dt, 'ms_per_epoch': 1e3 * dt / a.epochs,
             'note': 'wall clock around trainer.train (includes plan build of the second call, logging, checkpoint write)'}
@@ -63,7 +71,7 @@ for name in a.configs.split(','):
     for k in ('captured_step', 'capture_error'):
         if k in trainer.trainer_log:
             line[k] = trainer.trainer_log[k]
-    if shape.gnn == 'gcn':                                       # the fused engine alone, CUDA-graph replay
+    if shape.gnn == 'gcn' and not dense_ni:                      # the fused engine alone, CUDA-graph replay
         with torch.no_grad():
             zo = model.get_original_embeddings(data.x, data.train_pos_edge_index[:, data.dr_mask])
         eng = GCNDeleteEngine(model, data, data.neg_edge_index, z_ori=zo, hoist_layer1=False, static_negatives=True)
