@@ -23,6 +23,7 @@
 // accumulator is double buffered in TMEM so the epilogue of tile i overlaps the loads and MMAs
 // of tile i+1.
 #include <cstdlib>
+#include <cstring>
 
 #include "tc_common.cuh"
 
@@ -37,18 +38,6 @@ constexpr int EPI_LD = 36;                       // padded row (floats) of the p
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
 constexpr int PREFETCH = 4;                      // producer register ring depth (stages of loads in flight)
 
-struct Args {
-    const float* a; int64_t lda;
-    const int32_t* rows; int64_t m; int k;
-    const float* b; int b_is_nk; int n;
-    const float* bias; const float* out_scale; const float* gate; int64_t ldgate;
-    int relu_in, relu_out;
-    float* out; int64_t ldo;
-    uint32_t* relu_mask_out; const uint32_t* gate_bits;      // [row][n/32] bit c%32 of word c/32 <=> value > 0
-    int num_tiles;
-    int stages;
-    int debug;          // GD_TC_DEBUG bit mask (measurement only): 1 = no epilogue work, 2 = producers do not load, 4 = no MMAs, 8 = epilogue without global stores, 16 = epilogue without TMEM loads
-};
 
 // Warp roles of gemm_rows_tc_kernel: 16 producers, 4 epilogue warps (one per TMEM lane quarter), 1 MMA issuer.  Measured (tools/gemm_sweep.py with GD_TC_DEBUG):
 // with 4 epilogue warps running a flag-generic epilogue the kernel was epilogue bound at 5.5 us per
@@ -652,6 +641,12 @@ extern "C" int gd_gemm_rows_tc(const float* a, int64_t lda, const int32_t* rows,
     tc::Args g{a, lda, rows, m, k, b, b_is_nk, n, bias, out_scale, gate, ldgate, relu_in, relu_out, out, ldo,
                relu_mask_out, gate_bits, (int)ceil_div<int64_t>(m, tc::BM), tc::num_stages(k, n), 0};
     { const char* e = getenv("GD_TC_DEBUG"); g.debug = e ? atoi(e) : 0; }     // measurement only; read per call so one process can sweep it
+    // weights-in-TMEM kernel (gemm_tc_wt.cu) for the shapes / epilogues of the Del-training epoch; GD_GEMM_ROWS=ring keeps this one
+    {
+        const char* e = getenv("GD_GEMM_ROWS");
+        const bool want_wt = !(e && strcmp(e, "ring") == 0);
+        if (want_wt && tc::rows_wt_supported(g)) return tc::launch_rows_wt(g, stream);
+    }
     const size_t smem = tc::smem_bytes(k, n);
     const int grid = std::min(g.num_tiles, kNumSMs);
     const int need = (bias ? tc::EPI_BIAS : 0) | (out_scale ? tc::EPI_SCALE : 0) | (relu_out ? tc::EPI_RELU : 0) |

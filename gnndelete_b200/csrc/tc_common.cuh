@@ -180,5 +180,22 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 
+// arguments of the gathered-row GEMMs (gemm_tc.cu: A ring + resident B in shared memory; gemm_tc_wt.cu: weights in TMEM)
+struct Args {
+    const float* a; int64_t lda;
+    const int32_t* rows; int64_t m; int k;
+    const float* b; int b_is_nk; int n;
+    const float* bias; const float* out_scale; const float* gate; int64_t ldgate;
+    int relu_in, relu_out;
+    float* out; int64_t ldo;
+    uint32_t* relu_mask_out; const uint32_t* gate_bits;      // [row][n/32] bit c%32 of word c/32 <=> value > 0
+    int num_tiles;
+    int stages;
+    int debug;          // GD_TC_DEBUG bit mask (measurement only): 1 = no epilogue work, 2 = producers do not load, 4 = no MMAs, 8 = epilogue without global stores, 16 = epilogue without TMEM loads
+};
+
+bool rows_wt_supported(const Args& g);
+int launch_rows_wt(const Args& g, cudaStream_t stream);
+
 }  // namespace tc
 }  // namespace gd

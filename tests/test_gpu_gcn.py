@@ -215,6 +215,56 @@ def test_gemm_rows(lib, m, k, n, nk):
     U.assert_close(out2, ref2, what='gemm_rows gathered')
 
 
+@pytest.mark.parametrize('kernel', ['wt', 'ring'])
+@pytest.mark.parametrize('m,k,n,nk', [(40001, 128, 128, True), (30000, 128, 64, True), (20011, 64, 64, False), (25000, 64, 128, False),
+                                      (130, 32, 96, True), (63, 128, 128, False)])
+def test_gemm_rows_epoch_epilogues(lib, m, k, n, nk, kernel, monkeypatch):
+    """The epilogues of the Del-training epoch on both tcgen05 row GEMMs (weights in tensor memory, gemm_tc_wt.cu, and
+    the shared-memory ring, gemm_tc.cu): row scale, ReLU prologue, bit-packed ReLU mask out, gate bits in, gathered rows;
+    sizes with several tiles per CTA (ring wrap-around, both accumulator buffers) and ragged last tiles."""
+    from gnndelete_b200 import ops
+    monkeypatch.setenv('GD_GEMM_ROWS', kernel)
+    g = torch.Generator().manual_seed(m + k + n)
+    a = torch.randn(m, k, generator=g)
+    b = torch.randn((n, k) if nk else (k, n), generator=g)
+    s = torch.rand(m, generator=g) + 0.5
+    bm = b.double().t() if nk else b.double()
+    ad, bd, sd = a.to(DEV), b.to(DEV), s.to(DEV)
+    # (1) all rows: ReLU prologue + row scale
+    out = ops.gemm_rows(ad, bd, nk, out_scale=sd, relu_in=True)
+    U.assert_close(out, (a.double().clamp(min=0) @ bm) * s.double().view(-1, 1), what='scale + relu_in')
+    # (2) gathered rows in place + the ReLU mask of the result as bits
+    rows = torch.randperm(m, generator=g)[: (2 * m) // 3].sort()[0]
+    bits = torch.full((m, n // 32), -1, dtype=torch.int32, device=DEV)
+    out2 = torch.full((m, n), -7.0, device=DEV)
+    ops.gemm_rows(ad, bd, nk, out=out2, rows=rows.to(DEV).int(), relu_mask_out=bits)
+    ref2 = torch.full((m, n), -7.0, dtype=torch.float64)
+    prod = a.double()[rows] @ bm
+    ref2[rows] = prod
+    U.assert_close(out2, ref2, what='gathered rows')
+    got = ((bits[rows.to(DEV)].unsqueeze(-1) >> torch.arange(32, device=DEV)) & 1).reshape(rows.numel(), n).bool().cpu()
+    sure = prod.abs() > 1e-4 * prod.abs().max()                      # sign of near-zero products may differ in the last ulp
+    assert torch.equal(got[sure], (prod > 0)[sure]), 'ReLU mask bits'
+    assert torch.equal(bits[~torch.isin(torch.arange(m), rows).to(DEV)], torch.full((m - rows.numel(), n // 32), -1, dtype=torch.int32, device=DEV))
+    # (3) gate bits in + row scale (the dX1 GEMM): out = scale * (a . B) where the gate bit is set, else 0
+    gate = torch.rand(m, n, generator=g) > 0.4
+    w = (gate.view(m, n // 32, 32).long() << torch.arange(32)).sum(-1)
+    gbits = torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32).to(DEV)
+    out3 = torch.full((m, n), 3.0, device=DEV)
+    ops.gemm_rows(ad, bd, nk, out=out3, rows=rows.to(DEV).int(), out_scale=sd, gate_bits=gbits)
+    ref3 = torch.full((m, n), 3.0, dtype=torch.float64)
+    ref3[rows] = torch.where(gate[rows], prod * s.double()[rows].view(-1, 1), torch.zeros_like(prod))
+    U.assert_close(out3, ref3, what='gate bits + scale')
+    # (4) mask bits with a row scale (sign taken after scaling, scale > 0)
+    bits4 = torch.zeros(m, n // 32, dtype=torch.int32, device=DEV)
+    out4 = ops.gemm_rows(ad, bd, nk, out_scale=sd, relu_mask_out=bits4)
+    full = a.double() @ bm
+    U.assert_close(out4, full * s.double().view(-1, 1), what='scale + mask bits')
+    got4 = ((bits4.unsqueeze(-1) >> torch.arange(32, device=DEV)) & 1).reshape(m, n).bool().cpu()
+    sure4 = full.abs() > 1e-4 * full.abs().max()
+    assert torch.equal(got4[sure4], (full > 0)[sure4])
+
+
 @pytest.mark.parametrize('m,k1,n2', [(5000, 128, 128), (777, 64, 64), (300, 100, 30)])
 def test_gemm_tn_rows(lib, m, k1, n2):
     from gnndelete_b200 import ops
