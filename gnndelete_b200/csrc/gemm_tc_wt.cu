@@ -15,9 +15,11 @@
 //   * the tensor core reads only the X operand from shared memory: 3xTF32 as  W_hi x [x_hi | x_lo]  (ONE N = 128
 //     instruction into the adjacent main | correction accumulators) +  W_lo x x_hi  (N = 64): 6 KB per k-step, not 24;
 //   * the accumulators (main + correction, 128 columns per tile) are double buffered in the other half of TMEM.
-// The accumulator comes out transposed (thread = output feature, columns = rows): the epilogue turns 32 rows x 32
-// features per warp through a shared-memory tile and writes 128-byte runs of the (scattered) output rows; the bit-packed
-// ReLU mask of a row is a __ballot_sync over the 32 features a warp holds.
+// The accumulator comes out transposed (thread = output feature, columns = rows): an epilogue warp turns 32 rows x 32
+// features through a shared-memory tile and writes 128-byte runs of the (scattered) output rows with 128-bit stores
+// (storing straight from the feature-per-lane layout - one 32-bit store per row - measured 10-35 % slower); the bit-packed
+// ReLU mask of a row is a __ballot_sync over the 32 features a warp holds; the row scale is applied to the INPUT row by
+// the producers (s (x . W) = (s x) . W).
 //
 // Covers the epilogues of the Del-training epoch (row scale, ReLU prologue, ReLU bit mask out, gate bits in); bias,
 // ReLU epilogue and fp32 gates stay on gemm_tc.cu (rows_wt_supported()).
@@ -46,13 +48,14 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gemm_rows_wt_kernel(const Args 
     const int stage_bytes = kchunks * WT_ATOM;
     const int STAGES = g.stages;
     float* epi_buf = reinterpret_cast<float*>(smem + STAGES * stage_bytes);
-    __shared__ uint64_t full_bar[WT_MAX_STAGES], empty_bar[WT_MAX_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint64_t full_bar[WT_MAX_STAGES], empty_bar[WT_MAX_STAGES], tfull_bar[2], tempty_bar[2], w_bar;
     __shared__ uint32_t tmem_base_smem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], WT_PRODUCER_WARPS); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], WT_EPI_WARPS); }
+        mbar_init(&w_bar, WT_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == WT_MMA_WARP) {
@@ -65,30 +68,48 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gemm_rows_wt_kernel(const Args 
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    // ---- W -> tensor memory, once: thread = output feature f (TMEM lane), 16 k values per tcgen05.st; rows >= n are zero
-    if (warp >= WT_PRODUCER_WARPS && warp < WT_PRODUCER_WARPS + 4) {
-        const int q = warp & 3;
+    // ---- W -> tensor memory, once: thread = output feature f (TMEM lane), 16 k values per tcgen05.st; rows >= n are zero.
+    //      All 8 epilogue warps take part (the two warps of a lane quarter split the k range); only the MMA thread waits for
+    //      it (w_bar), the producers start loading straight away.
+    if (warp >= WT_PRODUCER_WARPS && warp < WT_MMA_WARP) {
+        const int q = warp & 3, half = (warp - WT_PRODUCER_WARPS) >> 2;
         const int f = q * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-        for (int c16 = 0; c16 < g.k / 16; ++c16) {
+        const bool vec = g.b_is_nk && (((uintptr_t)g.b) & 15) == 0;
+        for (int c16 = half; c16 < g.k / 16; c16 += 2) {
+            float w[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) w[e] = 0.f;
+            if (f < g.n) {
+                if (vec) {
+#pragma unroll
+                    for (int e4 = 0; e4 < 4; ++e4) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(g.b + (int64_t)f * g.k + c16 * 16) + e4);
+                        w[4 * e4] = v.x; w[4 * e4 + 1] = v.y; w[4 * e4 + 2] = v.z; w[4 * e4 + 3] = v.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int kk = c16 * 16 + e;
+                        w[e] = g.b_is_nk ? __ldg(g.b + (int64_t)f * g.k + kk) : __ldg(g.b + (int64_t)kk * g.n + f);
+                    }
+                }
+            }
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-                const int kk = c16 * 16 + e;
-                float w = 0.f;
-                if (f < g.n) w = g.b_is_nk ? __ldg(g.b + (int64_t)f * g.k + kk) : __ldg(g.b + (int64_t)kk * g.n + f);
                 float h, l;
-                split_tf32(w, h, l);
+                split_tf32(w[e], h, l);
                 hi[e] = __float_as_uint(h); lo[e] = __float_as_uint(l);
             }
             tmem_st16(t_lane + 16 * c16, hi);
             tmem_st16(t_lane + g.k + 16 * c16, lo);
         }
         tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&w_bar);
     }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
 
     if (warp < WT_PRODUCER_WARPS) {
         // ================================ producers ================================
@@ -103,8 +124,12 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gemm_rows_wt_kernel(const Args 
             return i < g.m ? (g.rows ? __ldg(g.rows + i) : (int32_t)i) : -1;
         };
         float4 buf[WT_PREFETCH][4];
+        float rsc[WT_PREFETCH];                                       // row scale: applied to the INPUT row (s (x . W) = (s x) . W), so the
+                                                                      // transposed accumulator needs no per-row factor in the epilogue
         int32_t rid_pf = row_of(WT_PREFETCH);                         // row id of the tile whose loads are issued next
-        auto issue = [&](float4 (&b)[4], int32_t rid) {
+        auto issue = [&](float4 (&b)[4], float& sc, int32_t rid) {
+            sc = 1.0f;
+            if (SCALE && rid >= 0) sc = __ldg(g.out_scale + rid);
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 b[p] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -116,7 +141,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gemm_rows_wt_kernel(const Args 
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g.a + (int64_t)rid * g.lda), "r"(g.k * 4) : "memory");
         };
 #pragma unroll
-        for (int d = 0; d < WT_PREFETCH; ++d) issue(buf[d], row_of(d));
+        for (int d = 0; d < WT_PREFETCH; ++d) issue(buf[d], rsc[d], row_of(d));
         l2_prefetch(rid_pf);
         uint32_t stage = 0, phase = 0;
         for (int t = 0; t < my_tiles; t += WT_PREFETCH) {
@@ -130,6 +155,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gemm_rows_wt_kernel(const Args 
                         if (p < kchunks) {
                             float4 x = buf[d][p];
                             if (g.relu_in) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                            if (SCALE) { const float sc = rsc[d]; x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc; }
                             float4 hi, lo;
                             split4(x, hi, lo);
                             const uint32_t o = p * WT_ATOM + swz(r0, j);
@@ -143,7 +169,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gemm_rows_wt_kernel(const Args 
                     if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
                     const int32_t rid = rid_pf;                       // loads of tile t + d + WT_PREFETCH
                     rid_pf = row_of(t + d + WT_PREFETCH + 1);
-                    issue(buf[d], rid);
+                    issue(buf[d], rsc[d], rid);
                     l2_prefetch(rid_pf);
                 }
             }
@@ -156,6 +182,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gemm_rows_wt_kernel(const Args 
             const uint32_t w_hi = tmem_base, w_lo = tmem_base + g.k;
             uint32_t stage = 0, phase = 0;
             int it = 0;
+            mbar_wait(&w_bar, 0);                                     // W_hi / W_lo are in tensor memory
+            tc_fence_after();
             for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
                 const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -183,20 +211,19 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gemm_rows_wt_kernel(const Args 
         // ================================ epilogue ================================
         // 8 warps: q = warp % 4 = TMEM lane quarter (32 output features, thread = feature), h = 32-row half of the tile.
         // accumulators -> registers -> [32 rows x 32 features] shared tile -> 128-byte runs of the output rows (8 lanes x 16 B
-        // per row, 4 rows per store).  Row ids / scales / gate words of the NEXT tile are loaded before this one is awaited.
+        // per row, 4 rows per store).  Row ids / gate words of the NEXT tile are loaded before this one is awaited.
         const int ew = warp - WT_PRODUCER_WARPS;
         const int q = warp & 3, h = ew >> 2;
         const bool active = q * 32 < g.n;
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
         float* tbuf = epi_buf + ew * (32 * 32);
         const int nw = g.n >> 5;
-        int32_t rid_n = -1; float sc_n = 1.0f; uint32_t gw_n = 0u;
+        int32_t rid_n = -1; uint32_t gw_n = 0u;
         auto load_meta = [&](int tile) {                              // this lane's row (32 h + lane) of `tile`
-            rid_n = -1; sc_n = 1.0f; gw_n = 0u;
+            rid_n = -1; gw_n = 0u;
             if (tile < g.num_tiles && active) {
                 const int64_t gi = (int64_t)tile * WT_ROWS + 32 * h + lane;
                 rid_n = gi < g.m ? (g.rows ? __ldg(g.rows + gi) : (int32_t)gi) : -1;
-                if (SCALE && rid_n >= 0) sc_n = __ldg(g.out_scale + rid_n);
                 if (GATE_BITS && rid_n >= 0) gw_n = __ldg(g.gate_bits + (int64_t)rid_n * nw + q);
             }
         };
@@ -205,7 +232,6 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gemm_rows_wt_kernel(const Args 
         for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             const int32_t rid = rid_n;
-            const float sc = sc_n;
             const uint32_t gw = gw_n;
             load_meta(tile + gridDim.x);
             uint32_t colbits = 0xffffffffu;                           // bit jj: gate of (row jj, this lane's feature)
@@ -233,9 +259,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gemm_rows_wt_kernel(const Args 
                         float x = __uint_as_float(pm[e]) + __uint_as_float(pc[e]);
                         if (GATE_BITS) { if (!((colbits >> jj) & 1u)) x = 0.f; }
                         if (MASK_OUT) {
-                            float xs = x;
-                            if (SCALE) xs *= __shfl_sync(0xffffffffu, sc, jj);
-                            const uint32_t v = __ballot_sync(0xffffffffu, xs > 0.f);   // the 32 features of row jj = one mask word
+                            const uint32_t v = __ballot_sync(0xffffffffu, x > 0.f);    // the 32 features of row jj = one mask word
                             if (lane == jj) posword = v;
                         }
                         tbuf[jj * 32 + lane] = x;
@@ -251,10 +275,6 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gemm_rows_wt_kernel(const Args 
                     const int jj = (lane >> 3) + 4 * i;
                     float4 o = lds128(tbuf + jj * 32 + (lane & 7) * 4);
                     const int32_t rr = __shfl_sync(0xffffffffu, rid, jj);
-                    if (SCALE) {
-                        const float s = __shfl_sync(0xffffffffu, sc, jj);
-                        o.x *= s; o.y *= s; o.z *= s; o.w *= s;
-                    }
                     if (rr >= 0) *reinterpret_cast<float4*>(g.out + (int64_t)rr * g.ldo + q * 32 + (lane & 7) * 4) = o;
                 }
                 __syncwarp();
