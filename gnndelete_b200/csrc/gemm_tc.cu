@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tn_tc_kernel(const TnArgs
         }
     } else if (warp == MMA_WARP) {
         if (elect_one()) {
-            const uint32_t idesc = make_idesc_mn(t.n2);
+            const uint32_t idesc = make_idesc_mn(t.n2), idesc2 = make_idesc_mn(2 * t.n2);
             // stage layout: A^T hi | A^T lo | G^T hi | G^T lo; rows 8 ks .. 8 ks + 7 of a stage = two 4-row k-atoms (512 B each)
             // inside every 4 KB feature-atom column, i.e. + 1024 bytes per k-step
             const uint64_t da0 = make_desc_mn(smem_u32(smem), TN_ATOM_COL, 512);
@@ -543,14 +543,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tn_tc_kernel(const TnArgs
                     fence_proxy_async();                           // the producers' generic stores -> async proxy
                     tc_fence_after();
                     const uint64_t da_hi = desc_advance(da0, stage * stage_bytes), da_lo = desc_advance(da_hi, TILE_BYTES);
-                    const uint64_t db_hi = desc_advance(da_lo, TILE_BYTES), db_lo = desc_advance(db_hi, g_tile);
+                    const uint64_t db_hi = desc_advance(da_lo, TILE_BYTES);        // G^T hi, immediately followed by G^T lo
                     const bool first = (s == grp * TN_FLUSH);
+                    // G^T lo follows G^T hi in atom-column order (same lbo), and the correction accumulator follows the main one
+                    // in TMEM: a_hi x [g_hi | g_lo] is ONE instruction of N = 2 n2 - two MMAs per k-step instead of three
 #pragma unroll
                     for (int ks = 0; ks < KC / 8; ++ks) {
                         const uint32_t accum = !(first && ks == 0);
-                        umma_tf32(dc, da_lo + 64 * ks, db_hi + 64 * ks, idesc, accum);
-                        umma_tf32(dc, da_hi + 64 * ks, db_lo + 64 * ks, idesc, 1);
-                        umma_tf32(d, da_hi + 64 * ks, db_hi + 64 * ks, idesc, accum);
+                        umma_tf32(d, da_hi + 64 * ks, db_hi + 64 * ks, idesc2, accum);      // main | corr (+)= a_hi x [g_hi | g_lo]
+                        umma_tf32(dc, da_lo + 64 * ks, db_hi + 64 * ks, idesc, 1);          // corr += a_lo x g_hi
                     }
                     umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
