@@ -394,16 +394,6 @@ static size_t smem_bytes(int k, int n) { return fixed_bytes(k, n) + (size_t)num_
 // into the CTA's partial buffer (plain fp32 adds, fixed order) while the MMAs continue on the
 // other pair — this bounds the tensor core's truncating accumulation chain to 32 steps.  A tiny
 // second kernel adds the per-CTA partials in CTA order: deterministic, no atomics.
-struct TnArgs {
-    const float* a; int64_t lda;
-    const float* g; int64_t ldg;
-    const int32_t* rows; int64_t m;
-    int k1, n2, relu_a;
-    const float* a_scale;
-    float* partial;                 // [gridDim.x][k1][n2]
-    int64_t rows_per_cta;
-    int stages;
-};
 constexpr int TN_FLUSH = 8;         // stages (x32 rows) per accumulator flush
 constexpr int TN_PREFETCH = 3;      // producer register ring depth (stages of row loads in flight)
 constexpr int TN_ATOM_COL = 4096;   // bytes of one 32-feature atom column of a stage: 8 k-atoms (4 rows x 128 B) = 32 rows
@@ -727,6 +717,21 @@ extern "C" int gd_gemm_tn_rows_tc(const float* a, int64_t lda, const float* g, i
     const int64_t rows_per_cta = ceil_div<int64_t>(ceil_div<int64_t>(m, grid), 32) * 32;
     tc::TnArgs t{a, lda, g, ldg, rows, m, k1, n2, relu_a, a_scale, static_cast<float*>(workspace), rows_per_cta,
                  tc::tn_stages(n2)};
+    {   // A^T in tensor memory (gemm_tn_wt.cu): the default for n2 <= 64 (two accumulator buffers fit next to the A^T stages:
+        // 68 vs 79 us on the 64 x 64 case); at n2 = 128 it has a single buffer and is slower than the kernel below (136 vs 107 us).
+        // GD_GEMM_TN=wt / ring forces one of them.
+        const char* e = getenv("GD_GEMM_TN");
+        const bool want_wt = e ? strcmp(e, "wt") == 0 : n2 <= 64;
+        if (want_wt && tc::tn_wt_supported(t)) {
+            int nparts = 0;
+            const int rc = tc::launch_tn_wt(t, stream, &nparts);
+            if (rc != GD_OK) return rc;
+            const int64_t cnt = (int64_t)k1 * n2;
+            GD_CUDA(launch_pdl(tn_reduce_kernel, (unsigned)ceil_div<int64_t>(cnt, 32), 256, 0, stream, (const float*)t.partial, nparts, cnt, c));
+            GD_LAUNCH_CHECK();
+            return GD_OK;
+        }
+    }
     const size_t smem = 1024 + (size_t)t.stages * (2 * tc::TILE_BYTES + 2 * n2 * 128) + tc::EPI_BYTES;
     GD_CUDA(cudaFuncSetAttribute(tc::gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GD_CUDA(launch_pdl(tc::gemm_tn_tc_kernel, grid, tc::NUM_THREADS, smem, stream, t));

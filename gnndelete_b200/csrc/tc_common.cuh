@@ -194,6 +194,21 @@ struct Args {
     int debug;          // GD_TC_DEBUG bit mask (measurement only): 1 = no epilogue work, 2 = producers do not load, 4 = no MMAs, 8 = epilogue without global stores, 16 = epilogue without TMEM loads
 };
 
+// arguments of the weight-gradient contractions  c[k1, n2] = sum_i a_scale[r(i)] pro(a[r(i), :k1])^T (x) g[r(i), :n2]
+struct TnArgs {
+    const float* a; int64_t lda;
+    const float* g; int64_t ldg;
+    const int32_t* rows; int64_t m;
+    int k1, n2, relu_a;
+    const float* a_scale;
+    float* partial;                 // [gridDim.x][k1][n2]
+    int64_t rows_per_cta;
+    int stages;
+};
+
+bool tn_wt_supported(const TnArgs& t);
+int launch_tn_wt(const TnArgs& t, cudaStream_t stream, int* nparts);     // fills t.partial [nparts][k1][n2]
+
 bool rows_wt_supported(const Args& g);
 int launch_rows_wt(const Args& g, cudaStream_t stream);
 

@@ -276,6 +276,27 @@ def test_gemm_tn_rows(lib, m, k1, n2):
     U.assert_close(out, ref, what='gemm_tn_rows')
 
 
+@pytest.mark.parametrize('kernel', ['wt', 'ring'])
+@pytest.mark.parametrize('m,k1,n2', [(60001, 128, 128), (50000, 64, 64), (45000, 128, 64), (45000, 64, 128), (9000, 96, 32), (100, 128, 128)])
+def test_gemm_tn_rows_both_tensor_core_kernels(lib, m, k1, n2, kernel, monkeypatch):
+    """The weight-gradient contraction on both tcgen05 kernels (A^T in tensor memory, gemm_tn_wt.cu, and both operands in
+    shared memory, gemm_tc.cu): gathered rows, all rows, ReLU prologue and row scale; sizes with several flush groups per
+    CTA, ragged last stages and a single partial stage."""
+    from gnndelete_b200 import ops
+    monkeypatch.setenv('GD_GEMM_TN', kernel)
+    g = torch.Generator().manual_seed(m + k1 + n2)
+    a, gr = torch.randn(m, k1, generator=g), torch.randn(m, n2, generator=g)
+    sc = torch.rand(m, generator=g) + 0.5
+    rows = torch.randperm(m, generator=g)[: (2 * m) // 3].sort()[0]
+    ad, gd_, rd, sd = a.to(DEV), gr.to(DEV), rows.to(DEV).int(), sc.to(DEV)
+    U.assert_close(ops.gemm_tn_rows(ad, gd_, rows=rd), a.double()[rows].t() @ gr.double()[rows], what='gathered rows')
+    U.assert_close(ops.gemm_tn_rows(ad, gd_), a.double().t() @ gr.double(), what='all rows')
+    ref = (a.double()[rows].clamp(min=0) * sc.double()[rows].view(-1, 1)).t() @ gr.double()[rows]
+    U.assert_close(ops.gemm_tn_rows(ad, gd_, rows=rd, relu_a=True, a_scale=sd), ref, what='relu + row scale')
+    # deterministic: partials are reduced in CTA order
+    assert torch.equal(ops.gemm_tn_rows(ad, gd_, rows=rd), ops.gemm_tn_rows(ad, gd_, rows=rd))
+
+
 def _load(gnn, om, shape, data, **kw):
     from gnndelete_b200 import models as M
     cls = {'gcn': M.GCNDelete, 'gin': M.GINDelete}[gnn]

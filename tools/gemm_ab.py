@@ -37,3 +37,13 @@ for name, fn in cases.items():
         res[mode] = t(fn)
     print(f'{name:36s} wt {res["wt"]:7.1f} us   ring {res["ring"]:7.1f} us   x{res["ring"] / res["wt"]:.2f}', flush=True)
 os.environ.pop('GD_GEMM_ROWS', None)
+g128 = torch.zeros(128, 128, device=dev); g64 = torch.zeros(64, 64, device=dev)
+tn = {'tn 128x128 rows (dw1)': lambda: ops.gemm_tn_rows(x128, o128, rows=rows, out=g128),
+      'tn 64x64 rows (dw2)': lambda: ops.gemm_tn_rows(x64, o64, rows=rows, out=g64)}
+for name, fn in tn.items():
+    res = {}
+    for mode in ('wt', 'ring'):
+        os.environ['GD_GEMM_TN'] = mode
+        res[mode] = t(fn)
+    print(f'{name:36s} wt {res["wt"]:7.1f} us   ring {res["ring"]:7.1f} us   x{res["ring"] / res["wt"]:.2f}', flush=True)
+os.environ.pop('GD_GEMM_TN', None)
