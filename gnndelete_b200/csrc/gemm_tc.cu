@@ -717,11 +717,10 @@ extern "C" int gd_gemm_tn_rows_tc(const float* a, int64_t lda, const float* g, i
     const int64_t rows_per_cta = ceil_div<int64_t>(ceil_div<int64_t>(m, grid), 32) * 32;
     tc::TnArgs t{a, lda, g, ldg, rows, m, k1, n2, relu_a, a_scale, static_cast<float*>(workspace), rows_per_cta,
                  tc::tn_stages(n2)};
-    {   // A^T in tensor memory (gemm_tn_wt.cu): the default for n2 <= 64 (two accumulator buffers fit next to the A^T stages:
-        // 68 vs 79 us on the 64 x 64 case); at n2 = 128 it has a single buffer and is slower than the kernel below (136 vs 107 us).
-        // GD_GEMM_TN=wt / ring forces one of them.
+    {   // A^T in tensor memory (gemm_tn_wt.cu) is the default (89 vs 104 us at 128 x 128, 65 vs 79 us at 64 x 64);
+        // GD_GEMM_TN=ring keeps the shared-memory operand kernel below
         const char* e = getenv("GD_GEMM_TN");
-        const bool want_wt = e ? strcmp(e, "wt") == 0 : n2 <= 64;
+        const bool want_wt = !(e && strcmp(e, "ring") == 0);
         if (want_wt && tc::tn_wt_supported(t)) {
             int nparts = 0;
             const int rc = tc::launch_tn_wt(t, stream, &nparts);

@@ -249,9 +249,12 @@ __global__ void __launch_bounds__(TW_THREADS, 1) gemm_tn_wt_kernel(const TnArgs 
                     const int row = q * 32 + i * 4 + rl;
                     if (row < t.k1) {
                         float4 o = *reinterpret_cast<const float4*>(tbuf + (i * 4 + rl) * TW_EPI_LD + cl * 4);
-                        float4* dst = reinterpret_cast<float4*>(part + (int64_t)row * t.n2 + c0 + cl * 4);
-                        if (grp > 0) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-                        *dst = o;
+                        // every element of the CTA's partial is updated by this one thread, group after group: a vector reduction
+                        // is deterministic here and, unlike a read-modify-write, does not wait for the old value (with one
+                        // accumulator buffer at n2 = 128 the MMAs wait for this drain)
+                        float* dst = part + (int64_t)row * t.n2 + c0 + cl * 4;
+                        if (grp > 0) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+                        else *reinterpret_cast<float4*>(dst) = o;
                     }
                 }
                 __syncwarp();
