@@ -16,19 +16,20 @@ for r in rd:
     ns = v * {'ns': 1, 'us': 1e3, 'usecond': 1e3, 'nsecond': 1, 'ms': 1e6, 'msecond': 1e6}.get(u, 1)
     name = re.sub(r'\(.*', '', r[ik]).replace('void ', '').replace('(int)', '').replace('(bool)', '')
     rows.append((name, ns))
-# an epoch of the fixed-negatives engine: from a gemm_rows_tc_kernel<2> ... to the 2nd adam_bump after it; take the last complete one
+# epochs end with the second Adam bump: cut the launch list there and take the last segment that looks like the recompute
+# epoch `value` times (three forward aggregation launches - two 64-wide layer-1 passes + layer 2 - and the backward one, the
+# fused loss, no dense-NI kernels, no set-up launches)
 ends = [i for i, (n, _) in enumerate(rows) if 'adam_bump' in n]
+segs, prev = [], -1
+for k in range(1, len(ends), 2):
+    segs.append(rows[prev + 1:ends[k] + 1]); prev = ends[k]
 best = None
-for e in reversed(ends):
-    j = e
-    seen_bump = 0
-    while j >= 0:
-        if 'adam_bump' in rows[j][0]: seen_bump += 1
-        if seen_bump > 2: break
-        j -= 1
-    seg = rows[j + 1:e + 1]
-    if any('spmm_batched_kernel' in n for n, _ in seg) and any('node_loss' in n or 'edge_loss' in n for n, _ in seg):
+for seg in reversed(segs):
+    if sum('spmm_batched_kernel' in n for n, _ in seg) == 4 and any('node_loss' in n for n, _ in seg) \
+            and not any('dense_ni' in n or 'pair_scatter' in n for n, _ in seg) and len(seg) <= 40:
         best = seg; break
+if best is None:
+    sys.exit('no complete recompute epoch in the launch list')
 agg = {}
 for n, ns in best:
     c, t = agg.get(n, (0, 0.0)); agg[n] = (c + 1, t + ns)
