@@ -90,10 +90,16 @@ __global__ void __launch_bounds__(TW_THREADS, 1) gemm_tn_wt_kernel(const TnArgs 
         float* raw = reinterpret_cast<float*>(smem + GS * stage_bytes + TW_EPI_BYTES);    // 2 x [64][k1] floats
         float4 xa[2][4];
         float xs[2];
+        int32_t rid_nx[2];                                          // row ids of the stage whose loads are issued next (loaded a stage
+                                                                    // earlier: an issue is never two dependent latencies)
+        auto fetch_rids = [&](int s) {
+#pragma unroll
+            for (int b = 0; b < 2; ++b) rid_nx[b] = s < nstages ? row_id(r_beg + (int64_t)s * TW_ROWS + 32 * b + lr) : -1;
+        };
         auto issue = [&](int s) {
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
-                const int32_t r = s < nstages ? row_id(r_beg + (int64_t)s * TW_ROWS + 32 * b + lr) : -1;
+                const int32_t r = rid_nx[b];
                 xs[b] = (t.a_scale && r >= 0) ? __ldg(t.a_scale + r) : 1.0f;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -101,7 +107,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1) gemm_tn_wt_kernel(const TnArgs 
                     if (r >= 0 && cj + 8 * i < a4) xa[b][i] = __ldg(reinterpret_cast<const float4*>(t.a + (int64_t)r * t.lda) + cj + 8 * i);
                 }
             }
+            fetch_rids(s + 1);
         };
+        fetch_rids(0);
         issue(0);
         for (int s = 0; s < nstages; ++s) {
             const uint32_t ta = s & 1;
@@ -154,9 +162,13 @@ __global__ void __launch_bounds__(TW_THREADS, 1) gemm_tn_wt_kernel(const TnArgs 
         const int g4 = t.n2 >> 2;
         const uint32_t row_off = (uint32_t)((rr >> 2) * 512 + (rr & 3) * 128 + ((((cj >> 1) ^ (rr & 3)) << 5) | ((cj & 1) << 4)));
         uint32_t stage = 0, phase = 0;
+        int32_t nrid0 = row_id(r_beg + rr), nrid1 = row_id(r_beg + rr + 32);       // row ids one stage ahead of the loads
         for (int s = 0; s < nstages; ++s) {
-            const int64_t i0 = r_beg + (int64_t)s * TW_ROWS + rr;
-            const int32_t rid0 = row_id(i0), rid1 = row_id(i0 + 32);
+            const int32_t rid0 = nrid0, rid1 = nrid1;
+            {
+                const int64_t i1 = r_beg + (int64_t)(s + 1) * TW_ROWS + rr;
+                nrid0 = row_id(i1); nrid1 = row_id(i1 + 32);
+            }
             float4 x[2][4];
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
