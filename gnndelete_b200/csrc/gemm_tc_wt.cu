@@ -23,6 +23,8 @@
 //
 // Covers the epilogues of the Del-training epoch (row scale, ReLU prologue, ReLU bit mask out, gate bits in); bias,
 // ReLU epilogue and fp32 gates stay on gemm_tc.cu (rows_wt_supported()).
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace gd {
@@ -36,15 +38,16 @@ constexpr int WT_THREADS = (WT_MMA_WARP + 1) * 32;
 constexpr int WT_MAX_STAGES = 6;
 constexpr int WT_ATOM = 16384;                 // one k-atom of a stage: [64 rows hi | 64 rows lo] x 128 B
 constexpr int WT_EPI_BYTES = WT_EPI_WARPS * 32 * 32 * 4;      // per warp: 32 rows x 32 features transpose tile
-constexpr int WT_PREFETCH = 2;                 // tiles of row loads in flight per producer thread (registers)
+// tiles of row loads in flight per producer thread: 8 float4 registers = 2 tiles at K = 128, 4 tiles at K <= 64
 constexpr uint32_t WT_COL_D = 256;             // TMEM: W_hi | W_lo in columns [0, 2k), accumulators 2 x (main 64 | corr 64) from 256
 constexpr int WT_TMEM_COLS = 512;
 
-template <bool SCALE, bool MASK_OUT, bool GATE_BITS>
+template <bool SCALE, bool MASK_OUT, bool GATE_BITS, int KCH>
 __global__ void __launch_bounds__(WT_THREADS, 1) gemm_rows_wt_kernel(const Args g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // by offset: keeps the shared address space
-    const int kchunks = g.k / KC;                                   // k-atoms (32 tf32 = one 128-byte swizzle row)
+    constexpr int kchunks = KCH;                                    // k-atoms (32 tf32 = one 128-byte swizzle row), g.k == 32 KCH
+    constexpr int WT_PREFETCH = KCH <= 2 ? 4 : 2;
     const int stage_bytes = kchunks * WT_ATOM;
     const int STAGES = g.stages;
     float* epi_buf = reinterpret_cast<float*>(smem + STAGES * stage_bytes);
@@ -123,17 +126,17 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gemm_rows_wt_kernel(const Args 
             const int64_t i = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * WT_ROWS + r0;
             return i < g.m ? (g.rows ? __ldg(g.rows + i) : (int32_t)i) : -1;
         };
-        float4 buf[WT_PREFETCH][4];
+        float4 buf[WT_PREFETCH][KCH];
         float rsc[WT_PREFETCH];                                       // row scale: applied to the INPUT row (s (x . W) = (s x) . W), so the
                                                                       // transposed accumulator needs no per-row factor in the epilogue
         int32_t rid_pf = row_of(WT_PREFETCH);                         // row id of the tile whose loads are issued next
-        auto issue = [&](float4 (&b)[4], float& sc, int32_t rid) {
+        auto issue = [&](float4 (&b)[KCH], float& sc, int32_t rid) {
             sc = 1.0f;
             if (SCALE && rid >= 0) sc = __ldg(g.out_scale + rid);
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
+            for (int p = 0; p < KCH; ++p) {
                 b[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p < kchunks && rid >= 0) b[p] = __ldg(reinterpret_cast<const float4*>(g.a + (int64_t)rid * g.lda + p * KC) + j);
+                if (rid >= 0) b[p] = __ldg(reinterpret_cast<const float4*>(g.a + (int64_t)rid * g.lda + p * KC) + j);
             }
         };
         auto l2_prefetch = [&](int32_t rid) {
@@ -151,8 +154,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gemm_rows_wt_kernel(const Args 
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = smem + stage * stage_bytes;
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        if (p < kchunks) {
+                    for (int p = 0; p < KCH; ++p) {
+                        {
                             float4 x = buf[d][p];
                             if (g.relu_in) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
                             if (SCALE) { const float sc = rsc[d]; x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc; }
@@ -320,15 +323,25 @@ int launch_rows_wt(const Args& g_in, cudaStream_t stream) {
         return GD_OK;
     };
     const int v = (g.out_scale ? 1 : 0) | (g.relu_mask_out ? 2 : 0) | (g.gate_bits ? 4 : 0);
+    auto by_k = [&](auto sc, auto mk, auto gt) -> int {
+        constexpr bool S = decltype(sc)::value, M = decltype(mk)::value, G = decltype(gt)::value;
+        switch (g.k / KC) {
+            case 1: return launch(gemm_rows_wt_kernel<S, M, G, 1>);
+            case 2: return launch(gemm_rows_wt_kernel<S, M, G, 2>);
+            case 3: return launch(gemm_rows_wt_kernel<S, M, G, 3>);
+            default: return launch(gemm_rows_wt_kernel<S, M, G, 4>);
+        }
+    };
+    using T = std::true_type; using F = std::false_type;
     switch (v) {
-        case 0: return launch(gemm_rows_wt_kernel<false, false, false>);
-        case 1: return launch(gemm_rows_wt_kernel<true, false, false>);
-        case 2: return launch(gemm_rows_wt_kernel<false, true, false>);
-        case 3: return launch(gemm_rows_wt_kernel<true, true, false>);
-        case 4: return launch(gemm_rows_wt_kernel<false, false, true>);
-        case 5: return launch(gemm_rows_wt_kernel<true, false, true>);
-        case 6: return launch(gemm_rows_wt_kernel<false, true, true>);
-        default: return launch(gemm_rows_wt_kernel<true, true, true>);
+        case 0: return by_k(F{}, F{}, F{});
+        case 1: return by_k(T{}, F{}, F{});
+        case 2: return by_k(F{}, T{}, F{});
+        case 3: return by_k(T{}, T{}, F{});
+        case 4: return by_k(F{}, F{}, T{});
+        case 5: return by_k(T{}, F{}, T{});
+        case 6: return by_k(F{}, T{}, T{});
+        default: return by_k(T{}, T{}, T{});
     }
 }
 
