@@ -217,7 +217,7 @@ def test_gemm_rows(lib, m, k, n, nk):
 
 @pytest.mark.parametrize('kernel', ['wt', 'ring'])
 @pytest.mark.parametrize('m,k,n,nk', [(40001, 128, 128, True), (30000, 128, 64, True), (20011, 64, 64, False), (25000, 64, 128, False),
-                                      (130, 32, 96, True), (63, 128, 128, False)])
+                                      (130, 32, 96, True), (5000, 96, 64, True), (63, 128, 128, False)])
 def test_gemm_rows_epoch_epilogues(lib, m, k, n, nk, kernel, monkeypatch):
     """The epilogues of the Del-training epoch on both tcgen05 row GEMMs (weights in tensor memory, gemm_tc_wt.cu, and
     the shared-memory ring, gemm_tc.cu): row scale, ReLU prologue, bit-packed ReLU mask out, gate bits in, gathered rows;
