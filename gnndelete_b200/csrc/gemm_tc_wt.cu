@@ -21,8 +21,8 @@
 // ReLU mask of a row is a __ballot_sync over the 32 features a warp holds; the row scale is applied to the INPUT row by
 // the producers (s (x . W) = (s x) . W).
 //
-// Covers the epilogues of the Del-training epoch (row scale, ReLU prologue, ReLU bit mask out, gate bits in); bias,
-// ReLU epilogue and fp32 gates stay on gemm_tc.cu (rows_wt_supported()).
+// Covers row scale, ReLU prologue / epilogue, bias, ReLU bit mask out, gate bits in; fp32 gate rows and a bias combined
+// with a row scale stay on gemm_tc.cu (rows_wt_supported()).
 #include <type_traits>
 
 #include "tc_common.cuh"
@@ -231,6 +231,11 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gemm_rows_wt_kernel(const Args 
             }
         };
         load_meta(blockIdx.x);
+        // bias (per output feature = per lane) and the ReLU epilogue are run-time options: one add / one max per element.  With a
+        // row scale the bias is added AFTER scaling in the contract (out = scale * (a . B) + bias is NOT what gemm_tc.cu computes:
+        // it computes scale * (a . B + bias)), so a bias together with a row scale stays on gemm_tc.cu (rows_wt_supported).
+        const float bias_f = (g.bias && active && q * 32 + lane < g.n) ? __ldg(g.bias + q * 32 + lane) : 0.f;
+        const bool relu_out = g.relu_out != 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -259,7 +264,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gemm_rows_wt_kernel(const Args 
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
                         const int jj = 16 * c + e;
-                        float x = __uint_as_float(pm[e]) + __uint_as_float(pc[e]);
+                        float x = __uint_as_float(pm[e]) + __uint_as_float(pc[e]) + bias_f;
+                        if (relu_out) x = fmaxf(x, 0.f);
                         if (GATE_BITS) { if (!((colbits >> jj) & 1u)) x = 0.f; }
                         if (MASK_OUT) {
                             const uint32_t v = __ballot_sync(0xffffffffu, x > 0.f);    // the 32 features of row jj = one mask word
@@ -305,7 +311,8 @@ static int wt_stages(int k) {
 
 bool rows_wt_supported(const Args& g) {
     if (g.k <= 0 || g.k > 128 || g.k % KC != 0 || g.n <= 0 || g.n > 128 || g.n % 32 != 0) return false;
-    if (g.bias || g.gate || g.relu_out) return false;                  // epilogues outside the Del-training epoch: gemm_tc.cu
+    if (g.gate) return false;                                          // fp32 gate rows: gemm_tc.cu
+    if (g.bias && g.out_scale) return false;                           // bias is added BEFORE the row scale there; here the scale sits on the input row
     if (g.lda % 4 != 0 || g.ldo % 4 != 0) return false;
     return wt_stages(g.k) >= 2;
 }

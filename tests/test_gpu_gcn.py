@@ -263,6 +263,15 @@ def test_gemm_rows_epoch_epilogues(lib, m, k, n, nk, kernel, monkeypatch):
     got4 = ((bits4.unsqueeze(-1) >> torch.arange(32, device=DEV)) & 1).reshape(m, n).bool().cpu()
     sure4 = full.abs() > 1e-4 * full.abs().max()
     assert torch.equal(got4[sure4], (full > 0)[sure4])
+    # (5) bias + ReLU epilogue (the conv layers of GIN / original-model training), all rows and gathered rows
+    bias = torch.randn(n, generator=g)
+    out5 = ops.gemm_rows(ad, bd, nk, bias=bias.to(DEV), relu_out=True)
+    U.assert_close(out5, (full + bias.double()).clamp(min=0), what='bias + relu_out')
+    out6 = torch.full((m, n), 2.0, device=DEV)
+    ops.gemm_rows(ad, bd, nk, out=out6, rows=rows.to(DEV).int(), bias=bias.to(DEV))
+    ref6 = torch.full((m, n), 2.0, dtype=torch.float64)
+    ref6[rows] = prod + bias.double()
+    U.assert_close(out6, ref6, what='gathered rows + bias')
 
 
 @pytest.mark.parametrize('m,k1,n2', [(5000, 128, 128), (777, 64, 64), (300, 100, 30)])
