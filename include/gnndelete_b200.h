@@ -299,7 +299,10 @@ int gd_gemm_rows(const float* a, int64_t lda, const int32_t* rows, int64_t m, in
 /* Same contract as gd_gemm_rows on the tensor cores: tcgen05.mma (kind::tf32) with TMEM
  * accumulators and a 3xTF32 operand split, so results match the fp32 path to ~1e-6 relative.
  * Supported when gd_gemm_rows_tc_supported() returns 1 (k <= ~128, n in {32, 64, 96, 128},
- * 16-byte aligned operands); B stays resident in shared memory, one persistent CTA per SM.
+ * 16-byte aligned operands); one persistent CTA per SM.  For k a multiple of 32 (no fp32 gate, no bias combined with a row
+ * scale) the product is computed transposed with B (hi and lo) resident in TENSOR MEMORY as the A operand and whole 64-row
+ * tiles of `a` streaming through shared memory (csrc/gemm_tc_wt.cu); otherwise B stays resident in shared memory
+ * (csrc/gemm_tc.cu; GD_GEMM_ROWS=ring forces it).
  * Two optional bit-packed ReLU helpers ([row][n/32] words, bit c%32 of word c/32):
  *   relu_mask_out : written with (out[r,c] > 0) — the forward records ReLU's mask for free;
  *   gate_bits     : out[r,c] is kept where the bit is set, else 0 — the backward's ReLU'
@@ -326,7 +329,10 @@ int gd_gemm_tn_rows(const float* a, int64_t lda, const float* g, int64_t ldg, co
                     int64_t m, int32_t k1, int32_t n2, int32_t relu_a, const float* a_scale, float* c,
                     void* workspace, size_t workspace_bytes, gd_stream_t stream);
 
-/* gd_gemm_tn_rows on the tensor cores (tcgen05, 3xTF32): rows are transposed while they are
+/* gd_gemm_tn_rows on the tensor cores (tcgen05, 3xTF32).  Default (csrc/gemm_tn_wt.cu): the rows of `a` go through a raw
+ * shared tile into TENSOR MEMORY as the A operand [k1 lanes x 64 rows], only `g` is staged in operand form, partial sums
+ * are added group after group with vector reductions by one thread per element (deterministic).  GD_GEMM_TN=ring
+ * (csrc/gemm_tc.cu): rows are transposed while they are
  * staged, every CTA accumulates a contiguous range of rows in TMEM and flushes to its own
  * partial every 256 rows, a second kernel adds the partials in order (deterministic). */
 int gd_gemm_tn_rows_tc_supported(int32_t k1, int32_t n2, int64_t lda, int64_t ldg);
