@@ -242,14 +242,6 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gemm_rows_wt_kernel(const Args 
             const int32_t rid = rid_n;
             const uint32_t gw = gw_n;
             load_meta(tile + gridDim.x);
-            uint32_t colbits = 0xffffffffu;                           // bit jj: gate of (row jj, this lane's feature)
-            if (GATE_BITS && active) {
-#pragma unroll
-                for (int b = 0; b < 32; ++b) {
-                    const uint32_t v = __ballot_sync(0xffffffffu, (gw >> b) & 1u);
-                    if (lane == b) colbits = v;
-                }
-            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             if (active) {
@@ -266,7 +258,6 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gemm_rows_wt_kernel(const Args 
                         const int jj = 16 * c + e;
                         float x = __uint_as_float(pm[e]) + __uint_as_float(pc[e]) + bias_f;
                         if (relu_out) x = fmaxf(x, 0.f);
-                        if (GATE_BITS) { if (!((colbits >> jj) & 1u)) x = 0.f; }
                         if (MASK_OUT) {
                             const uint32_t v = __ballot_sync(0xffffffffu, x > 0.f);    // the 32 features of row jj = one mask word
                             if (lane == jj) posword = v;
@@ -278,12 +269,22 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gemm_rows_wt_kernel(const Args 
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                if (MASK_OUT) { if (rid >= 0) g.relu_mask_out[(int64_t)rid * nw + q] = posword; }
+                // gate bits are applied after the transposition (a lane then holds four features of ONE row: the row's gate word
+                // comes with one shuffle; transposing the 32 x 32 bit block with ballots cost 10 us per 200 k rows); the mask word
+                // of a gated row is the AND of both
+                if (MASK_OUT) { if (rid >= 0) g.relu_mask_out[(int64_t)rid * nw + q] = GATE_BITS ? (posword & gw) : posword; }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int jj = (lane >> 3) + 4 * i;
                     float4 o = lds128(tbuf + jj * 32 + (lane & 7) * 4);
                     const int32_t rr = __shfl_sync(0xffffffffu, rid, jj);
+                    if (GATE_BITS) {
+                        const uint32_t nib = __shfl_sync(0xffffffffu, gw, jj) >> ((lane & 7) * 4);
+                        if (!(nib & 1u)) o.x = 0.f;
+                        if (!(nib & 2u)) o.y = 0.f;
+                        if (!(nib & 4u)) o.z = 0.f;
+                        if (!(nib & 8u)) o.w = 0.f;
+                    }
                     if (rr >= 0) *reinterpret_cast<float4*>(g.out + (int64_t)rr * g.ldo + q * 32 + (lane & 7) * 4) = o;
                 }
                 __syncwarp();
