@@ -255,6 +255,11 @@ def test_gemm_rows_epoch_epilogues(lib, m, k, n, nk, kernel, monkeypatch):
     ref3 = torch.full((m, n), 3.0, dtype=torch.float64)
     ref3[rows] = torch.where(gate[rows], prod * s.double()[rows].view(-1, 1), torch.zeros_like(prod))
     U.assert_close(out3, ref3, what='gate bits + scale')
+    # ... and the ReLU mask of a gated result: bit = gate bit AND (value > 0)
+    bits3 = torch.zeros(m, n // 32, dtype=torch.int32, device=DEV)
+    ops.gemm_rows(ad, bd, nk, out=out3, rows=rows.to(DEV).int(), gate_bits=gbits, relu_mask_out=bits3)
+    got3 = ((bits3[rows.to(DEV)].unsqueeze(-1) >> torch.arange(32, device=DEV)) & 1).reshape(rows.numel(), n).bool().cpu()
+    assert torch.equal(got3[sure], (gate[rows] & (prod > 0))[sure]), 'mask bits of a gated result'
     # (4) mask bits with a row scale (sign taken after scaling, scale > 0)
     bits4 = torch.zeros(m, n // 32, dtype=torch.int32, device=DEV)
     out4 = ops.gemm_rows(ad, bd, nk, out_scale=sd, relu_mask_out=bits4)
