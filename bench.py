@@ -209,9 +209,13 @@ def time_kernels(eng, data, steps):
         timed('gemm_da2', lambda: ops.gemm_rows(eng.dz, w2, True, out=eng.da2, rows=eng.rows2, out_scale=p.dinv))
         ops.copy_rows(eng.dz, eng.da2, eng.comp2, row_scale=p.dinv)
         timed('spmm_bwd_f64', lambda: ops.spmm(p.bwd, eng.da2, out=eng.dh1))
-        timed('gemm_dx1', lambda: ops.gemm_rows(eng.dh1, W2, False, out=eng.dx1, rows=eng.rows1, out_scale=p.dinv,
-                                                gate=None if eng.bitmask else eng.x1, gate_bits=eng.x1_bits))
-        timed('gemm_dw1', lambda: ops.gemm_tn_rows(eng.a1, eng.dx1, rows=eng.rows1, out=eng.params[0].grad))
+        if eng.fused_dxdw:      # dX1 chained into dW_del1 through tensor memory: one kernel (+ the reduction of the partials)
+            timed('gemm_dxdw1', lambda: ops.gemm_dxdw(eng.dh1, W2, False, eng.a1, rows=eng.rows1, in_scale=p.dinv,
+                                                      gate_bits=eng.x1_bits, out=eng.params[0].grad))
+        else:
+            timed('gemm_dx1', lambda: ops.gemm_rows(eng.dh1, W2, False, out=eng.dx1, rows=eng.rows1, out_scale=p.dinv,
+                                                    gate=None if eng.bitmask else eng.x1, gate_bits=eng.x1_bits))
+            timed('gemm_dw1', lambda: ops.gemm_tn_rows(eng.a1, eng.dx1, rows=eng.rows1, out=eng.params[0].grad))
     # deletion-mask construction (setup path, A9): the 2-hop + 1-hop k_hop masks of delete_gnn.py:128-151 on the DIRECTED
     # edge list (rebuilt here from the symmetrised one); each call ends with a host read of its status word, so the
     # bracket includes one launch gap
@@ -779,11 +783,15 @@ def main():
         'spmm_bwd_f64': spmm_algo_bytes(n, nnz, out),
         'gemm_xw1': gemm_algo_bytes(n, shape.in_dim, hid, False), 'gemm_xw2': gemm_algo_bytes(n, hid, out, False),
         'gemm_del1': gemm_algo_bytes(n1, hid, hid, True), 'gemm_del2': gemm_algo_bytes(n2, out, out, True),
-        'gemm_da2': gemm_algo_bytes(n2, out, out, True), 'gemm_dx1': gemm_algo_bytes(n1, out, hid, True),
-        'gemm_dw1': gemm_algo_bytes(n1, hid, hid, True), 'gemm_dw2': gemm_algo_bytes(n2, out, out, True),
+        'gemm_da2': gemm_algo_bytes(n2, out, out, True), 'gemm_dw2': gemm_algo_bytes(n2, out, out, True),
         'loss_fwd_bwd': loss_algo_bytes(n_df, n_ni, n, out),
         'khop_masks_2hop_1hop': khop_algo_bytes(shape.num_edges, n),
     }
+    if eng_k.fused_dxdw:    # rows of dH1 [out] and a1 [hid] read once, row id + scale + gate bits per row; dX1 never touches HBM
+        algo['gemm_dxdw1'] = n1 * (4 * out + 4 * hid + 8 + hid // 8) + 4 * out * hid + 4 * hid * hid
+    else:
+        algo['gemm_dx1'] = gemm_algo_bytes(n1, out, hid, True)
+        algo['gemm_dw1'] = gemm_algo_bytes(n1, hid, hid, True)
     kernels = {k: {'ms': kt[k], 'algo_bytes': algo[k], 'gbs': algo[k] / (kt[k] * 1e-3) / 1e9,
                    'frac': algo[k] / (kt[k] * 1e-3) / 1e9 / peak} for k in algo}
     agg = ['spmm_l1_f128', 'spmm_l2_f64', 'spmm_bwd_f64']

@@ -82,6 +82,8 @@ SIGNATURES = {
     'gd_gemm_tn_rows_tc_supported': (C.c_int, [_i32, _i32, _i64, _i64]),
     'gd_gemm_tn_tc_workspace_bytes': (_sz, [_i32, _i32]),
     'gd_gemm_tn_rows_tc': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    'gd_gemm_dxdw_tc_supported': (C.c_int, [_i32, _i32, _i32, _i64, _i64]),
+    'gd_gemm_dxdw_tc': (C.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _sz, _vp]),
     'gd_copy_rows': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     'gd_copy_rows_scaled': (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _i64, _vp]),
     'gd_relu_fwd': (C.c_int, [_vp, _i64, _vp, _vp]),

@@ -671,8 +671,9 @@ extern "C" int gd_gemm_rows_tc_batch(const float* a, int64_t lda, int64_t m, int
 
 // out[i] = sum_p partial[p][i] in a fixed order: warp w of a block adds the partials p = w, w + 8, ... for 32
 // consecutive elements (coalesced, all loads independent), then the 8 warp sums are added in warp order.
+// tr_k1 > 0: the partials are [tr_n][tr_k1] (gemm_dxdw_wt.cu) and `out` is [tr_k1][tr_n].
 __global__ void __launch_bounds__(256) tn_reduce_kernel(const float* __restrict__ partial, int nparts, int64_t count,
-                                                        float* __restrict__ out) {
+                                                        float* __restrict__ out, int tr_k1, int tr_n) {
     __shared__ float red[8][32];
     gd::pdl_wait();
     gd::pdl_trigger();
@@ -689,9 +690,17 @@ __global__ void __launch_bounds__(256) tn_reduce_kernel(const float* __restrict_
         float r = red[0][lane];
 #pragma unroll
         for (int k = 1; k < 8; ++k) r += red[k][lane];
-        out[i] = r;
+        out[tr_k1 > 0 ? (i % tr_k1) * tr_n + i / tr_k1 : i] = r;
     }
 }
+
+namespace gd { namespace tc {
+int launch_tn_reduce(const float* partial, int nparts, int64_t count, float* out, cudaStream_t stream, int tr_k1, int tr_n) {
+    GD_CUDA(launch_pdl(tn_reduce_kernel, (unsigned)ceil_div<int64_t>(count, 32), 256, 0, stream, partial, nparts, count, out, tr_k1, tr_n));
+    GD_LAUNCH_CHECK();
+    return GD_OK;
+}
+}}  // namespace gd::tc
 
 extern "C" int gd_gemm_tn_rows_tc_supported(int32_t k1, int32_t n2, int64_t lda, int64_t ldg) {
     if (k1 <= 0 || k1 > 128 || k1 % 4 != 0 || n2 <= 0 || n2 > 128 || n2 % 32 != 0) return 0;
@@ -726,7 +735,7 @@ extern "C" int gd_gemm_tn_rows_tc(const float* a, int64_t lda, const float* g, i
             const int rc = tc::launch_tn_wt(t, stream, &nparts);
             if (rc != GD_OK) return rc;
             const int64_t cnt = (int64_t)k1 * n2;
-            GD_CUDA(launch_pdl(tn_reduce_kernel, (unsigned)ceil_div<int64_t>(cnt, 32), 256, 0, stream, (const float*)t.partial, nparts, cnt, c));
+            GD_CUDA(launch_pdl(tn_reduce_kernel, (unsigned)ceil_div<int64_t>(cnt, 32), 256, 0, stream, (const float*)t.partial, nparts, cnt, c, 0, 0));
             GD_LAUNCH_CHECK();
             return GD_OK;
         }
@@ -736,7 +745,7 @@ extern "C" int gd_gemm_tn_rows_tc(const float* a, int64_t lda, const float* g, i
     GD_CUDA(launch_pdl(tc::gemm_tn_tc_kernel, grid, tc::NUM_THREADS, smem, stream, t));
     GD_LAUNCH_CHECK();
     const int64_t count = (int64_t)k1 * n2;
-    GD_CUDA(launch_pdl(tn_reduce_kernel, (unsigned)ceil_div<int64_t>(count, 32), 256, 0, stream, (const float*)t.partial, grid, count, c));
+    GD_CUDA(launch_pdl(tn_reduce_kernel, (unsigned)ceil_div<int64_t>(count, 32), 256, 0, stream, (const float*)t.partial, grid, count, c, 0, 0));
     GD_LAUNCH_CHECK();
     return GD_OK;
 }

@@ -209,6 +209,9 @@ struct TnArgs {
 bool tn_wt_supported(const TnArgs& t);
 int launch_tn_wt(const TnArgs& t, cudaStream_t stream, int* nparts);     // fills t.partial [nparts][k1][n2]
 
+// out = sum of the partials in CTA order; tr_k1 > 0: partials are [tr_n][tr_k1], out is [tr_k1][tr_n]
+int launch_tn_reduce(const float* partial, int nparts, int64_t count, float* out, cudaStream_t stream, int tr_k1 = 0, int tr_n = 0);
+
 bool rows_wt_supported(const Args& g);
 int launch_rows_wt(const Args& g, cudaStream_t stream);
 

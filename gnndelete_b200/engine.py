@@ -70,11 +70,14 @@ class GCNDeleteEngine:
         self.dz = torch.empty(n, out, **f32)
         self.da2 = torch.empty(n, out, **f32)
         self.dh1 = torch.empty(n, out, **f32)
-        self.dx1 = torch.zeros(n, hid, **f32)       # only the S1 rows are ever written / read
         # ReLU mask of x1 on the S1 rows as bits (written by the Del1 GEMM, read by the dX1 GEMM)
         self.bitmask = ops.gemm_tc_available(hid, hid, hid, hid) and ops.gemm_tc_available(out, hid, out, hid) \
             and hid % 32 == 0
         self.x1_bits = torch.zeros(n, hid // 32, dtype=torch.int32, device=dev) if self.bitmask else None
+        # dX1 chained into dW_del1 through tensor memory (gemm_dxdw_wt.cu); GD_FUSED_DXDW=0 keeps the two kernels
+        self.fused_dxdw = self.bitmask and os.environ.get('GD_FUSED_DXDW', '1') != '0' \
+            and ops.gemm_dxdw_supported(self.dh1, torch.empty(out, hid, **f32), False, self.a1)
+        self.dx1 = None if self.fused_dxdw else torch.zeros(n, hid, **f32)       # only the S1 rows are ever written / read
         self.hoist = bool(hoist_layer1)
         self._layer1_done = False
         self.params = [model.deletion1.deletion_weight, model.deletion2.deletion_weight]
@@ -137,7 +140,12 @@ class GCNDeleteEngine:
         self._del_rows(self.dz, self.da2, self.comp2, lambda: ops.gemm_rows(                  # D^-1/2 (dz[S2] @ W2^T)
             self.dz, w2, True, out=self.da2, rows=self.rows2, out_scale=p.dinv), row_scale=p.dinv)
         ops.spmm(p.bwd, self.da2, out=self.dh1)                                    # A^T (D^-1/2 dA2)
-        ops.gemm_rows(self.dh1, m.conv2.lin.weight.detach(), False, out=self.dx1, rows=self.rows1,
+        w_lin2 = m.conv2.lin.weight.detach()
+        if self.fused_dxdw:
+            # dX1 = ReLU' (D^-1/2 dH1) W_2 on S1 chained into dW_del1 = a1[S1]^T dX1 through tensor memory
+            ops.gemm_dxdw(self.dh1, w_lin2, False, self.a1, rows=self.rows1, in_scale=p.dinv, gate_bits=self.x1_bits, out=g1)
+            return
+        ops.gemm_rows(self.dh1, w_lin2, False, out=self.dx1, rows=self.rows1,
                       out_scale=p.dinv, gate=None if self.bitmask else self.x1,
                       gate_bits=self.x1_bits)                                      # ReLU' (D^-1/2 dH1) W_2 on S1
         ops.gemm_tn_rows(self.a1, self.dx1, rows=self.rows1, out=g1)               # dW_del1
@@ -287,7 +295,11 @@ class GATDeleteEngine(GCNDeleteEngine):
         L.call('gd_gat_bwd_src', p.bwd.ref, L.ptr(self.alpha_t), L.ptr(self.dpre_t), L.ptr(self.da2), self.da2.stride(0), out,
                L.ptr(a['src']), L.ptr(a['dst']), L.ptr(self.da_dst), L.ptr(self.dh1), self.dh1.stride(0), L.ptr(self.da_src),
                L.ptr(p.bwd.gat_scratch(out)), L.stream())
-        ops.gemm_rows(self.dh1, c2.lin_src.weight.detach(), False, out=self.dx1, rows=self.rows1,
+        w_src2 = c2.lin_src.weight.detach()
+        if self.fused_dxdw:
+            ops.gemm_dxdw(self.dh1, w_src2, False, self.a1, rows=self.rows1, gate_bits=self.x1_bits, out=g1)
+            return
+        ops.gemm_rows(self.dh1, w_src2, False, out=self.dx1, rows=self.rows1,
                       gate=None if self.bitmask else self.x1, gate_bits=self.x1_bits)          # ReLU' (dH1 W_2) on S1
         ops.gemm_tn_rows(self.a1, self.dx1, rows=self.rows1, out=g1)               # dW_del1
 

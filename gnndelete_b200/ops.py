@@ -170,6 +170,35 @@ def gemm_tn_rows(a, g, rows=None, relu_a=False, a_scale=None, out=None):
     return out
 
 
+def gemm_dxdw_supported(x, b, b_is_nk, a):
+    """Whether :func:`gemm_dxdw` (the chained input-gradient / weight-gradient kernel) takes these operands."""
+    k = x.shape[1]
+    n = b.shape[0] if b_is_nk else b.shape[1]
+    return (GEMM_BACKEND != 'simt' and x.dtype == torch.float32 and a.dtype == torch.float32
+            and bool(L.load().gd_gemm_dxdw_tc_supported(k, n, a.shape[1], x.stride(0), a.stride(0))))
+
+
+def gemm_dxdw(x, b, b_is_nk, a, rows=None, in_scale=None, gate_bits=None, out=None):
+    """``out[k1,n] = sum_r a[r,:]^T (x) (gate[r,:] * ((in_scale[r] x[r,:]) @ B))`` over all rows or the ``rows`` list:
+    the DeletionLayer input gradient chained into its weight gradient through tensor memory (the [rows, n] gradient is
+    never written).  Same results as ``gemm_rows(..., out_scale, gate_bits)`` followed by ``gemm_tn_rows``."""
+    k = x.shape[1]
+    n = b.shape[0] if b_is_nk else b.shape[1]
+    k1 = a.shape[1]
+    m = x.shape[0] if rows is None else rows.numel()
+    if out is None:
+        out = torch.empty(k1, n, dtype=torch.float32, device=x.device)
+    nbytes = L.load().gd_gemm_tn_tc_workspace_bytes(k1, n)
+    key = (x.device, nbytes)
+    ws = _tn_ws.get(key)
+    if ws is None:
+        ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=x.device)
+        _tn_ws[key] = ws
+    L.call('gd_gemm_dxdw_tc', L.ptr(x), x.stride(0), L.ptr(_f32(b)), int(b_is_nk), k, n, L.ptr(in_scale), L.ptr(gate_bits),
+           L.ptr(a), a.stride(0), k1, L.ptr(rows), m, L.ptr(out), L.ptr(ws), nbytes, L.stream())
+    return out
+
+
 def copy_rows(src, dst, rows, row_scale=None):
     """``dst[rows] = src[rows]`` (``* row_scale[rows]`` when given)."""
     L.call('gd_copy_rows_scaled', L.ptr(src), src.stride(0), L.ptr(rows), rows.numel(), src.shape[1],

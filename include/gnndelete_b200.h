@@ -341,6 +341,18 @@ int gd_gemm_tn_rows_tc(const float* a, int64_t lda, const float* g, int64_t ldg,
                        int64_t m, int32_t k1, int32_t n2, int32_t relu_a, const float* a_scale, float* c,
                        void* workspace, size_t workspace_bytes, gd_stream_t stream);
 
+/* Input gradient of a gathered-row linear map chained into the weight gradient of the DeletionLayer in front of it
+ * (csrc/gemm_dxdw_wt.cu; autograd of framework/models/deletion.py:23-33 `torch.matmul(x[mask], deletion_weight)` under
+ * the ReLU and GCNConv.lin of framework/models/gcn.py:15-19):
+ *   dX[r, :n] = gate[r, :] (.) ((in_scale[r] x[r, :k]) . B),    c[k1, n] = sum_r a[r, :k1]^T (x) dX[r, :]
+ * over r in `rows` (or 0..m).  dX stays in tensor memory (the transposed accumulator of the first product is the A operand
+ * of the second); same results as gd_gemm_rows_tc + gd_gemm_tn_rows_tc.  k in {32, 64}; n, k1 multiples of 32, <= 128.
+ * gate_bits: [row][n / 32] bit masks (optional).  workspace: gd_gemm_tn_tc_workspace_bytes(k1, n). */
+int gd_gemm_dxdw_tc_supported(int32_t k, int32_t n, int32_t k1, int64_t ldx, int64_t lda);
+int gd_gemm_dxdw_tc(const float* x, int64_t ldx, const float* b, int32_t b_is_nk, int32_t k, int32_t n,
+                    const float* in_scale, const uint32_t* gate_bits, const float* a, int64_t lda, int32_t k1,
+                    const int32_t* rows, int64_t m, float* c, void* workspace, size_t workspace_bytes, gd_stream_t stream);
+
 /* dst[rows[i], :] = src[rows[i], :]  (the unmasked rows of DeletionLayer.forward's clone). */
 int gd_copy_rows(const float* src, int64_t lds, const int32_t* rows, int64_t m, int32_t feat,
                  float* dst, int64_t ldd, gd_stream_t stream);

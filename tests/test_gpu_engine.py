@@ -113,6 +113,34 @@ def test_engine_new_negatives_every_epoch(lib, static):
             U.assert_close(eng6.epoch().cpu(), g_, tol=1e-5, what='pipelined vs synchronous step (float reductions)')
 
 
+def test_engine_chained_dx_dw_kernel(lib, monkeypatch):
+    """GD_FUSED_DXDW=1: dX1 chained into dW_del1 through tensor memory -- same loss curve and weights as the oracle, and
+    the first-step gradient within fp32 rounding of the two-kernel engine's."""
+    from gnndelete_b200 import models as M
+    from gnndelete_b200.engine import GCNDeleteEngine
+    shape, raw, df, data, neg = U.make_case('cora', 0.05)
+    epochs = 10
+    om, zo, hist = _oracle_run(shape, data, neg, epochs, torch.float64)
+    init = U.oracle_model('gcn', shape, data, dtype=torch.float32)
+
+    def engine(flag):
+        monkeypatch.setenv('GD_FUSED_DXDW', flag)
+        m = M.GCNDelete(U.args_for(shape), data.sdf_node_1hop_mask, data.sdf_node_2hop_mask)
+        m.load_state_dict(init.state_dict())
+        m = m.to(DEV)
+        return m, GCNDeleteEngine(m, data.clone().to(DEV), neg.to(DEV), z_ori=zo.float().to(DEV))
+
+    m0, e0 = engine('0')
+    m1, e1 = engine('1')
+    assert e1.fused_dxdw and not e0.fused_dxdw
+    e0.forward_backward(); e1.forward_backward()
+    U.assert_close(e1.params[0].grad, e0.params[0].grad, tol=1e-5, what='dW_del1, chained vs two kernels')
+    e1.capture()
+    got = torch.stack([e1.epoch().clone() for _ in range(epochs)]).cpu().double()
+    U.assert_close(got, hist, tol=1e-4, what='loss curve')
+    U.assert_close(m1.deletion1.deletion_weight, om.deletion1.deletion_weight, tol=1e-4, what='W_del1 after training')
+
+
 def test_engine_first_step_tight(lib):
     """One epoch at the 1e-5 bar: losses and both Del gradients."""
     import __graft_entry__ as G

@@ -311,6 +311,37 @@ def test_gemm_tn_rows_both_tensor_core_kernels(lib, m, k1, n2, kernel, monkeypat
     assert torch.equal(ops.gemm_tn_rows(ad, gd_, rows=rd), ops.gemm_tn_rows(ad, gd_, rows=rd))
 
 
+@pytest.mark.parametrize('m,k,n,k1', [(60001, 64, 128, 128), (130000, 64, 128, 128), (9000, 32, 64, 96), (20000, 64, 96, 64),
+                                      (300, 64, 128, 128), (64, 32, 32, 32)])
+def test_gemm_dxdw_chained_kernel(lib, m, k, n, k1):
+    """Input gradient chained into the weight gradient through tensor memory (gemm_dxdw_wt.cu) vs fp64 and vs the two-kernel
+    path it replaces: gathered rows with row scale and gate bits, all rows without, several flush groups per CTA, ragged
+    last tiles, a single partial tile."""
+    from gnndelete_b200 import ops
+    g = torch.Generator().manual_seed(m + k + n + k1)
+    x, a = torch.randn(m, k, generator=g), torch.randn(m, k1, generator=g)
+    w = torch.randn(k, n, generator=g) / k ** 0.5
+    sc = torch.rand(m, generator=g) + 0.5
+    gate = torch.rand(m, n, generator=g) > 0.4
+    rows = torch.randperm(m, generator=g)[: (2 * m) // 3].sort()[0]
+    bits = torch.zeros(m, n // 32, dtype=torch.int64)
+    for j in range(n):
+        bits[:, j // 32] |= gate[:, j].long() << (j % 32)
+    bits = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).int()
+    xd, ad, wd, sd, bd, rd = x.to(DEV), a.to(DEV), w.to(DEV), sc.to(DEV), bits.to(DEV), rows.to(DEV).int()
+    assert ops.gemm_dxdw_supported(xd, wd, False, ad)
+    dx = ((x.double() * sc.double().view(-1, 1)) @ w.double()) * gate.double()
+    ref = a.double()[rows].t() @ dx[rows]
+    out = ops.gemm_dxdw(xd, wd, False, ad, rows=rd, in_scale=sd, gate_bits=bd)
+    U.assert_close(out, ref, what='gathered rows, scale, gate bits')
+    dxd = torch.zeros(m, n, device=DEV)
+    ops.gemm_rows(xd, wd, False, out=dxd, rows=rd, out_scale=sd, gate_bits=bd)
+    two = ops.gemm_tn_rows(ad, dxd, rows=rd)
+    assert (out - two).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    U.assert_close(ops.gemm_dxdw(xd, wd.t().contiguous(), True, ad), a.double().t() @ (x.double() @ w.double()), what='all rows, B as [n, k]')
+    assert torch.equal(ops.gemm_dxdw(xd, wd, False, ad, rows=rd, in_scale=sd, gate_bits=bd), out)      # deterministic
+
+
 def _load(gnn, om, shape, data, **kw):
     from gnndelete_b200 import models as M
     cls = {'gcn': M.GCNDelete, 'gin': M.GINDelete}[gnn]

@@ -47,3 +47,13 @@ for name, fn in tn.items():
         res[mode] = t(fn)
     print(f'{name:36s} wt {res["wt"]:7.1f} us   ring {res["ring"]:7.1f} us   x{res["ring"] / res["wt"]:.2f}', flush=True)
 os.environ.pop('GD_GEMM_TN', None)
+# chained dX1 -> dW_del1 (gemm_dxdw_wt.cu) vs the two kernels it replaces
+def two():
+    ops.gemm_rows(x64, w128_64, False, out=o128, rows=rows, out_scale=sc, gate_bits=bits)
+    ops.gemm_tn_rows(x128, o128, rows=rows, out=g128)
+bits.fill_(-1)
+g128b = torch.zeros(128, 128, device=dev)
+two(); ops.gemm_dxdw(x64, w128_64, False, x128, rows=rows, in_scale=sc, gate_bits=bits, out=g128b)
+torch.cuda.synchronize()
+print('chained vs two kernels: max rel diff', ((g128b - g128).abs().max() / g128.abs().max()).item(), flush=True)
+print(f'{"dx1 + dw1 two kernels":36s} {t(two):7.1f} us   chained {t(lambda: ops.gemm_dxdw(x64, w128_64, False, x128, rows=rows, in_scale=sc, gate_bits=bits, out=g128b)):7.1f} us', flush=True)
