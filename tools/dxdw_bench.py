@@ -1,4 +1,4 @@
-"""Chained dX / dW kernel (gemm_dxdw_wt.cu) at the Collab epoch shape: knob sweep (GD_DXDW_FLUSH / GD_DXDW_DIAG) or --once."""
+"""Chained dX / dW kernel (gemm_dxdw_wt.cu) at the Collab epoch shape: against the two kernels it replaces, or --once (for ncu)."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gnndelete_b200 import ops
@@ -30,6 +30,4 @@ def two():
     ops.gemm_rows(x, w, False, out=dx, rows=rows, out_scale=sc, gate_bits=bits)
     ops.gemm_tn_rows(a, dx, rows=rows, out=out)
 print(f'rows {rows.numel()}  two kernels {t(two):.1f} us', flush=True)
-for flush, diag in [(16, 0), (16, 15), (16, 15 + 64), (16, 15 + 48), (16, 15 + 48 + 64), (16, 15 + 128), (16, 255), (16, 64), (16, 48)]:
-    os.environ['GD_DXDW_FLUSH'] = str(flush); os.environ['GD_DXDW_DIAG'] = str(diag)
-    print(f'flush {flush:2d} diag {diag:2d}: {t(fn):7.1f} us', flush=True)
+print(f'chained {t(fn):.1f} us', flush=True)
